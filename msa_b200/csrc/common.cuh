@@ -1,0 +1,94 @@
+// Shared device/host helpers for the MMBert sm_100a kernels.
+// Everything in csrc/ is compiled with -gencode arch=compute_100a,code=sm_100a.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/mmbert_sm100.h"
+
+namespace mmb {
+
+// ------------------------------------------------------------------ error plumbing (host)
+void set_last_error(const char* fmt, ...);
+int check_launch(const char* what);  // returns MMB_OK / MMB_ECUDA after a kernel launch
+
+#define MMB_REQUIRE(cond, ...)                                   \
+    do {                                                         \
+        if (!(cond)) {                                           \
+            ::mmb::set_last_error(__VA_ARGS__);                  \
+            return MMB_EINVAL;                                   \
+        }                                                        \
+    } while (0)
+
+#define MMB_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t e__ = (call);                                                   \
+        if (e__ != cudaSuccess) {                                                   \
+            ::mmb::set_last_error("%s failed: %s", #call, cudaGetErrorString(e__)); \
+            return MMB_ECUDA;                                                       \
+        }                                                                           \
+    } while (0)
+
+int num_sms();
+
+// ------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+    return __bfloat1622float2(v);
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// Exact (erf) GELU, the activation HF BERT uses ("gelu" -> F.gelu default).
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// d/dx gelu(x) = Phi(x) + x * phi(x)
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+// Counter-based RNG for dropout: a 64-bit counter (stream, element index) mixed with the seed by a
+// splitmix64-style finaliser. Forward and backward regenerate identical masks from (seed, stream, idx);
+// nothing is stored.  Returns 32 uniform bits.
+__device__ __forceinline__ uint32_t rng_bits(uint64_t seed, uint32_t stream, uint64_t idx) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1) + ((uint64_t)stream << 40) * 0xD1B54A32D192ED03ull;
+    z ^= (uint64_t)stream * 0xA24BAED4963EE407ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (uint32_t)(z >> 16);
+}
+// keep-decision for dropout probability p: keep iff bits >= p * 2^32
+__device__ __forceinline__ bool rng_keep(uint64_t seed, uint32_t stream, uint64_t idx, uint32_t thresh) {
+    return rng_bits(seed, stream, idx) >= thresh;
+}
+#endif  // __CUDACC__
+
+inline uint32_t dropout_threshold(float p) {
+    if (p <= 0.f) return 0u;
+    double t = (double)p * 4294967296.0;
+    if (t >= 4294967295.0) return 0xFFFFFFFFu;
+    return (uint32_t)t;
+}
+
+}  // namespace mmb

@@ -1,0 +1,478 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a.
+//
+//   TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> smem ring (kStages) -> tcgen05.mma (cta_group::1, 128 x BN x 16)
+//   -> fp32 accumulators in TMEM (double buffered: 2 x BN columns) -> tcgen05.ld -> epilogue -> global.
+//
+// Warp roles (384 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer, warp 2 = TMEM
+// allocator, warp 3 idle, warps 4..11 = epilogue (warp w may only touch TMEM lanes 32*(w%4)..+31, so the
+// two epilogue warpgroups split the BN columns in halves).
+//
+// Replaces the cuBLASLt dispatches behind every nn.Linear of the reference path and their autograd
+// backward (see include/mmbert_sm100.h: mmb_gemm).  Both operands may be K-major (activations, weights)
+// or MN-major (dY^T / X^T read in place for wgrad), selected in the UMMA instruction descriptor.
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mmb {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int kGemmThreads = 384;
+constexpr int kEpiWarp0 = 4;
+constexpr int kNumEpiWarps = 8;
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int kStages = (BN == 256) ? 4 : 6;
+    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kTmemCols = 2 * BN;  // 512 or 256: power of two
+    static constexpr int kBarBytes = 256;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+};
+
+struct GemmParams {
+    void* C;
+    void* aux;
+    const float* bias;
+    int64_t ldc, ldaux;
+    int M, N, K;
+    int a_mn, b_mn;  // 1 = MN-major operand
+    int epilogue;
+    int split_k;
+    int kb_per_split;  // k-blocks (of BK) per split
+    int m_tiles, n_tiles, total_tiles;
+    float alpha;
+    // UMMA smem-descriptor parameters per operand (bytes): leading/stride byte offsets, per-UMMA_K advance
+    uint32_t a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step;
+};
+
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], int ncols_valid) {
+    if (ncols_valid >= 32) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+            u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+            u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+            u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+            d4[i] = u;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < ncols_valid) dst[i] = __float2bfloat16_rn(v[i]);
+    }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t smem_base = ptx::smem_u32(smem);
+    const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+    // barrier layout: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then the TMEM base slot
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 4));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            ptx::mbar_init(tfull_bar(a), 1);
+            ptx::mbar_init(tempty_bar(a), kNumEpiWarps);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<Cfg::kTmemCols>(ptx::smem_u32(tmem_slot));
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_kb = (p.K + BK - 1) / BK;
+    const int mn_tiles = p.m_tiles * p.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        // ================================ TMA producer ================================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const int ks = t / mn_tiles;
+            const int r = t - ks * mn_tiles;
+            const int n_blk = r / p.m_tiles;
+            const int m_blk = r - n_blk * p.m_tiles;
+            const int kb0 = ks * p.kb_per_split;
+            const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+                const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+                const uint32_t sb = sa + Cfg::kABytes;
+                ptx::mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                if (!p.a_mn) {
+                    ptx::tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < BM / 64; ++i)
+                        ptx::tma_load_2d(sa + i * 8192, &tmA, full_bar(stage), m_blk * BM + i * 64, kb * BK);
+                }
+                if (!p.b_mn) {
+                    ptx::tma_load_2d(sb, &tmB, full_bar(stage), kb * BK, n_blk * BN);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < BN / 64; ++i)
+                        ptx::tma_load_2d(sb + i * 8192, &tmB, full_bar(stage), n_blk * BN + i * 64, kb * BK);
+                }
+                if (++stage == Cfg::kStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================================ MMA issuer ================================
+        // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6), a=bf16 [7,10), b=bf16 [10,13),
+        // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        // K-major SW128: 8-row groups 1024 B apart (SBO); advance 32 B per UMMA_K inside the swizzled row.
+        // MN-major SW128: 64-element MN blocks 8192 B apart (LBO), 8-k groups 1024 B apart (SBO);
+        //                 advance two k-groups (2048 B) per UMMA_K.
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const int ks = t / mn_tiles;
+            const int kb0 = ks * p.kb_per_split;
+            const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+            ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BN;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                ptx::mbar_wait(full_bar(stage), phase);
+                ptx::tc_fence_after();
+                const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+                const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    const uint64_t da = ptx::umma_desc_sw128(sa + k * p.a_step, p.a_lbo, p.a_sbo);
+                    const uint64_t db = ptx::umma_desc_sw128(sb + k * p.b_step, p.b_lbo, p.b_sbo);
+                    ptx::umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                }
+                ptx::umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+                if (++stage == Cfg::kStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            ptx::umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ================================ epilogue ================================
+        const int ew = warp - kEpiWarp0;
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        const int half = ew >> 2;      // which half of the BN columns
+        constexpr int kColsPerWarp = BN / 2;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const int ks = t / mn_tiles;
+            const int r = t - ks * mn_tiles;
+            const int n_blk = r / p.m_tiles;
+            const int m_blk = r - n_blk * p.m_tiles;
+            ptx::mbar_wait(tfull_bar(acc), acc_phase);
+            ptx::tc_fence_after();
+            const int row = m_blk * BM + quarter * 32 + lane;
+            const bool row_ok = row < p.M;
+#pragma unroll 1
+            for (int c = 0; c < kColsPerWarp; c += 32) {
+                const int col0 = n_blk * BN + half * kColsPerWarp + c;
+                if (col0 >= p.N) break;  // warp-uniform
+                uint32_t raw[32];
+                const uint32_t taddr = tmem_base + acc * BN + half * kColsPerWarp + c + ((uint32_t)(quarter * 32) << 16);
+                ptx::tmem_ld_32x32(taddr, raw);
+                ptx::tmem_ld_wait();
+                const int nvalid = min(32, p.N - col0);
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
+                if (p.bias != nullptr && p.epilogue != MMB_EPI_ATOMIC_ADD_F32 && p.epilogue != MMB_EPI_DGELU_BF16) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (i < nvalid) v[i] += __ldg(p.bias + col0 + i);
+                }
+                if (row_ok) switch (p.epilogue) {
+                    case MMB_EPI_STORE_BF16: {
+                        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0, v, nvalid);
+                    } break;
+                    case MMB_EPI_GELU_BF16: {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
+                        if (p.aux != nullptr)
+                            store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.aux) + (size_t)row * p.ldaux + col0, v, nvalid);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+                        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0, v, nvalid);
+                    } break;
+                    case MMB_EPI_RELU_BF16: {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0, v, nvalid);
+                    } break;
+                    case MMB_EPI_STORE_F32: {
+                        float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+                        if (nvalid == 32) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (i < nvalid) dst[i] = v[i];
+                        }
+                    } break;
+                    case MMB_EPI_ATOMIC_ADD_F32: {
+                        float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+                        if (nvalid == 32) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                ptx::red_add_v4(dst + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (i < nvalid) atomicAdd(dst + i, v[i]);
+                        }
+                    } break;
+                    case MMB_EPI_DGELU_BF16: {
+                        const __nv_bfloat16* u = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ldaux + col0;
+                        if (nvalid == 32) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const uint4 q = __ldg(reinterpret_cast<const uint4*>(u) + i);
+                                const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z),
+                                             f3 = unpack_bf16x2(q.w);
+                                v[8 * i + 0] *= gelu_erf_grad(f0.x);
+                                v[8 * i + 1] *= gelu_erf_grad(f0.y);
+                                v[8 * i + 2] *= gelu_erf_grad(f1.x);
+                                v[8 * i + 3] *= gelu_erf_grad(f1.y);
+                                v[8 * i + 4] *= gelu_erf_grad(f2.x);
+                                v[8 * i + 5] *= gelu_erf_grad(f2.y);
+                                v[8 * i + 6] *= gelu_erf_grad(f3.x);
+                                v[8 * i + 7] *= gelu_erf_grad(f3.y);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (i < nvalid) v[i] *= gelu_erf_grad(__bfloat162float(u[i]));
+                        }
+                        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0, v, nvalid);
+                    } break;
+                    default: break;
+                }
+                __syncwarp();  // reconverge before the next .sync.aligned TMEM load
+            }
+            // all TMEM reads of this warp are complete (tcgen05.wait::ld) -> hand the accumulator back
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    // teardown
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    });
+    return fn;
+}
+
+struct TmapKey {
+    const void* ptr;
+    uint64_t d0, d1, ld;
+    uint32_t b0, b1;
+    bool operator==(const TmapKey& o) const {
+        return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && ld == o.ld && b0 == o.b0 && b1 == o.b1;
+    }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        uint64_t h = reinterpret_cast<uint64_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+        h ^= (k.d0 + 0x7F4A7C15ull) * 0xBF58476D1CE4E5B9ull;
+        h ^= (k.d1 + 0x94D049BBull) * 0x94D049BB133111EBull;
+        h ^= (k.ld << 17) ^ ((uint64_t)k.b0 << 40) ^ ((uint64_t)k.b1 << 52);
+        return (size_t)(h ^ (h >> 29));
+    }
+};
+
+// bf16 2-D tensor map, SWIZZLE_128B: dims {d0 (contiguous), d1 (rows)}, row stride ld elements, box {b0, b1}.
+// Cached: the encode is pure host work but the engine issues ~150 GEMMs per step over a fixed buffer set.
+static int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0,
+                          uint32_t b1) {
+    static std::mutex mu;
+    static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+    TmapKey key{ptr, d0, d1, ld, b0, b1};
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) {
+            *out = it->second;
+            return MMB_OK;
+        }
+    }
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) {
+        set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+        return MMB_ECUDA;
+    }
+    cuuint64_t dims[2] = {d0, d1};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {b0, b1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled failed (%d) ptr=%p dims=(%llu,%llu) ld=%llu box=(%u,%u)", (int)r, ptr,
+                       (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)ld, b0, b1);
+        return MMB_ECUDA;
+    }
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, *out);
+    return MMB_OK;
+}
+
+template <int BN>
+static int launch_gemm(const mmb_gemm_args* a, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    CUtensorMap tmA, tmB;
+    int rc;
+    if (a->a_major == MMB_MAJOR_K)
+        rc = make_tmap_bf16(&tmA, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BK, BM);
+    else
+        rc = make_tmap_bf16(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BK);
+    if (rc != MMB_OK) return rc;
+    if (a->b_major == MMB_MAJOR_K)
+        rc = make_tmap_bf16(&tmB, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BK, BN);
+    else
+        rc = make_tmap_bf16(&tmB, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BK);
+    if (rc != MMB_OK) return rc;
+
+    GemmParams p;
+    p.C = a->C;
+    p.aux = a->aux;
+    p.bias = a->bias;
+    p.ldc = a->ldc;
+    p.ldaux = a->ldaux;
+    p.M = a->M;
+    p.N = a->N;
+    p.K = a->K;
+    p.a_mn = a->a_major == MMB_MAJOR_MN;
+    p.b_mn = a->b_major == MMB_MAJOR_MN;
+    p.epilogue = a->epilogue;
+    const int total_kb = (a->K + BK - 1) / BK;
+    int split = a->split_k < 1 ? 1 : a->split_k;
+    if (split > total_kb) split = total_kb;
+    p.kb_per_split = (total_kb + split - 1) / split;
+    p.split_k = (total_kb + p.kb_per_split - 1) / p.kb_per_split;  // every split non-empty
+    p.m_tiles = (a->M + BM - 1) / BM;
+    p.n_tiles = (a->N + BN - 1) / BN;
+    p.total_tiles = p.m_tiles * p.n_tiles * p.split_k;
+    p.alpha = a->alpha;
+    // K-major SW128: 8-row groups 1024 B apart (SBO), LBO unused; 32 B per UMMA_K inside the swizzled row.
+    // MN-major SW128: 64-element MN blocks 8192 B apart (LBO), 8-k groups 1024 B apart (SBO); two k-groups
+    // (2048 B) per UMMA_K.  dbg_flags bit 1 swaps LBO/SBO of MN-major operands, bit 2 sets K-major LBO = 16 B.
+    const bool swap = (a->dbg_flags & 2) != 0;
+    const uint32_t k_lbo = (a->dbg_flags & 4) ? 16u : 0u;
+    p.a_lbo = p.a_mn ? (swap ? 1024u : 8192u) : k_lbo;
+    p.a_sbo = p.a_mn ? (swap ? 8192u : 1024u) : 1024u;
+    p.a_step = p.a_mn ? 2048u : 32u;
+    p.b_lbo = p.b_mn ? (swap ? 1024u : 8192u) : k_lbo;
+    p.b_sbo = p.b_mn ? (swap ? 8192u : 1024u) : 1024u;
+    p.b_step = p.b_mn ? 2048u : 32u;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        MMB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg::kSmemBytes));
+        attr_set = true;
+    }
+    const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    gemm_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+    return check_launch("gemm_tcgen05_kernel");
+}
+
+}  // namespace mmb
+
+extern "C" int mmb_gemm(const mmb_gemm_args* a, void* stream) {
+    using namespace mmb;
+    MMB_REQUIRE(a != nullptr, "mmb_gemm: null args");
+    MMB_REQUIRE(a->A && a->B && a->C, "mmb_gemm: null operand");
+    MMB_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "mmb_gemm: empty problem M=%d N=%d K=%d", a->M, a->N, a->K);
+    MMB_REQUIRE((a->lda % 8) == 0 && (a->ldb % 8) == 0, "mmb_gemm: lda/ldb must be multiples of 8 (got %lld, %lld)",
+                (long long)a->lda, (long long)a->ldb);
+    const bool f32_out = a->epilogue == MMB_EPI_STORE_F32 || a->epilogue == MMB_EPI_ATOMIC_ADD_F32;
+    MMB_REQUIRE((a->ldc % (f32_out ? 4 : 8)) == 0, "mmb_gemm: ldc=%lld misaligned", (long long)a->ldc);
+    MMB_REQUIRE(((uintptr_t)a->A % 16) == 0 && ((uintptr_t)a->B % 16) == 0 && ((uintptr_t)a->C % 16) == 0,
+                "mmb_gemm: operands must be 16-byte aligned");
+    MMB_REQUIRE(a->epilogue >= 0 && a->epilogue <= MMB_EPI_DGELU_BF16, "mmb_gemm: bad epilogue %d", a->epilogue);
+    MMB_REQUIRE(a->split_k <= 1 || a->epilogue == MMB_EPI_ATOMIC_ADD_F32, "mmb_gemm: split_k needs ATOMIC_ADD_F32");
+    if (a->epilogue == MMB_EPI_DGELU_BF16)
+        MMB_REQUIRE(a->aux != nullptr && (a->ldaux % 8) == 0, "mmb_gemm: DGELU needs aux with ldaux %% 8 == 0");
+    if (a->epilogue == MMB_EPI_GELU_BF16 && a->aux) MMB_REQUIRE((a->ldaux % 8) == 0, "mmb_gemm: ldaux %% 8 != 0");
+    const int min_lda = a->a_major == MMB_MAJOR_K ? a->K : a->M;
+    const int min_ldb = a->b_major == MMB_MAJOR_K ? a->K : a->N;
+    MMB_REQUIRE(a->lda >= min_lda && a->ldb >= min_ldb && a->ldc >= a->N, "mmb_gemm: leading dimension too small");
+    // N <= 128-wide problems (and anything forced by dbg_flags bit 0) use the 128x128 tile
+    const bool bn128 = (a->dbg_flags & 1) || a->N <= 128;
+    return bn128 ? launch_gemm<128>(a, (cudaStream_t)stream) : launch_gemm<256>(a, (cudaStream_t)stream);
+}

@@ -1,0 +1,54 @@
+// Library-wide host plumbing: thread-local error string, device checks, version.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace mmb {
+
+static thread_local char g_err[1024] = "";
+
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_last_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+        return MMB_ECUDA;
+    }
+    return MMB_OK;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace mmb
+
+extern "C" int mmb_version(void) { return MMB_VERSION; }
+extern "C" const char* mmb_last_error(void) { return mmb::g_err; }
+extern "C" int mmb_check_device(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        mmb::set_last_error("no CUDA device");
+        return MMB_ECUDA;
+    }
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) {
+        mmb::set_last_error("libmmbert_sm100 needs compute capability 10.x (B200), found %d.x", major);
+        return MMB_EARCH;
+    }
+    return MMB_OK;
+}
