@@ -1,0 +1,194 @@
+"""TEST INFRASTRUCTURE — CPU restatement ("port") of the reference's MMBert hot path.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may
+import this module, and only as the checker (or the timed CPU baseline) — never as the product path.
+
+It restates, as plain functional torch on a ``state_dict`` (no nn.Module, no transformers import), the
+arithmetic of:
+  * MMBertForPretraining.forward            /root/reference/MMBertForPretraining.py:392-449
+  * MMBertForPretraining.get_outputs        :367-390      (CE with ignore_index -100, mean over valid)
+  * MMBertModel.forward + extended mask     :216-285, :57-154  ((1-m)*-10000, frame mask = feature 0 only)
+  * MMBertPreTrainingHeads.forward          :292-302
+  * JointEmbeddings.forward, CPC.forward    /root/reference/MMBertEmbedding.py:57-72, :21-32
+  * transformers 5.5.0 modeling_bert.py (third-party, not vendored in the reference; the reference pins
+    transformers==2.8.0 but only imports that exist in >=4.x): BertEmbeddings :72-112, eager attention
+    :115-140, BertSelfAttention :168-207, BertSelfOutput :294-298, BertIntermediate :339-342 (exact erf
+    GELU), BertOutput :352-356, BertPooler :462-468, BertPredictionHeadTransform :481-485,
+    BertLMPredictionHead :498-501 (decoder weight tied to the word embeddings, :733-736).
+
+Pinning: the reference ships no tests or golden vectors, so this restatement is pinned
+against the live reference executed in the build container: ``tests/golden/*.npz`` are produced by
+``tests/golden/make_golden.py`` from the unmodified reference, and ``tests/test_oracle.py`` checks this file
+against them (all 13 outputs + logits, every parameter gradient and the set of parameters without
+gradient) — and, where /root/reference is present, against the live reference directly.
+
+Dropout is not restated (RNG streams cannot match): the oracle is the p=0 / eval() arithmetic.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+class Cfg:
+    """The few BertConfig fields the path reads."""
+
+    def __init__(self, hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
+                 vocab_size=30522, max_position_embeddings=512, layer_norm_eps=1e-12, num_labels=7):
+        self.hidden_size = hidden_size
+        self.num_hidden_layers = num_hidden_layers
+        self.num_attention_heads = num_attention_heads
+        self.intermediate_size = intermediate_size
+        self.vocab_size = vocab_size
+        self.max_position_embeddings = max_position_embeddings
+        self.layer_norm_eps = layer_norm_eps
+        self.num_labels = num_labels
+
+
+def _ln(x, w, b, eps):
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * w + b
+
+
+def _lin(x, sd, name):
+    return x @ sd[name + ".weight"].t() + sd[name + ".bias"]
+
+
+def _gelu(x):
+    return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+def _ext_mask(m, dtype):
+    # MMBertForPretraining.py:74-77 (3-D frame mask -> feature 0 only), :152-153
+    if m.dim() == 3:
+        m = m[:, :, 0]
+    return (1.0 - m.to(dtype))[:, None, None, :] * -10000.0
+
+
+def _cross_entropy(logits, labels):
+    # torch.nn.CrossEntropyLoss(): ignore_index=-100, mean over non-ignored rows (NaN when there are none)
+    valid = labels != -100
+    lse = torch.logsumexp(logits, dim=-1)
+    picked = logits.gather(-1, labels.clamp(min=0)[:, None])[:, 0]
+    return ((lse - picked) * valid).sum() / valid.sum()
+
+
+def bert_pass(sd, cfg, ids, mask, token_type, frames=None, frame_mask=None, dtype=torch.float64):
+    """MMBertModel.forward for one pass -> (sequence_output [B,S,H], pooled [B,H])."""
+    H, nh = cfg.hidden_size, cfg.num_attention_heads
+    d = H // nh
+    B, T = ids.shape
+    joint = frames is not None
+    if joint:
+        token_type = torch.zeros_like(ids)          # :223
+    # nn.Embedding(vocab, H, padding_idx=config.pad_token_id == 0): lookups of id 0 contribute NO gradient to
+    # row 0 (modeling_bert.py:58); the tied decoder's gradient into row 0 is kept.
+    e = F.embedding(ids.long(), sd["bert.embeddings.word_embeddings.weight"], padding_idx=0) \
+        + sd["bert.embeddings.token_type_embeddings.weight"][token_type.long()] \
+        + sd["bert.embeddings.position_embeddings.weight"][:T][None]
+    x = _ln(e, sd["bert.embeddings.LayerNorm.weight"], sd["bert.embeddings.LayerNorm.bias"], cfg.layer_norm_eps)
+    ext = _ext_mask(mask, dtype)
+    if joint:
+        which = "Wv" if frames.shape[-1] == sd["bert.jointEmbeddings.Wv.weight"].shape[1] else "Ws"
+        f = frames.float().to(dtype)                 # MMBertEmbedding.py:62: pair_ids.float()
+        p = torch.relu(_lin(f, sd, "bert.jointEmbeddings." + which))
+        x = torch.cat((x, p), dim=1)
+        x = _ln(x, sd["bert.jointEmbeddings.LayerNorm.weight"], sd["bert.jointEmbeddings.LayerNorm.bias"], 1e-5)
+        ext = torch.cat((ext, _ext_mask(frame_mask, dtype)), dim=-1)
+    S = x.shape[1]
+    for i in range(cfg.num_hidden_layers):
+        pre = f"bert.encoder.layer.{i}."
+        q = _lin(x, sd, pre + "attention.self.query").view(B, S, nh, d).transpose(1, 2)
+        k = _lin(x, sd, pre + "attention.self.key").view(B, S, nh, d).transpose(1, 2)
+        v = _lin(x, sd, pre + "attention.self.value").view(B, S, nh, d).transpose(1, 2)
+        s = (q @ k.transpose(2, 3)) * (d ** -0.5) + ext
+        ctx = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B, S, H)
+        a = _ln(_lin(ctx, sd, pre + "attention.output.dense") + x,
+                sd[pre + "attention.output.LayerNorm.weight"], sd[pre + "attention.output.LayerNorm.bias"],
+                cfg.layer_norm_eps)
+        h = _gelu(_lin(a, sd, pre + "intermediate.dense"))
+        x = _ln(_lin(h, sd, pre + "output.dense") + a,
+                sd[pre + "output.LayerNorm.weight"], sd[pre + "output.LayerNorm.bias"], cfg.layer_norm_eps)
+    pooled = torch.tanh(_lin(x[:, 0], sd, "bert.pooler.dense"))
+    return x, pooled
+
+
+def lm_head(sd, cfg, seq):
+    t = _gelu(_lin(seq, sd, "cls.predictions.transform.dense"))
+    t = _ln(t, sd["cls.predictions.transform.LayerNorm.weight"], sd["cls.predictions.transform.LayerNorm.bias"],
+            cfg.layer_norm_eps)
+    return t @ sd["bert.embeddings.word_embeddings.weight"].t() + sd["cls.predictions.bias"]
+
+
+def cpc(sd, name, x, y):
+    xp = _lin(y, sd, name + ".net")
+    xp = xp / xp.norm(dim=1, keepdim=True)
+    x = x / x.norm(dim=1, keepdim=True)
+    pos = (x * xp).sum(-1)
+    neg = torch.logsumexp(x @ xp.t(), dim=-1)
+    return -(pos - neg).mean()
+
+
+def forward(sd, cfg, input_ids, token_type_ids, attention_mask, masked_labels, ap_label, sentiment,
+            alpha=1.0, beta=1.0, dtype=torch.float64):
+    """MMBertForPretraining.forward -> ((13-tuple), logits), same structure as the reference."""
+    sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+    ids_t, vis, aud, ids_v, ids_s = input_ids
+    m_t, (m_tv, m_v), (m_ts, m_s) = attention_mask
+    lab_t, lab_v, lab_s = masked_labels
+    ap_v, ap_s = ap_label
+    V = cfg.vocab_size
+
+    seq_t, p_t = bert_pass(sd, cfg, ids_t, m_t, token_type_ids[0], dtype=dtype)
+    seq_v, p_v = bert_pass(sd, cfg, ids_v, m_tv, None, vis, m_v, dtype=dtype)
+    seq_s, p_s = bert_pass(sd, cfg, ids_s, m_ts, None, aud, m_s, dtype=dtype)
+    pred_t, pred_v, pred_s = lm_head(sd, cfg, seq_t), lm_head(sd, cfg, seq_v), lm_head(sd, cfg, seq_s)
+    rel_t = _lin(p_t, sd, "cls.seq_relationship")
+    al_v = _lin(seq_v[:, 0], sd, "cls.align")
+    al_s = _lin(seq_s[:, 0], sd, "cls.align")
+    mlm = (_cross_entropy(pred_t.reshape(-1, V), lab_t.reshape(-1))
+           + _cross_entropy(pred_v.reshape(-1, V), lab_v.reshape(-1))
+           + _cross_entropy(pred_s.reshape(-1, V), lab_s.reshape(-1))) / 3.0
+    ap = (_cross_entropy(al_v, ap_v.reshape(-1)) + _cross_entropy(al_s, ap_s.reshape(-1))) / 2.0
+
+    def score(p, vname):
+        return _lin(torch.relu(_lin(torch.cat((p, p), dim=1), sd, "attn")), sd, vname)
+
+    pooled = torch.cat((p_t * score(p_t, "vt"), p_v * score(p_v, "vv"), p_s * score(p_s, "vs")), dim=1)
+    temp = _lin(pooled, sd, "classifier1_1")
+    logits = _lin(temp, sd, "classifier1_2")
+    nce = cpc(sd, "cpc_zt", p_t, temp) + cpc(sd, "cpc_zv", p_v, temp) + cpc(sd, "cpc_za", p_s, temp)
+    out_logits = logits
+    if cfg.num_labels == 1:
+        out_logits = torch.tanh(logits)
+    label = ((out_logits.reshape(-1) - sentiment.reshape(-1).to(dtype)) ** 2).mean()
+    joint = alpha * mlm + ap + label - beta * nce
+    return (joint, None, None, None, ap, label, nce, pred_t, rel_t, pred_v, al_v, pred_s, al_s), out_logits
+
+
+# parameters that the reference leaves with ``grad is None`` after backward
+NO_GRAD_PARAMS = ("bert.jointEmbeddings.W_cv.weight", "bert.jointEmbeddings.W_cv.bias",
+                  "bert.jointEmbeddings.W_cs.weight", "bert.jointEmbeddings.W_cs.bias",
+                  "cls.seq_relationship.weight", "cls.seq_relationship.bias")
+# state_dict aliases of tied parameters (canonical name first)
+TIED = {"cls.predictions.decoder.weight": "bert.embeddings.word_embeddings.weight",
+        "cls.predictions.decoder.bias": "cls.predictions.bias"}
+
+
+def forward_backward(sd, cfg, batch, alpha=1.0, beta=1.0, dtype=torch.float64):
+    """Runs forward + ``joint_loss.backward()`` on leaf copies of ``sd``.
+    Returns (outputs, logits, grads) where grads maps canonical parameter names to gradients
+    (None for parameters the path does not touch)."""
+    leaves = {}
+    for k, v in sd.items():
+        if k in TIED or not v.is_floating_point():
+            continue
+        leaves[k] = v.detach().to(dtype).clone().requires_grad_(True)
+    full = dict(leaves)
+    for alias, canon in TIED.items():
+        full[alias] = leaves[canon]
+    out, logits = forward(full, cfg, alpha=alpha, beta=beta, dtype=dtype, **batch)
+    out[0].backward()
+    grads = {k: (v.grad if v.grad is not None else None) for k, v in leaves.items()}
+    return out, logits, grads
