@@ -82,6 +82,91 @@ typedef struct mmb_gemm_args {
 
 int mmb_gemm(const mmb_gemm_args* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * dropout + residual + LayerNorm (warp-per-row, HBM-bound).
+ *   out = LayerNorm_eps( dropout_p(y) + res ) * gamma + beta ;  mean/rstd saved for backward.
+ * Replaces BertSelfOutput.forward (modeling_bert.py:295-297), BertOutput.forward (:353-355) and, with
+ * res == NULL and p_drop == 0, the LayerNorm of BertPredictionHeadTransform (:484).  The dense bias is
+ * added by the producing GEMM's epilogue.  Dropout masks come from a counter-based generator keyed by
+ * (seed, rng_stream, row * H + col): backward regenerates them, nothing is stored.
+ */
+typedef struct mmb_drln_fwd_args {
+    const void* y;   /* [M,H] bf16 dense output (bias included) */
+    const void* res; /* [M,H] bf16 residual or NULL */
+    const float* gamma;
+    const float* beta;
+    void* out;   /* [M,H] bf16 */
+    float* mean; /* [M] */
+    float* rstd; /* [M] */
+    int32_t M, H;
+    float eps;
+    float p_drop;
+    uint64_t seed;
+    uint32_t rng_stream;
+} mmb_drln_fwd_args;
+int mmb_dropout_residual_ln_fwd(const mmb_drln_fwd_args* a, void* stream);
+
+/* Backward of the above (autograd of modeling_bert.py:295-297 / :353-355).
+ *   dz = LayerNormBackward(g1 + g2);  d_res = dz;  d_y = dz * mask / (1-p)
+ *   dgamma += sum_rows (g1+g2) * xhat;  dbeta += sum_rows (g1+g2);  dbias += sum_rows d_y   (fp32 atomics)
+ */
+typedef struct mmb_drln_bwd_args {
+    const void* g1; /* [M,H] bf16 gradient of out */
+    const void* g2; /* [M,H] bf16 second gradient of out (residual use by the next block) or NULL */
+    const void* y;
+    const void* res; /* or NULL */
+    const float* mean;
+    const float* rstd;
+    const float* gamma;
+    void* d_y;     /* [M,H] bf16 */
+    void* d_res;   /* [M,H] bf16 or NULL */
+    float* dgamma; /* [H] accumulated */
+    float* dbeta;  /* [H] accumulated */
+    float* dbias;  /* [H] accumulated, or NULL */
+    int32_t M, H;
+    float p_drop;
+    uint64_t seed;
+    uint32_t rng_stream;
+} mmb_drln_bwd_args;
+int mmb_dropout_residual_ln_bwd(const mmb_drln_bwd_args* a, void* stream);
+
+/* out[n] += sum_m X[m,n] — bias gradients of the dense layers whose dY is produced by a GEMM / attention
+ * kernel (autograd of nn.Linear bias, modeling_bert.py:179-181, :340). */
+typedef struct mmb_colsum_args {
+    const void* X; /* [M,N] bf16 */
+    float* out;    /* [N] f32, accumulated */
+    int64_t ld;
+    int32_t M, N;
+} mmb_colsum_args;
+int mmb_colsum_bf16(const mmb_colsum_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Masked multi-head self-attention over packed variable-length sequences, head dim 64.
+ *   ctx = dropout_p(softmax(Q K^T / 8 + keybias)) V      per (sequence, head)
+ * Replaces BertSelfAttention.forward's attention_interface call (modeling_bert.py:194-206 ->
+ * eager_attention_forward :115-140) with the extended mask built at MMBertForPretraining.py:246-250.
+ * Q|K|V are read in place from the fused projection output qkv [rows, 3H] (Q at column h*64, K at
+ * H + h*64, V at 2H + h*64); keybias[row] = (1 - mask) * -10000 for the key stored at that packed row.
+ * lse ([heads, rows] f32, log2 domain) is saved for backward.  mmb_attn_bwd writes dQ|dK|dV into dqkv with
+ * the same layout (autograd of the same lines); dsum [heads, rows] f32 is caller-provided scratch.
+ */
+typedef struct mmb_attn_args {
+    const void* qkv;        /* [rows, 3H] bf16 */
+    void* ctx;              /* [rows, H] bf16 (output of fwd, input of bwd) */
+    float* lse;             /* [heads, rows] */
+    const float* keybias;   /* [rows] */
+    const int32_t* cu_seqlens; /* [nseq + 1] row offsets */
+    const void* dctx;       /* bwd: [rows, H] bf16 */
+    void* dqkv;             /* bwd: [rows, 3H] bf16 */
+    float* dsum;            /* bwd scratch: [heads, rows] */
+    int32_t H, nheads, nseq, max_seqlen, total_rows;
+    float p_drop;
+    uint64_t seed;
+    uint32_t rng_stream;
+} mmb_attn_args;
+int mmb_attn_fwd(const mmb_attn_args* a, void* stream);
+int mmb_attn_bwd(const mmb_attn_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,3 +84,60 @@ def gemm(A, B, C, M, N, K, *, a_major=MAJOR_K, b_major=MAJOR_K, epilogue=EPI_STO
     a.a_major, a.b_major, a.epilogue, a.split_k = a_major, b_major, epilogue, split_k
     a.alpha, a.dbg_flags = alpha, dbg_flags
     call("gemm", a)
+
+
+class DrlnFwdArgs(ctypes.Structure):
+    _fields_ = [("y", ctypes.c_void_p), ("res", ctypes.c_void_p), ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p),
+                ("out", ctypes.c_void_p), ("mean", ctypes.c_void_p), ("rstd", ctypes.c_void_p),
+                ("M", ctypes.c_int32), ("H", ctypes.c_int32), ("eps", ctypes.c_float), ("p_drop", ctypes.c_float),
+                ("seed", ctypes.c_uint64), ("rng_stream", ctypes.c_uint32)]
+
+
+class DrlnBwdArgs(ctypes.Structure):
+    _fields_ = [("g1", ctypes.c_void_p), ("g2", ctypes.c_void_p), ("y", ctypes.c_void_p), ("res", ctypes.c_void_p),
+                ("mean", ctypes.c_void_p), ("rstd", ctypes.c_void_p), ("gamma", ctypes.c_void_p),
+                ("d_y", ctypes.c_void_p), ("d_res", ctypes.c_void_p), ("dgamma", ctypes.c_void_p),
+                ("dbeta", ctypes.c_void_p), ("dbias", ctypes.c_void_p),
+                ("M", ctypes.c_int32), ("H", ctypes.c_int32), ("p_drop", ctypes.c_float),
+                ("seed", ctypes.c_uint64), ("rng_stream", ctypes.c_uint32)]
+
+
+class ColsumArgs(ctypes.Structure):
+    _fields_ = [("X", ctypes.c_void_p), ("out", ctypes.c_void_p), ("ld", ctypes.c_int64),
+                ("M", ctypes.c_int32), ("N", ctypes.c_int32)]
+
+
+class AttnArgs(ctypes.Structure):
+    _fields_ = [("qkv", ctypes.c_void_p), ("ctx", ctypes.c_void_p), ("lse", ctypes.c_void_p),
+                ("keybias", ctypes.c_void_p), ("cu_seqlens", ctypes.c_void_p), ("dctx", ctypes.c_void_p),
+                ("dqkv", ctypes.c_void_p), ("dsum", ctypes.c_void_p),
+                ("H", ctypes.c_int32), ("nheads", ctypes.c_int32), ("nseq", ctypes.c_int32),
+                ("max_seqlen", ctypes.c_int32), ("total_rows", ctypes.c_int32), ("p_drop", ctypes.c_float),
+                ("seed", ctypes.c_uint64), ("rng_stream", ctypes.c_uint32)]
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def drln_fwd(y, res, gamma, beta, out, mean, rstd, eps, p_drop=0.0, seed=0, rng_stream=0):
+    a = DrlnFwdArgs(_p(y), _p(res), _p(gamma), _p(beta), _p(out), _p(mean), _p(rstd), y.shape[0], y.shape[1],
+                    eps, p_drop, seed, rng_stream)
+    call("dropout_residual_ln_fwd", a)
+
+
+def drln_bwd(g1, g2, y, res, mean, rstd, gamma, d_y, d_res, dgamma, dbeta, dbias, p_drop=0.0, seed=0, rng_stream=0):
+    a = DrlnBwdArgs(_p(g1), _p(g2), _p(y), _p(res), _p(mean), _p(rstd), _p(gamma), _p(d_y), _p(d_res), _p(dgamma),
+                    _p(dbeta), _p(dbias), y.shape[0], y.shape[1], p_drop, seed, rng_stream)
+    call("dropout_residual_ln_bwd", a)
+
+
+def colsum(X, out):
+    a = ColsumArgs(_p(X), _p(out), X.stride(0), X.shape[0], X.shape[1])
+    call("colsum_bf16", a)
+
+
+def attn_args(qkv, ctx, lse, keybias, cu_seqlens, H, nheads, max_seqlen, dctx=None, dqkv=None, dsum=None,
+              p_drop=0.0, seed=0, rng_stream=0):
+    return AttnArgs(_p(qkv), _p(ctx), _p(lse), _p(keybias), _p(cu_seqlens), _p(dctx), _p(dqkv), _p(dsum),
+                    H, nheads, cu_seqlens.numel() - 1, max_seqlen, qkv.shape[0], p_drop, seed, rng_stream)

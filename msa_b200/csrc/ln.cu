@@ -1,0 +1,189 @@
+// HBM-bound row kernels of the encoder block: dropout + residual + LayerNorm (forward / backward) and the
+// bf16 column-sum used for bias gradients.  One warp per row, 16-byte vector accesses, warp-shuffle statistics.
+//
+// Replaces the ATen kernel chains behind
+//   BertSelfOutput.forward  modeling_bert.py:295-297   LayerNorm(dropout(dense(x)) + input)
+//   BertOutput.forward      modeling_bert.py:353-355
+//   BertPredictionHeadTransform LayerNorm :484 (res == NULL, p == 0)
+// (the dense bias is already added by the GEMM epilogue).
+#include "common.cuh"
+#include "rowops.cuh"
+
+namespace mmb {
+
+constexpr int kLnWarps = 8;
+
+template <int NCH>
+__global__ void __launch_bounds__(kLnWarps * 32)
+drln_fwd_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ res,
+                const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
+                float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int H, float eps, uint32_t thresh,
+                float inv_keep, uint64_t seed, uint32_t stream) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nw = gridDim.x * kLnWarps;
+    for (int row = blockIdx.x * kLnWarps + warp; row < M; row += nw) {
+        RowF<NCH> z;
+        row_load_bf16(z, y + (size_t)row * H, H, lane);
+        row_dropout(z, H, lane, seed, stream, (uint64_t)row, thresh, inv_keep);
+        if (res != nullptr) {
+            RowF<NCH> r;
+            row_load_bf16(r, res + (size_t)row * H, H, lane);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) z.v[c][i] += r.v[c][i];
+        }
+        float mean, rstd;
+        row_stats(z, H, lane, eps, mean, rstd);
+        row_affine(z, H, lane, mean, rstd, gamma, beta);
+        row_store_bf16(z, out + (size_t)row * H, H, lane);
+        if (lane == 0) {
+            mean_out[row] = mean;
+            rstd_out[row] = rstd;
+        }
+    }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(kLnWarps * 32)
+drln_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
+                const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ res,
+                const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
+                __nv_bfloat16* __restrict__ d_y, __nv_bfloat16* __restrict__ d_res, float* __restrict__ dgamma,
+                float* __restrict__ dbeta, float* __restrict__ dbias, int M, int H, uint32_t thresh, float inv_keep,
+                uint64_t seed, uint32_t stream) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nw = gridDim.x * kLnWarps;
+    RowF<NCH> acc_g, acc_b, acc_bias;
+    row_zero(acc_g);
+    row_zero(acc_b);
+    row_zero(acc_bias);
+    for (int row = blockIdx.x * kLnWarps + warp; row < M; row += nw) {
+        // recompute the LayerNorm input exactly as the forward did: z = dropout(y) + res
+        RowF<NCH> z;
+        row_load_bf16(z, y + (size_t)row * H, H, lane);
+        row_dropout(z, H, lane, seed, stream, (uint64_t)row, thresh, inv_keep);
+        if (res != nullptr) {
+            RowF<NCH> r;
+            row_load_bf16(r, res + (size_t)row * H, H, lane);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) z.v[c][i] += r.v[c][i];
+        }
+        RowF<NCH> g;
+        row_load_bf16(g, g1 + (size_t)row * H, H, lane);
+        if (g2 != nullptr) {
+            RowF<NCH> t;
+            row_load_bf16(t, g2 + (size_t)row * H, H, lane);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g.v[c][i] += t.v[c][i];
+        }
+        row_ln_bwd(z, g, H, lane, mean_in[row], rstd_in[row], gamma, acc_g, acc_b);
+        // g now holds dz: gradient of the residual branch
+        if (d_res != nullptr) row_store_bf16(g, d_res + (size_t)row * H, H, lane);
+        // gradient of the dense output (pre-dropout): dz * mask / keep
+        if (thresh != 0u) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const int e = (c * 32 + lane) * 8;
+                if (e < H) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        g.v[c][i] = rng_keep(seed, stream, (uint64_t)row * H + e + i, thresh) ? g.v[c][i] * inv_keep : 0.f;
+                }
+            }
+        }
+        row_round_bf16(g);  // the bias gradient sums exactly what the wgrad GEMM will read
+        row_store_bf16(g, d_y + (size_t)row * H, H, lane);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc_bias.v[c][i] += g.v[c][i];
+    }
+    cta_flush_columns(acc_g, dgamma, H, smem, warp, lane, kLnWarps);
+    cta_flush_columns(acc_b, dbeta, H, smem, warp, lane, kLnWarps);
+    if (dbias != nullptr) cta_flush_columns(acc_bias, dbias, H, smem, warp, lane, kLnWarps);
+}
+
+// out[n] += sum_m X[m, n]   (X bf16, row stride ld).  Each thread owns 8 adjacent columns.
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, float* __restrict__ out, int M, int N, int64_t ld,
+                   int rows_per_cta) {
+    __shared__ float red[8][32 * 8 + 1];
+    const int cg = threadIdx.x & 31;  // column group within the CTA's 256-column strip
+    const int rr = threadIdx.x >> 5;  // row lane 0..7
+    const int col0 = blockIdx.x * 256 + cg * 8;
+    const int r0 = blockIdx.y * rows_per_cta;
+    const int r1 = min(M, r0 + rows_per_cta);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (col0 < N) {
+        for (int r = r0 + rr; r < r1; r += 8) {
+            const uint4 q = *reinterpret_cast<const uint4*>(X + (size_t)r * ld + col0);
+            const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+            acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[rr][cg * 8 + i] = acc[i];
+    __syncthreads();
+    const int col = blockIdx.x * 256 + threadIdx.x;
+    if (col < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) s += red[r][threadIdx.x];
+        atomicAdd(out + col, s);
+    }
+}
+
+}  // namespace mmb
+
+using namespace mmb;
+
+extern "C" int mmb_dropout_residual_ln_fwd(const mmb_drln_fwd_args* a, void* stream) {
+    MMB_REQUIRE(a && a->y && a->gamma && a->beta && a->out && a->mean && a->rstd, "drln_fwd: null pointer");
+    MMB_REQUIRE(a->M > 0 && a->H > 0 && a->H % 8 == 0 && a->H <= 1024, "drln_fwd: bad shape M=%d H=%d", a->M, a->H);
+    const uint32_t thresh = dropout_threshold(a->p_drop);
+    const float inv_keep = a->p_drop > 0.f ? 1.0f / (1.0f - a->p_drop) : 1.0f;
+    const int grid = min((a->M + kLnWarps - 1) / kLnWarps, num_sms() * 4);
+    MMB_DISPATCH_NCH(a->H, (drln_fwd_kernel<NCH><<<grid, kLnWarps * 32, 0, (cudaStream_t)stream>>>(
+                               (const __nv_bfloat16*)a->y, (const __nv_bfloat16*)a->res, a->gamma, a->beta,
+                               (__nv_bfloat16*)a->out, a->mean, a->rstd, a->M, a->H, a->eps, thresh, inv_keep, a->seed,
+                               a->rng_stream)));
+    return check_launch("drln_fwd_kernel");
+}
+
+extern "C" int mmb_dropout_residual_ln_bwd(const mmb_drln_bwd_args* a, void* stream) {
+    MMB_REQUIRE(a && a->g1 && a->y && a->mean && a->rstd && a->gamma && a->d_y && a->dgamma && a->dbeta,
+                "drln_bwd: null pointer");
+    MMB_REQUIRE(a->M > 0 && a->H > 0 && a->H % 8 == 0 && a->H <= 1024, "drln_bwd: bad shape M=%d H=%d", a->M, a->H);
+    const uint32_t thresh = dropout_threshold(a->p_drop);
+    const float inv_keep = a->p_drop > 0.f ? 1.0f / (1.0f - a->p_drop) : 1.0f;
+    const int grid = min((a->M + kLnWarps - 1) / kLnWarps, num_sms());
+    const size_t smem = (size_t)kLnWarps * a->H * sizeof(float);
+    MMB_DISPATCH_NCH(a->H, (drln_bwd_kernel<NCH><<<grid, kLnWarps * 32, smem, (cudaStream_t)stream>>>(
+                               (const __nv_bfloat16*)a->g1, (const __nv_bfloat16*)a->g2, (const __nv_bfloat16*)a->y,
+                               (const __nv_bfloat16*)a->res, a->mean, a->rstd, a->gamma, (__nv_bfloat16*)a->d_y,
+                               (__nv_bfloat16*)a->d_res, a->dgamma, a->dbeta, a->dbias, a->M, a->H, thresh, inv_keep,
+                               a->seed, a->rng_stream)));
+    return check_launch("drln_bwd_kernel");
+}
+
+extern "C" int mmb_colsum_bf16(const mmb_colsum_args* a, void* stream) {
+    MMB_REQUIRE(a && a->X && a->out, "colsum: null pointer");
+    MMB_REQUIRE(a->M > 0 && a->N > 0 && a->N % 8 == 0 && a->ld % 8 == 0, "colsum: bad shape M=%d N=%d ld=%lld", a->M,
+                a->N, (long long)a->ld);
+    const int strips = (a->N + 255) / 256;
+    int ysplit = (num_sms() * 2 + strips - 1) / strips;
+    if (ysplit > (a->M + 63) / 64) ysplit = (a->M + 63) / 64;
+    if (ysplit < 1) ysplit = 1;
+    const int rows_per_cta = (a->M + ysplit - 1) / ysplit;
+    dim3 grid(strips, (a->M + rows_per_cta - 1) / rows_per_cta);
+    colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a->X, a->out, a->M, a->N, a->ld,
+                                                              rows_per_cta);
+    return check_launch("colsum_bf16_kernel");
+}
