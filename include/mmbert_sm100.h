@@ -109,6 +109,8 @@ int mmb_dropout_residual_ln_fwd(const mmb_drln_fwd_args* a, void* stream);
 /* Backward of the above (autograd of modeling_bert.py:295-297 / :353-355).
  *   dz = LayerNormBackward(g1 + g2);  d_res = dz;  d_y = dz * mask / (1-p)
  *   dgamma += sum_rows (g1+g2) * xhat;  dbeta += sum_rows (g1+g2);  dbias += sum_rows d_y   (fp32 atomics)
+ * With gelu_aux (LM-head transform: LayerNorm(gelu(dense(x))), modeling_bert.py:482-484) d_y is additionally
+ * multiplied by gelu'(aux) so that it is the gradient of the dense output.
  */
 typedef struct mmb_drln_bwd_args {
     const void* g1; /* [M,H] bf16 gradient of out */
@@ -123,6 +125,7 @@ typedef struct mmb_drln_bwd_args {
     float* dgamma; /* [H] accumulated */
     float* dbeta;  /* [H] accumulated */
     float* dbias;  /* [H] accumulated, or NULL */
+    const void* gelu_aux; /* [M,H] bf16 or NULL: y = gelu(aux) -> d_y is chained through gelu'(aux) */
     int32_t M, H;
     float p_drop;
     uint64_t seed;
@@ -166,6 +169,163 @@ typedef struct mmb_attn_args {
 } mmb_attn_args;
 int mmb_attn_fwd(const mmb_attn_args* a, void* stream);
 int mmb_attn_bwd(const mmb_attn_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Packed batch: the reference's three encoder passes (MMBertForPretraining.py:402-404) are packed into
+ * one variable-length batch of 3B sequences, rows ordered
+ *   [pass 0: B x T text] [pass 1: B x (T + Lv) text|visual] [pass 2: B x (T + La) text|speech].
+ * Input tensors are consumed in the dtypes the reference's collate produces (model_utils.py:117-142):
+ * ids/labels int64, frames float64, masks float64 or int64 — selected by an MMB_DT_* code.
+ */
+enum { MMB_DT_F32 = 0, MMB_DT_F64 = 1, MMB_DT_I64 = 2, MMB_DT_I32 = 3, MMB_DT_U8 = 4 };
+
+/* keybias[row] = (1 - mask) * -10000 (MMBertForPretraining.py:152-153; frame masks: feature 0 only, :75-77),
+ * cu_seqlens[3B+1] row offsets, label_count[3] = number of labels != -100 per pass (CrossEntropyLoss
+ * mean denominator, :381-383). */
+typedef struct mmb_pack_args {
+    const void* mask_text[3]; /* [B,T] text-half mask of each pass */
+    int32_t mask_text_dtype[3];
+    const void* mask_frame[2]; /* [B,L,D] visual / speech masks */
+    int32_t mask_frame_dtype[2];
+    int32_t frame_dim[2];
+    const void* labels[3]; /* int64 [B,T], [B,T+Lv], [B,T+La]; may be NULL */
+    float* keybias;        /* [rows] */
+    int32_t* cu_seqlens;   /* [3B+1] */
+    int32_t* label_count;  /* [3] */
+    int32_t B, T;
+    int32_t L[2];
+} mmb_pack_args;
+int mmb_pack_prepare(const mmb_pack_args* a, void* stream);
+
+/* Fused embeddings, forward and backward.
+ *   text rows : LN_eps1(word[id] + type[tt] + pos[s]) -> dropout(p1) [-> LN_eps2 -> dropout(p2) in joint passes]
+ *   frame rows: relu(W f32(frame) + b) (rounded to bf16, saved in pframe) -> LN_eps2 -> dropout(p2)
+ * Replaces BertEmbeddings.forward (modeling_bert.py:103-112) and JointEmbeddings.forward
+ * (MMBertEmbedding.py:61-70).  wT are the projection weights transposed to [D,H] (refreshed with the
+ * bf16 weight copies).  mmb_embed_bwd consumes dx0 and ACCUMULATES (fp32 atomics) into the g_* buffers:
+ * word-embedding rows (id 0 = padding_idx gets none), position, token-type, both LayerNorms, Wv/Ws and biases.
+ */
+typedef struct mmb_embed_args {
+    const void* ids[3];     /* int64 [B,T]: text, text-with-visual, text-with-speech ids */
+    const void* token_type; /* int64 [B,T] (pass 0; joint passes use type 0, MMBertForPretraining.py:223) */
+    const void* frames[2];  /* [B,Lv,Dv], [B,La,Da] */
+    int32_t frames_dtype[2];
+    int32_t frame_dim[2];
+    const float* word; /* [V,H] */
+    const float* pos;  /* [max_pos,H] */
+    const float* type; /* [2,H] */
+    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+    const float* wT[2]; /* [D,H] */
+    const float* wb[2]; /* [H] */
+    float eps1, eps2, p_drop1, p_drop2;
+    uint64_t seed;
+    void* x0; /* [rows,H] bf16 */
+    float *mean1, *rstd1, *mean2, *rstd2; /* [rows] */
+    void* pframe;                         /* [B*(Lv+La), H] bf16 */
+    /* backward */
+    const void* dx0;  /* [rows,H] bf16 */
+    const void* dx0b; /* [rows,H] bf16 second gradient to add, or NULL */
+    void* dpre;      /* [B*(Lv+La), H] bf16 scratch */
+    float *g_word, *g_pos, *g_type, *g_ln1_g, *g_ln1_b, *g_ln2_g, *g_ln2_b;
+    float* g_w[2];  /* [H,D] */
+    float* g_wb[2]; /* [H] */
+    int32_t B, T;
+    int32_t L[2];
+    int32_t H, V, max_pos;
+} mmb_embed_args;
+int mmb_embed_fwd(const mmb_embed_args* a, void* stream);
+int mmb_embed_bwd(const mmb_embed_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Masked-LM cross entropy over the tied-decoder logits (bf16 [rows, ldl], ldl = V rounded up to 8).
+ * Replaces CrossEntropyLoss()(prediction_scores.view(-1,V), labels.view(-1)) at
+ * MMBertForPretraining.py:381-384 (ignore_index -100, mean over the labelled rows of each pass).
+ * fwd: row_lse[row] and loss_sum[pass] for labelled rows.  bwd: dlogits = coef * gscale / count[pass] *
+ * (softmax - onehot) for labelled rows and (dense != 0) zeros elsewhere — the reference's autograd runs the
+ * decoder dgrad/wgrad GEMMs over all rows; dense keeps that work faithful.
+ */
+typedef struct mmb_ce_args {
+    const void* logits;    /* [rows, ldl] bf16 */
+    void* dlogits;         /* [rows, ldl] bf16 (bwd) */
+    const void* labels[3]; /* int64 per pass */
+    const int32_t* label_count; /* [3] from mmb_pack_prepare */
+    float* row_lse;        /* [rows] */
+    float* loss_sum;       /* [3] */
+    const float* gscale;   /* device scalar: d(joint_loss) upstream gradient, NULL = 1 */
+    float coef;            /* alpha / 3 */
+    int32_t V;
+    int64_t ldl;
+    int32_t B, T;
+    int32_t L[2];
+    int32_t dense;
+} mmb_ce_args;
+int mmb_ce_fwd(const mmb_ce_args* a, void* stream);
+int mmb_ce_bwd(const mmb_ce_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pooler + alignment/NSP heads + score-attention fusion + sentiment head + CPC x3 + loss combination
+ * on the 3B [CLS] rows.  Replaces BertPooler.forward (modeling_bert.py:462-468),
+ * MMBertPreTrainingHeads.forward (MMBertForPretraining.py:295-302), the fusion/classifier block (:406-415),
+ * CPC.forward (MMBertEmbedding.py:21-32) and the losses (:386-388, :427-443), plus autograd of all of it.
+ * All weights fp32 in nn.Linear layout [out,in].  losses[8] = joint, mlm, ap, label, nce, mlm_t, mlm_v, mlm_s.
+ * mmb_heads_bwd ACCUMULATES parameter gradients into g_* and ADDS the [CLS]-row gradients into dseq_out.
+ * cls.seq_relationship is evaluated for its output only (never in a loss): it has no gradient entry.
+ */
+typedef struct mmb_heads_args {
+    const void* seq_out;       /* [rows,H] bf16 encoder output */
+    void* dseq_out;            /* [rows,H] bf16 gradient buffer (bwd: [CLS] rows are incremented) */
+    const int32_t* cu_seqlens; /* [3B+1] */
+    void* workspace;           /* mmb_heads_workspace_bytes(B,H) bytes, must persist fwd -> bwd */
+    const float *w_pooler, *b_pooler, *w_seqrel, *b_seqrel, *w_align, *b_align, *w_attn, *b_attn;
+    const float *w_c11, *b_c11, *w_c12, *b_c12;
+    const float* w_v[3]; /* vt, vv, vs */
+    const float* b_v[3];
+    const float* w_cpc[3]; /* cpc_zt, cpc_zv, cpc_za .net */
+    const float* b_cpc[3];
+    float *g_w_pooler, *g_b_pooler, *g_w_align, *g_b_align, *g_w_attn, *g_b_attn, *g_w_c11, *g_b_c11, *g_w_c12, *g_b_c12;
+    float* g_w_v[3];
+    float* g_b_v[3];
+    float* g_w_cpc[3];
+    float* g_b_cpc[3];
+    const void* ap_label[2]; /* int64 [B] visual, speech */
+    const float* sentiment;  /* [B] f32 */
+    const float* ce_loss_sum;   /* [3] from mmb_ce_fwd */
+    const int32_t* label_count; /* [3] */
+    float* losses;     /* [8] */
+    float* logits_out; /* [B]  (tanh applied iff num_labels == 1) */
+    float* rel_out;    /* [B,2] seq_relationship(pooled_text) or NULL */
+    float* align_out;  /* [2B,2] align scores (visual rows, then speech rows) or NULL */
+    const float* gscale; /* device scalar upstream gradient, NULL = 1 */
+    float alpha, beta;
+    int32_t B, H, num_labels;
+} mmb_heads_args;
+size_t mmb_heads_workspace_bytes(int B, int H);
+int mmb_heads_fwd(const mmb_heads_args* a, void* stream);
+int mmb_heads_bwd(const mmb_heads_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Weight maintenance.  mmb_cast_bf16 refreshes the bf16 GEMM operand copies from the fp32 master
+ * parameters; mmb_transpose_f32 builds the [D,H] frame-projection weights the embedding kernel streams.
+ * mmb_adamw is one fused pass over a flat parameter range with the semantics of the AdamW the reference
+ * constructs (train.py:76-92 -> transformers.optimization.AdamW, <= 4.x): m/v update, step size
+ * lr * sqrt(1-beta2^t) / (1-beta1^t) when correct_bias, eps added to sqrt(v), then p -= lr * wd * p;
+ * optionally writes the refreshed bf16 copy in the same pass.  grad_scale multiplies the gradient first
+ * (1/world_size after a SUM all-reduce).
+ */
+int mmb_cast_bf16(const float* src, void* dst, size_t n, void* stream);
+int mmb_transpose_f32(const float* src, float* dst, int R, int C, void* stream);
+typedef struct mmb_adamw_args {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    void* p_bf16; /* bf16 mirror of p or NULL */
+    size_t n;     /* elements, multiple of 4 */
+    float lr, beta1, beta2, eps, weight_decay, grad_scale;
+    int32_t step;         /* 1-based */
+    int32_t correct_bias; /* HF default: 1 */
+} mmb_adamw_args;
+int mmb_adamw(const mmb_adamw_args* a, void* stream);
 
 #ifdef __cplusplus
 }

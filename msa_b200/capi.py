@@ -58,86 +58,155 @@ def call(name, args_struct):
     check(fn(ctypes.byref(args_struct), stream_ptr()), "mmb_" + name)
 
 
-class GemmArgs(ctypes.Structure):
-    _fields_ = [
-        ("A", ctypes.c_void_p), ("B", ctypes.c_void_p), ("C", ctypes.c_void_p), ("aux", ctypes.c_void_p),
-        ("bias", ctypes.c_void_p),
-        ("lda", ctypes.c_int64), ("ldb", ctypes.c_int64), ("ldc", ctypes.c_int64), ("ldaux", ctypes.c_int64),
-        ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32),
-        ("a_major", ctypes.c_int32), ("b_major", ctypes.c_int32),
-        ("epilogue", ctypes.c_int32), ("split_k", ctypes.c_int32),
-        ("alpha", ctypes.c_float), ("dbg_flags", ctypes.c_int32),
-    ]
+
+# ---------------------------------------------------------------------------------------------------
+# The argument structures are generated from include/mmbert_sm100.h, so the Python side cannot drift
+# from the C ABI.  Only the header's own conventions are parsed (plain scalars, pointers, fixed arrays).
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mmbert_sm100.h")
+_SCALARS = {"int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "uint32_t": ctypes.c_uint32,
+            "uint64_t": ctypes.c_uint64, "float": ctypes.c_float, "size_t": ctypes.c_size_t, "int": ctypes.c_int}
 
 
-def gemm(A, B, C, M, N, K, *, a_major=MAJOR_K, b_major=MAJOR_K, epilogue=EPI_STORE_BF16, bias=None, aux=None,
-         split_k=1, alpha=1.0, lda=None, ldb=None, ldc=None, ldaux=None, dbg_flags=0):
-    """C[M,N] = epilogue(alpha * A·Bᵀ).  A/B are 2-D bf16 CUDA tensors (stride(1) == 1); see mmb_gemm."""
-    a = GemmArgs()
-    a.A, a.B, a.C, a.aux, a.bias = A.data_ptr(), B.data_ptr(), C.data_ptr(), \
-        (aux.data_ptr() if aux is not None else 0), (bias.data_ptr() if bias is not None else 0)
-    a.lda = A.stride(0) if lda is None else lda
-    a.ldb = B.stride(0) if ldb is None else ldb
-    a.ldc = C.stride(0) if ldc is None else ldc
-    a.ldaux = (aux.stride(0) if aux is not None else 0) if ldaux is None else ldaux
-    a.M, a.N, a.K = M, N, K
-    a.a_major, a.b_major, a.epilogue, a.split_k = a_major, b_major, epilogue, split_k
-    a.alpha, a.dbg_flags = alpha, dbg_flags
-    call("gemm", a)
+def _parse_header(path=HEADER_PATH):
+    import re
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    structs = {}
+    for m in re.finditer(r"typedef\s+struct\s+(\w+)\s*\{(.*?)\}\s*(\w+)\s*;", src, flags=re.S):
+        fields = []
+        for stmt in m.group(2).split(";"):
+            stmt = " ".join(stmt.split())
+            if not stmt:
+                continue
+            mm = re.match(r"^((?:const\s+)?\w+)\s*(.*)$", stmt)
+            base, decls = mm.group(1).replace("const ", "").strip(), mm.group(2)
+            for d in decls.split(","):
+                d = d.strip()
+                is_ptr = d.startswith("*")
+                d = d.lstrip("* ").strip()
+                am = re.match(r"^(\w+)\s*\[(\d+)\]$", d)
+                name, count = (am.group(1), int(am.group(2))) if am else (d, None)
+                ctype = ctypes.c_void_p if is_ptr else _SCALARS[base]
+                fields.append((name, ctype * count if count else ctype))
+        structs[m.group(3)] = fields
+    funcs = re.findall(r"^\s*(?:int|size_t|const char\*)\s+(mmb_\w+)\s*\(", src, flags=re.M)
+    return structs, funcs
 
 
-class DrlnFwdArgs(ctypes.Structure):
-    _fields_ = [("y", ctypes.c_void_p), ("res", ctypes.c_void_p), ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p),
-                ("out", ctypes.c_void_p), ("mean", ctypes.c_void_p), ("rstd", ctypes.c_void_p),
-                ("M", ctypes.c_int32), ("H", ctypes.c_int32), ("eps", ctypes.c_float), ("p_drop", ctypes.c_float),
-                ("seed", ctypes.c_uint64), ("rng_stream", ctypes.c_uint32)]
+_STRUCT_FIELDS, DECLARED_FUNCTIONS = _parse_header()
 
 
-class DrlnBwdArgs(ctypes.Structure):
-    _fields_ = [("g1", ctypes.c_void_p), ("g2", ctypes.c_void_p), ("y", ctypes.c_void_p), ("res", ctypes.c_void_p),
-                ("mean", ctypes.c_void_p), ("rstd", ctypes.c_void_p), ("gamma", ctypes.c_void_p),
-                ("d_y", ctypes.c_void_p), ("d_res", ctypes.c_void_p), ("dgamma", ctypes.c_void_p),
-                ("dbeta", ctypes.c_void_p), ("dbias", ctypes.c_void_p),
-                ("M", ctypes.c_int32), ("H", ctypes.c_int32), ("p_drop", ctypes.c_float),
-                ("seed", ctypes.c_uint64), ("rng_stream", ctypes.c_uint32)]
+def _make_struct(cname):
+    return type(cname, (ctypes.Structure,), {"_fields_": _STRUCT_FIELDS[cname]})
 
 
-class ColsumArgs(ctypes.Structure):
-    _fields_ = [("X", ctypes.c_void_p), ("out", ctypes.c_void_p), ("ld", ctypes.c_int64),
-                ("M", ctypes.c_int32), ("N", ctypes.c_int32)]
+GemmArgs = _make_struct("mmb_gemm_args")
+DrlnFwdArgs = _make_struct("mmb_drln_fwd_args")
+DrlnBwdArgs = _make_struct("mmb_drln_bwd_args")
+ColsumArgs = _make_struct("mmb_colsum_args")
+AttnArgs = _make_struct("mmb_attn_args")
+PackArgs = _make_struct("mmb_pack_args")
+EmbedArgs = _make_struct("mmb_embed_args")
+CeArgs = _make_struct("mmb_ce_args")
+HeadsArgs = _make_struct("mmb_heads_args")
+AdamwArgs = _make_struct("mmb_adamw_args")
+
+DT_F32, DT_F64, DT_I64, DT_I32, DT_U8 = range(5)
+_DT = {torch.float32: DT_F32, torch.float64: DT_F64, torch.int64: DT_I64, torch.int32: DT_I32, torch.uint8: DT_U8,
+       torch.bool: DT_U8}
 
 
-class AttnArgs(ctypes.Structure):
-    _fields_ = [("qkv", ctypes.c_void_p), ("ctx", ctypes.c_void_p), ("lse", ctypes.c_void_p),
-                ("keybias", ctypes.c_void_p), ("cu_seqlens", ctypes.c_void_p), ("dctx", ctypes.c_void_p),
-                ("dqkv", ctypes.c_void_p), ("dsum", ctypes.c_void_p),
-                ("H", ctypes.c_int32), ("nheads", ctypes.c_int32), ("nseq", ctypes.c_int32),
-                ("max_seqlen", ctypes.c_int32), ("total_rows", ctypes.c_int32), ("p_drop", ctypes.c_float),
-                ("seed", ctypes.c_uint64), ("rng_stream", ctypes.c_uint32)]
+def dtype_code(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise MMBError(f"unsupported input dtype {t.dtype}")
 
 
 def _p(t):
     return 0 if t is None else t.data_ptr()
 
 
-def drln_fwd(y, res, gamma, beta, out, mean, rstd, eps, p_drop=0.0, seed=0, rng_stream=0):
-    a = DrlnFwdArgs(_p(y), _p(res), _p(gamma), _p(beta), _p(out), _p(mean), _p(rstd), y.shape[0], y.shape[1],
-                    eps, p_drop, seed, rng_stream)
-    call("dropout_residual_ln_fwd", a)
+def fill(struct, **kw):
+    """Sets fields of a ctypes struct; tensors become device pointers, lists fill fixed arrays."""
+    for k, v in kw.items():
+        if isinstance(v, (list, tuple)):
+            arr = getattr(struct, k)
+            for i, x in enumerate(v):
+                arr[i] = _p(x) if (torch.is_tensor(x) or x is None) else x
+        elif torch.is_tensor(v) or v is None:
+            setattr(struct, k, _p(v))
+        else:
+            setattr(struct, k, v)
+    return struct
 
 
-def drln_bwd(g1, g2, y, res, mean, rstd, gamma, d_y, d_res, dgamma, dbeta, dbias, p_drop=0.0, seed=0, rng_stream=0):
-    a = DrlnBwdArgs(_p(g1), _p(g2), _p(y), _p(res), _p(mean), _p(rstd), _p(gamma), _p(d_y), _p(d_res), _p(dgamma),
-                    _p(dbeta), _p(dbias), y.shape[0], y.shape[1], p_drop, seed, rng_stream)
-    call("dropout_residual_ln_bwd", a)
+def gemm_args(A, B, C, M, N, K, *, a_major=MAJOR_K, b_major=MAJOR_K, epilogue=EPI_STORE_BF16, bias=None, aux=None,
+              split_k=1, alpha=1.0, lda=None, ldb=None, ldc=None, ldaux=None, dbg_flags=0):
+    a = GemmArgs()
+    return fill(a, A=A, B=B, C=C, aux=aux, bias=bias,
+                lda=A.stride(0) if lda is None else lda, ldb=B.stride(0) if ldb is None else ldb,
+                ldc=C.stride(0) if ldc is None else ldc,
+                ldaux=((aux.stride(0) if aux is not None else 0) if ldaux is None else ldaux),
+                M=M, N=N, K=K, a_major=a_major, b_major=b_major, epilogue=epilogue, split_k=split_k, alpha=alpha,
+                dbg_flags=dbg_flags)
+
+
+def gemm(A, B, C, M, N, K, **kw):
+    """C[M,N] = epilogue(alpha * A·Bᵀ).  A/B are 2-D bf16 CUDA tensors (stride(1) == 1); see mmb_gemm."""
+    call("gemm", gemm_args(A, B, C, M, N, K, **kw))
+
+
+def drln_fwd_args(y, res, gamma, beta, out, mean, rstd, eps, p_drop=0.0, seed=0, rng_stream=0):
+    return fill(DrlnFwdArgs(), y=y, res=res, gamma=gamma, beta=beta, out=out, mean=mean, rstd=rstd, M=y.shape[0],
+                H=y.shape[1], eps=eps, p_drop=p_drop, seed=seed, rng_stream=rng_stream)
+
+
+def drln_fwd(*a, **kw):
+    call("dropout_residual_ln_fwd", drln_fwd_args(*a, **kw))
+
+
+def drln_bwd_args(g1, g2, y, res, mean, rstd, gamma, d_y, d_res, dgamma, dbeta, dbias, p_drop=0.0, seed=0,
+                  rng_stream=0):
+    return fill(DrlnBwdArgs(), g1=g1, g2=g2, y=y, res=res, mean=mean, rstd=rstd, gamma=gamma, d_y=d_y, d_res=d_res,
+                dgamma=dgamma, dbeta=dbeta, dbias=dbias, M=y.shape[0], H=y.shape[1], p_drop=p_drop, seed=seed,
+                rng_stream=rng_stream)
+
+
+def drln_bwd(*a, **kw):
+    call("dropout_residual_ln_bwd", drln_bwd_args(*a, **kw))
+
+
+def colsum_args(X, out):
+    return fill(ColsumArgs(), X=X, out=out, ld=X.stride(0), M=X.shape[0], N=X.shape[1])
 
 
 def colsum(X, out):
-    a = ColsumArgs(_p(X), _p(out), X.stride(0), X.shape[0], X.shape[1])
-    call("colsum_bf16", a)
+    call("colsum_bf16", colsum_args(X, out))
 
 
 def attn_args(qkv, ctx, lse, keybias, cu_seqlens, H, nheads, max_seqlen, dctx=None, dqkv=None, dsum=None,
               p_drop=0.0, seed=0, rng_stream=0):
-    return AttnArgs(_p(qkv), _p(ctx), _p(lse), _p(keybias), _p(cu_seqlens), _p(dctx), _p(dqkv), _p(dsum),
-                    H, nheads, cu_seqlens.numel() - 1, max_seqlen, qkv.shape[0], p_drop, seed, rng_stream)
+    return fill(AttnArgs(), qkv=qkv, ctx=ctx, lse=lse, keybias=keybias, cu_seqlens=cu_seqlens, dctx=dctx, dqkv=dqkv,
+                dsum=dsum, H=H, nheads=nheads, nseq=cu_seqlens.numel() - 1, max_seqlen=max_seqlen,
+                total_rows=qkv.shape[0], p_drop=p_drop, seed=seed, rng_stream=rng_stream)
+
+
+def cast_bf16(src, dst):
+    L = lib()
+    L.mmb_cast_bf16.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    check(L.mmb_cast_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), stream_ptr()), "mmb_cast_bf16")
+
+
+def transpose_f32(src, dst, R, C):
+    L = lib()
+    L.mmb_transpose_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    check(L.mmb_transpose_f32(src.data_ptr(), dst.data_ptr(), R, C, stream_ptr()), "mmb_transpose_f32")
+
+
+def heads_workspace_bytes(B, H):
+    L = lib()
+    L.mmb_heads_workspace_bytes.restype = ctypes.c_size_t
+    L.mmb_heads_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+    return L.mmb_heads_workspace_bytes(B, H)

@@ -1,0 +1,545 @@
+// Pooler, alignment / NSP heads, score-attention fusion, sentiment head, CPC and the loss combination,
+// forward and backward, on the 3B [CLS] rows of the packed batch.  Everything here is O(B * H^2) with B ~ 64
+// (< 0.1 % of the path's FLOPs), so it runs in fp32 on CUDA cores as a short fixed sequence of small kernels
+// launched from one C entry point (no host synchronisation, scratch in a caller-provided workspace).
+//
+// Replaces
+//   BertPooler.forward                modeling_bert.py:462-468
+//   MMBertPreTrainingHeads.forward    MMBertForPretraining.py:295-302 (align on seq[:,0]; seq_relationship on pooled)
+//   fusion / classifier               MMBertForPretraining.py:406-415
+//   CPC.forward x3                    MMBertEmbedding.py:21-32 (in-batch negatives)
+//   losses                            MMBertForPretraining.py:386-388 (AP CE), :427-443
+// and their autograd backward.
+#include "common.cuh"
+
+namespace mmb {
+
+enum { ACT_NONE = 0, ACT_TANH = 1, ACT_RELU = 2 };
+
+// Y[r][n] = act(sum_k X[r][k] W[n][k] + b[n]);   grid (ceil(N/8), ceil(R/8)), 8 warps: warp = one column, 8 rows
+__global__ void __launch_bounds__(256)
+sl_linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw, const float* __restrict__ b,
+                 float* __restrict__ Y, int ldy, int R, int N, int K, int act) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 8 + warp;
+    const int r0 = blockIdx.y * 8;
+    if (n >= N) return;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = lane; k < K; k += 32) {
+        const float w = __ldg(W + (size_t)n * ldw + k);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (r0 + i < R) acc[i] = fmaf(w, X[(size_t)(r0 + i) * ldx + k], acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
+    if (lane == 0) {
+        const float bias = b ? b[n] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (r0 + i < R) {
+                float v = acc[i] + bias;
+                if (act == ACT_TANH) v = tanhf(v);
+                else if (act == ACT_RELU) v = fmaxf(v, 0.f);
+                Y[(size_t)(r0 + i) * ldy + n] = v;
+            }
+        }
+    }
+}
+
+// dX[r][k] (+)= sum_n dY[r][n] W[n][k];   grid (ceil(K/256), ceil(R/8)); thread = one k, 8 rows
+__global__ void __launch_bounds__(256)
+sl_dx_kernel(const float* __restrict__ dY, int ldy, const float* __restrict__ W, int ldw, float* __restrict__ dX, int ldx,
+             int R, int N, int K, int accumulate) {
+    __shared__ float sdy[8][64];
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    const int r0 = blockIdx.y * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int n0 = 0; n0 < N; n0 += 64) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 8 * 64; i += 256) {
+            const int r = i >> 6, nn = i & 63;
+            sdy[r][nn] = (r0 + r < R && n0 + nn < N) ? dY[(size_t)(r0 + r) * ldy + n0 + nn] : 0.f;
+        }
+        __syncthreads();
+        if (k < K) {
+            const int nmax = min(64, N - n0);
+            for (int nn = 0; nn < nmax; ++nn) {
+                const float w = __ldg(W + (size_t)(n0 + nn) * ldw + k);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(sdy[i][nn], w, acc[i]);
+            }
+        }
+    }
+    if (k < K) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (r0 + i < R) {
+                float* d = dX + (size_t)(r0 + i) * ldx + k;
+                *d = accumulate ? *d + acc[i] : acc[i];
+            }
+        }
+    }
+}
+
+// dW[n][k] += sum_r dY[r][n] X[r][k];  db[n] += sum_r dY[r][n];   grid (ceil(K/256), N); thread = one k
+__global__ void __launch_bounds__(256)
+sl_dw_kernel(const float* __restrict__ dY, int ldy, const float* __restrict__ X, int ldx, float* __restrict__ dW, int ldw,
+             float* __restrict__ db, int R, int N, int K) {
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    const int n = blockIdx.y;
+    float acc = 0.f, bacc = 0.f;
+    for (int r = 0; r < R; ++r) {
+        const float g = dY[(size_t)r * ldy + n];
+        bacc += g;
+        if (k < K) acc = fmaf(g, X[(size_t)r * ldx + k], acc);
+    }
+    if (k < K) dW[(size_t)n * ldw + k] += acc;   // each (n,k) is owned by exactly one thread of this launch
+    if (db && k == 0) db[n] += bacc;
+}
+
+// ---------------------------------------------------------------- small fused elementwise kernels
+__global__ void gather_cls_kernel(const __nv_bfloat16* __restrict__ seq, const int* __restrict__ cu, float* __restrict__ X0,
+                                  int R, int H) {
+    const int r = blockIdx.x;
+    const __nv_bfloat16* src = seq + (size_t)cu[r] * H;
+    for (int j = threadIdx.x; j < H; j += blockDim.x) X0[(size_t)r * H + j] = __bfloat162float(src[j]);
+}
+__global__ void scatter_cls_grad_kernel(const float* __restrict__ dX0, const int* __restrict__ cu, __nv_bfloat16* __restrict__ g,
+                                        int R, int H) {
+    const int r = blockIdx.x;
+    __nv_bfloat16* dst = g + (size_t)cu[r] * H;
+    for (int j = threadIdx.x; j < H; j += blockDim.x)
+        dst[j] = __float2bfloat16_rn(__bfloat162float(dst[j]) + dX0[(size_t)r * H + j]);
+}
+__global__ void dup_cols_kernel(const float* __restrict__ P, float* __restrict__ PP, int R, int H) {  // PP = [P, P]
+    const int r = blockIdx.x;
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        const float v = P[(size_t)r * H + j];
+        PP[(size_t)r * 2 * H + j] = v;
+        PP[(size_t)r * 2 * H + H + j] = v;
+    }
+}
+struct VPtrs {  // per-modality score vectors (0 = vt, 1 = vv, 2 = vs) and their gradients
+    const float* w[3];
+    const float* b[3];
+    float* gw[3];
+    float* gb[3];
+};
+// s[r] = U[r] . v_m + b_m ; PC[b][m*H + j] = P[r][j] * s[r]      (r = m*B + b; m: 0 = vt, 1 = vv, 2 = vs)
+__global__ void __launch_bounds__(256)
+score_scale_kernel(const float* __restrict__ U, const float* __restrict__ P, const VPtrs vp, float* __restrict__ s,
+                   float* __restrict__ PC, int B, int H) {
+    __shared__ float red[8];
+    const int r = blockIdx.x, m = r / B, b = r - m * B;
+    const float* v = vp.w[m];
+    float acc = 0.f;
+    for (int j = threadIdx.x; j < H; j += 256) acc = fmaf(U[(size_t)r * H + j], v[j], acc);
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    tot += vp.b[m][0];
+    if (threadIdx.x == 0) s[r] = tot;
+    for (int j = threadIdx.x; j < H; j += 256) PC[(size_t)b * 3 * H + m * H + j] = P[(size_t)r * H + j] * tot;
+}
+// backward of the above: ds[r] = sum_j dPC[b][mH+j] P[r][j]; dP[r][j] += dPC * s[r]; dU[r][j] = ds v_m[j] (masked by U>0);
+// dv_m[j] += ds U[r][j]; dbv_m += ds
+__global__ void __launch_bounds__(256)
+score_scale_bwd_kernel(const float* __restrict__ dPC, const float* __restrict__ P, const float* __restrict__ U,
+                       const float* __restrict__ s, const VPtrs vp, float* __restrict__ dP, float* __restrict__ dA, int B,
+                       int H) {
+    __shared__ float red[8];
+    const int r = blockIdx.x, m = r / B, b = r - m * B;
+    float acc = 0.f;
+    for (int j = threadIdx.x; j < H; j += 256) acc = fmaf(dPC[(size_t)b * 3 * H + m * H + j], P[(size_t)r * H + j], acc);
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    float ds = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) ds += red[w];
+    const float sr = s[r];
+    const float* v = vp.w[m];
+    for (int j = threadIdx.x; j < H; j += 256) {
+        const size_t idx = (size_t)r * H + j;
+        dP[idx] += dPC[(size_t)b * 3 * H + m * H + j] * sr;
+        const float u = U[idx];
+        dA[idx] = u > 0.f ? ds * v[j] : 0.f;
+        atomicAdd(vp.gw[m] + j, ds * u);
+    }
+    if (threadIdx.x == 0) atomicAdd(vp.gb[m], ds);
+}
+
+// CPC forward for one modality: row i -> xn_i, an_i (unit vectors), softmax row Sm_i over G_ij = xn_i . an_j,
+// accumulates nce += -(pos_i - neg_i) / B.   Two kernels: normalise, then rows.
+__global__ void __launch_bounds__(256)
+normalize_rows_kernel(const float* __restrict__ X, float* __restrict__ Y, float* __restrict__ norms, int H) {
+    __shared__ float red[8];
+    const int r = blockIdx.x;
+    float acc = 0.f;
+    for (int j = threadIdx.x; j < H; j += 256) {
+        const float v = X[(size_t)r * H + j];
+        acc = fmaf(v, v, acc);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    const float nrm = sqrtf(tot);
+    if (threadIdx.x == 0) norms[r] = nrm;
+    for (int j = threadIdx.x; j < H; j += 256) Y[(size_t)r * H + j] = X[(size_t)r * H + j] / nrm;
+}
+// one CTA per row i; dynamic smem: B floats
+__global__ void __launch_bounds__(256)
+cpc_rows_kernel(const float* __restrict__ xn, const float* __restrict__ an, float* __restrict__ Sm, float* __restrict__ nce,
+                int B, int H) {
+    extern __shared__ float g[];
+    __shared__ float red[8];
+    const int i = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = warp; j < B; j += 8) {
+        float acc = 0.f;
+        for (int k = lane; k < H; k += 32) acc = fmaf(xn[(size_t)i * H + k], an[(size_t)j * H + k], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) g[j] = acc;
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int j = threadIdx.x; j < B; j += 256) mx = fmaxf(mx, g[j]);
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int j = threadIdx.x; j < B; j += 256) sum += expf(g[j] - mx);
+    sum = warp_sum(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w];
+    const float neg = mx + logf(sum);
+    for (int j = threadIdx.x; j < B; j += 256) Sm[(size_t)i * B + j] = expf(g[j] - neg);
+    if (threadIdx.x == 0) atomicAdd(nce, -(g[i] - neg) / (float)B);
+}
+// dG_ij = c * (delta_ij - Sm_ij)   (c = beta * gs / B);  in place over Sm
+__global__ void cpc_dg_kernel(float* __restrict__ Sm, const float* __restrict__ gscale, float beta, int B) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * B) return;
+    const float c = beta * (gscale ? *gscale : 1.f) / (float)B;
+    const int i = idx / B, j = idx - i * B;
+    Sm[idx] = c * ((i == j ? 1.f : 0.f) - Sm[idx]);
+}
+// dv = (dy - y (y . dy)) / ||v||   per row;  out (+)= dv
+__global__ void __launch_bounds__(256)
+normalize_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, const float* __restrict__ norms,
+                     float* __restrict__ out, int H, int accumulate) {
+    __shared__ float red[8];
+    const int r = blockIdx.x;
+    float acc = 0.f;
+    for (int j = threadIdx.x; j < H; j += 256) acc = fmaf(y[(size_t)r * H + j], dy[(size_t)r * H + j], acc);
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    float dot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) dot += red[w];
+    const float inv = 1.f / norms[r];
+    for (int j = threadIdx.x; j < H; j += 256) {
+        const size_t idx = (size_t)r * H + j;
+        const float v = (dy[idx] - y[idx] * dot) * inv;
+        out[idx] = accumulate ? out[idx] + v : v;
+    }
+}
+// G-shaped products for CPC backward: out[i][k] = sum_j M[i][j] Y[j][k]  (transpose = 0) or sum_j M[j][i] Y[j][k] (1)
+__global__ void __launch_bounds__(256)
+bb_matmul_kernel(const float* __restrict__ Mx, const float* __restrict__ Y, float* __restrict__ out, int B, int H, int transpose) {
+    const int i = blockIdx.x;
+    for (int k = threadIdx.x; k < H; k += 256) {
+        float acc = 0.f;
+        for (int j = 0; j < B; ++j) acc = fmaf(transpose ? Mx[(size_t)j * B + i] : Mx[(size_t)i * B + j], Y[(size_t)j * H + k], acc);
+        out[(size_t)i * H + k] = acc;
+    }
+}
+
+struct LossParams {
+    const float* al;          // [2B,2] alignment scores (visual rows then speech rows)
+    const long long* ap[2];   // [B] labels
+    const float* logit;       // [B] classifier output
+    const float* sentiment;   // [B]
+    const float* ce_loss_sum; // [3]
+    const int* label_count;   // [3]
+    const float* nce;         // [1]
+    float* losses;            // [8]: joint, mlm, ap, label, nce, mlm_t, mlm_v, mlm_s
+    float* logits_out;        // [B] (tanh applied iff num_labels == 1)
+    float* dal;               // [2B,2]  backward
+    float* dlogit;            // [B]     backward
+    const float* gscale;
+    float alpha, beta;
+    int B, num_labels;
+};
+// single CTA: AP cross entropies, MSE, loss combination (MMBertForPretraining.py:386-388, 427-443)
+__global__ void __launch_bounds__(256)
+final_losses_kernel(const LossParams p) {
+    __shared__ float red[8];
+    float ap_acc = 0.f, mse_acc = 0.f;
+    for (int i = threadIdx.x; i < 2 * p.B; i += 256) {
+        const int mod = i / p.B, b = i - mod * p.B;
+        const float a0 = p.al[2 * i], a1 = p.al[2 * i + 1];
+        const float mx = fmaxf(a0, a1);
+        const float lse = mx + logf(expf(a0 - mx) + expf(a1 - mx));
+        const long long lab = p.ap[mod][b];
+        ap_acc += (lse - (lab == 0 ? a0 : a1)) / (float)p.B;
+    }
+    for (int i = threadIdx.x; i < p.B; i += 256) {
+        float o = p.logit[i];
+        if (p.num_labels == 1) o = tanhf(o);
+        p.logits_out[i] = o;
+        const float d = o - p.sentiment[i];
+        mse_acc += d * d / (float)p.B;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ap_acc = warp_sum(ap_acc);
+    if (lane == 0) red[warp] = ap_acc;
+    __syncthreads();
+    float ap_tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) ap_tot += red[w];
+    __syncthreads();
+    mse_acc = warp_sum(mse_acc);
+    if (lane == 0) red[warp] = mse_acc;
+    __syncthreads();
+    float mse = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) mse += red[w];
+    if (threadIdx.x == 0) {
+        float mlm = 0.f;
+        for (int i = 0; i < 3; ++i) {
+            const float li = p.ce_loss_sum[i] / (float)p.label_count[i];  // NaN when a pass has no label, as the reference
+            p.losses[5 + i] = li;
+            mlm += li;
+        }
+        mlm /= 3.f;
+        const float ap = ap_tot * 0.5f, nce = p.nce[0];
+        p.losses[0] = p.alpha * mlm + ap + mse - p.beta * nce;
+        p.losses[1] = mlm;
+        p.losses[2] = ap;
+        p.losses[3] = mse;
+        p.losses[4] = nce;
+    }
+}
+__global__ void __launch_bounds__(256)
+final_losses_bwd_kernel(const LossParams p) {
+    const float gs = p.gscale ? *p.gscale : 1.f;
+    for (int i = threadIdx.x; i < 2 * p.B; i += 256) {
+        const int mod = i / p.B, b = i - mod * p.B;
+        const float a0 = p.al[2 * i], a1 = p.al[2 * i + 1];
+        const float mx = fmaxf(a0, a1);
+        const float e0 = expf(a0 - mx), e1 = expf(a1 - mx);
+        const float inv = 1.f / (e0 + e1);
+        const long long lab = p.ap[mod][b];
+        const float c = gs * 0.5f / (float)p.B;
+        p.dal[2 * i] = c * (e0 * inv - (lab == 0 ? 1.f : 0.f));
+        p.dal[2 * i + 1] = c * (e1 * inv - (lab == 1 ? 1.f : 0.f));
+    }
+    for (int i = threadIdx.x; i < p.B; i += 256) {
+        const float o = p.logits_out[i];
+        float d = gs * 2.f * (o - p.sentiment[i]) / (float)p.B;
+        if (p.num_labels == 1) d *= (1.f - o * o);
+        p.dlogit[i] = d;
+    }
+}
+__global__ void tanh_bwd_kernel(float* __restrict__ dP, const float* __restrict__ P, int n) {  // dZ = dP (1 - P^2), in place
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dP[i] *= (1.f - P[i] * P[i]);
+}
+__global__ void fold_dup_grad_kernel(const float* __restrict__ dPP, float* __restrict__ dP, int R, int H) {  // dP += dPP[:, :H] + dPP[:, H:]
+    const int r = blockIdx.x;
+    for (int j = threadIdx.x; j < H; j += blockDim.x)
+        dP[(size_t)r * H + j] += dPP[(size_t)r * 2 * H + j] + dPP[(size_t)r * 2 * H + H + j];
+}
+
+// ---------------------------------------------------------------- workspace layout (floats)
+struct HeadsWs {
+    size_t X0, P, PP, U, s, PC, temp, logit, XH, xn, an, nx, na, Sm, al, rel, nce, ptrs;
+    size_t dX0, dP, dPP, dA, dPC, dtemp, dlogit, dXH, dxn, dan, dal, total;
+};
+static HeadsWs heads_ws(int B, int H) {
+    HeadsWs w;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += (n + 3) / 4 * 4; return r; };
+    const size_t R = 3 * (size_t)B;
+    w.X0 = take(R * H); w.P = take(R * H); w.PP = take(R * 2 * H); w.U = take(R * H); w.s = take(R);
+    w.PC = take((size_t)B * 3 * H); w.temp = take((size_t)B * H); w.logit = take(B);
+    w.XH = take(3 * (size_t)B * H); w.xn = take(3 * (size_t)B * H); w.an = take(3 * (size_t)B * H);
+    w.nx = take(3 * (size_t)B); w.na = take(3 * (size_t)B); w.Sm = take(3 * (size_t)B * B);
+    w.al = take(4 * (size_t)B); w.rel = take(2 * (size_t)B); w.nce = take(4); w.ptrs = take(32);
+    w.dX0 = take(R * H); w.dP = take(R * H); w.dPP = take(R * 2 * H); w.dA = take(R * H);
+    w.dPC = take((size_t)B * 3 * H); w.dtemp = take((size_t)B * H); w.dlogit = take(B);
+    w.dXH = take((size_t)B * H); w.dxn = take((size_t)B * H); w.dan = take((size_t)B * H); w.dal = take(4 * (size_t)B);
+    w.total = o;
+    return w;
+}
+
+static inline void linear(cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy,
+                          int R, int N, int K, int act) {
+    dim3 g((N + 7) / 8, (R + 7) / 8);
+    sl_linear_kernel<<<g, 256, 0, st>>>(X, ldx, W, ldw, b, Y, ldy, R, N, K, act);
+}
+static inline void dx(cudaStream_t st, const float* dY, int ldy, const float* W, int ldw, float* dX, int ldx, int R, int N,
+                      int K, int accumulate) {
+    dim3 g((K + 255) / 256, (R + 7) / 8);
+    sl_dx_kernel<<<g, 256, 0, st>>>(dY, ldy, W, ldw, dX, ldx, R, N, K, accumulate);
+}
+static inline void dw(cudaStream_t st, const float* dY, int ldy, const float* X, int ldx, float* dW, int ldw, float* db, int R,
+                      int N, int K) {
+    dim3 g((K + 255) / 256, N);
+    sl_dw_kernel<<<g, 256, 0, st>>>(dY, ldy, X, ldx, dW, ldw, db, R, N, K);
+}
+
+}  // namespace mmb
+
+using namespace mmb;
+
+extern "C" size_t mmb_heads_workspace_bytes(int B, int H) { return heads_ws(B, H).total * sizeof(float); }
+
+static int heads_check(const mmb_heads_args* a) {
+    MMB_REQUIRE(a && a->seq_out && a->cu_seqlens && a->workspace && a->losses && a->logits_out, "heads: null pointer");
+    MMB_REQUIRE(a->B > 0 && a->H > 0, "heads: bad dims");
+    MMB_REQUIRE(a->w_pooler && a->b_pooler && a->w_align && a->b_align && a->w_attn && a->b_attn && a->w_c11 && a->b_c11 &&
+                    a->w_c12 && a->b_c12 && a->ap_label[0] && a->ap_label[1] && a->sentiment && a->ce_loss_sum &&
+                    a->label_count,
+                "heads: null parameter");
+    for (int m = 0; m < 3; ++m) MMB_REQUIRE(a->w_v[m] && a->b_v[m] && a->w_cpc[m] && a->b_cpc[m], "heads: null v/cpc %d", m);
+    return MMB_OK;
+}
+
+static VPtrs vptrs(const mmb_heads_args* a) {
+    VPtrs v;
+    for (int m = 0; m < 3; ++m) {
+        v.w[m] = a->w_v[m];
+        v.b[m] = a->b_v[m];
+        v.gw[m] = a->g_w_v[m];
+        v.gb[m] = a->g_b_v[m];
+    }
+    return v;
+}
+
+static LossParams loss_params(const mmb_heads_args* a, float* ws, const HeadsWs& w) {
+    LossParams lp;
+    lp.al = ws + w.al;
+    lp.ap[0] = (const long long*)a->ap_label[0];
+    lp.ap[1] = (const long long*)a->ap_label[1];
+    lp.logit = ws + w.logit;
+    lp.sentiment = a->sentiment;
+    lp.ce_loss_sum = a->ce_loss_sum;
+    lp.label_count = a->label_count;
+    lp.nce = ws + w.nce;
+    lp.losses = a->losses;
+    lp.logits_out = a->logits_out;
+    lp.dal = ws + w.dal;
+    lp.dlogit = ws + w.dlogit;
+    lp.gscale = a->gscale;
+    lp.alpha = a->alpha;
+    lp.beta = a->beta;
+    lp.B = a->B;
+    lp.num_labels = a->num_labels;
+    return lp;
+}
+
+extern "C" int mmb_heads_fwd(const mmb_heads_args* a, void* stream) {
+    int rc = heads_check(a);
+    if (rc != MMB_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = a->B, H = a->H, R = 3 * B;
+    const HeadsWs w = heads_ws(B, H);
+    float* ws = (float*)a->workspace;
+    const VPtrs vp = vptrs(a);
+
+    gather_cls_kernel<<<R, 256, 0, st>>>((const __nv_bfloat16*)a->seq_out, a->cu_seqlens, ws + w.X0, R, H);
+    linear(st, ws + w.X0, H, a->w_pooler, H, a->b_pooler, ws + w.P, H, R, H, H, ACT_TANH);
+    if (a->w_seqrel && a->b_seqrel) linear(st, ws + w.P, H, a->w_seqrel, H, a->b_seqrel, ws + w.rel, 2, B, 2, H, ACT_NONE);
+    linear(st, ws + w.X0 + (size_t)B * H, H, a->w_align, H, a->b_align, ws + w.al, 2, 2 * B, 2, H, ACT_NONE);
+    dup_cols_kernel<<<R, 256, 0, st>>>(ws + w.P, ws + w.PP, R, H);
+    linear(st, ws + w.PP, 2 * H, a->w_attn, 2 * H, a->b_attn, ws + w.U, H, R, H, 2 * H, ACT_RELU);
+    score_scale_kernel<<<R, 256, 0, st>>>(ws + w.U, ws + w.P, vp, ws + w.s, ws + w.PC, B, H);
+    linear(st, ws + w.PC, 3 * H, a->w_c11, 3 * H, a->b_c11, ws + w.temp, H, B, H, 3 * H, ACT_NONE);
+    linear(st, ws + w.temp, H, a->w_c12, H, a->b_c12, ws + w.logit, 1, B, 1, H, ACT_NONE);
+    MMB_CUDA(cudaMemsetAsync(ws + w.nce, 0, 4 * sizeof(float), st));
+    for (int m = 0; m < 3; ++m) {
+        float* XH = ws + w.XH + (size_t)m * B * H;
+        float* xn = ws + w.xn + (size_t)m * B * H;
+        float* an = ws + w.an + (size_t)m * B * H;
+        linear(st, ws + w.temp, H, a->w_cpc[m], H, a->b_cpc[m], XH, H, B, H, H, ACT_NONE);
+        normalize_rows_kernel<<<B, 256, 0, st>>>(XH, an, ws + w.na + (size_t)m * B, H);
+        normalize_rows_kernel<<<B, 256, 0, st>>>(ws + w.P + (size_t)m * B * H, xn, ws + w.nx + (size_t)m * B, H);
+        cpc_rows_kernel<<<B, 256, B * sizeof(float), st>>>(xn, an, ws + w.Sm + (size_t)m * B * B, ws + w.nce, B, H);
+    }
+    LossParams lp = loss_params(a, ws, w);
+    final_losses_kernel<<<1, 256, 0, st>>>(lp);
+    // user-visible score outputs
+    if (a->rel_out) MMB_CUDA(cudaMemcpyAsync(a->rel_out, ws + w.rel, 2 * B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (a->align_out) MMB_CUDA(cudaMemcpyAsync(a->align_out, ws + w.al, 4 * B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return check_launch("heads_fwd");
+}
+
+extern "C" int mmb_heads_bwd(const mmb_heads_args* a, void* stream) {
+    int rc = heads_check(a);
+    if (rc != MMB_OK) return rc;
+    MMB_REQUIRE(a->dseq_out && a->g_w_pooler && a->g_b_pooler && a->g_w_align && a->g_b_align && a->g_w_attn && a->g_b_attn &&
+                    a->g_w_c11 && a->g_b_c11 && a->g_w_c12 && a->g_b_c12,
+                "heads_bwd: null gradient pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = a->B, H = a->H, R = 3 * B;
+    const HeadsWs w = heads_ws(B, H);
+    float* ws = (float*)a->workspace;
+    const VPtrs vp = vptrs(a);
+    LossParams lp = loss_params(a, ws, w);
+
+    MMB_CUDA(cudaMemsetAsync(ws + w.dP, 0, (size_t)R * H * sizeof(float), st));
+    MMB_CUDA(cudaMemsetAsync(ws + w.dX0, 0, (size_t)R * H * sizeof(float), st));
+    final_losses_bwd_kernel<<<1, 256, 0, st>>>(lp);
+    // classifier1_2
+    dx(st, ws + w.dlogit, 1, a->w_c12, H, ws + w.dtemp, H, B, 1, H, 0);
+    dw(st, ws + w.dlogit, 1, ws + w.temp, H, a->g_w_c12, H, a->g_b_c12, B, 1, H);
+    // CPC x3 (joint loss has -beta * nce)
+    for (int m = 0; m < 3; ++m) {
+        MMB_REQUIRE(a->g_w_cpc[m] && a->g_b_cpc[m] && a->g_w_v[m] && a->g_b_v[m], "heads_bwd: null cpc/v grads");
+        float* Sm = ws + w.Sm + (size_t)m * B * B;
+        const float* xn = ws + w.xn + (size_t)m * B * H;
+        const float* an = ws + w.an + (size_t)m * B * H;
+        cpc_dg_kernel<<<(B * B + 255) / 256, 256, 0, st>>>(Sm, a->gscale, a->beta, B);          // Sm <- dG
+        bb_matmul_kernel<<<B, 256, 0, st>>>(Sm, an, ws + w.dxn, B, H, 0);                          // dXn = dG An
+        bb_matmul_kernel<<<B, 256, 0, st>>>(Sm, xn, ws + w.dan, B, H, 1);                          // dAn = dG^T Xn
+        normalize_bwd_kernel<<<B, 256, 0, st>>>(xn, ws + w.dxn, ws + w.nx + (size_t)m * B, ws + w.dP + (size_t)m * B * H, H, 1);
+        normalize_bwd_kernel<<<B, 256, 0, st>>>(an, ws + w.dan, ws + w.na + (size_t)m * B, ws + w.dXH, H, 0);
+        dx(st, ws + w.dXH, H, a->w_cpc[m], H, ws + w.dtemp, H, B, H, H, 1);
+        dw(st, ws + w.dXH, H, ws + w.temp, H, a->g_w_cpc[m], H, a->g_b_cpc[m], B, H, H);
+    }
+    // classifier1_1
+    dx(st, ws + w.dtemp, H, a->w_c11, 3 * H, ws + w.dPC, 3 * H, B, H, 3 * H, 0);
+    dw(st, ws + w.dtemp, H, ws + w.PC, 3 * H, a->g_w_c11, 3 * H, a->g_b_c11, B, H, 3 * H);
+    // score scaling, v_m, relu
+    score_scale_bwd_kernel<<<R, 256, 0, st>>>(ws + w.dPC, ws + w.P, ws + w.U, ws + w.s, vp, ws + w.dP, ws + w.dA, B, H);
+    // attn Linear on [P, P]
+    dx(st, ws + w.dA, H, a->w_attn, 2 * H, ws + w.dPP, 2 * H, R, H, 2 * H, 0);
+    dw(st, ws + w.dA, H, ws + w.PP, 2 * H, a->g_w_attn, 2 * H, a->g_b_attn, R, H, 2 * H);
+    fold_dup_grad_kernel<<<R, 256, 0, st>>>(ws + w.dPP, ws + w.dP, R, H);
+    // pooler: P = tanh(X0 Wp^T + bp)
+    tanh_bwd_kernel<<<(R * H + 255) / 256, 256, 0, st>>>(ws + w.dP, ws + w.P, R * H);
+    dx(st, ws + w.dP, H, a->w_pooler, H, ws + w.dX0, H, R, H, H, 1);
+    dw(st, ws + w.dP, H, ws + w.X0, H, a->g_w_pooler, H, a->g_b_pooler, R, H, H);
+    // align on seq[:,0] of the two joint passes
+    dx(st, ws + w.dal, 2, a->w_align, H, ws + w.dX0 + (size_t)B * H, H, 2 * B, 2, H, 1);
+    dw(st, ws + w.dal, 2, ws + w.X0 + (size_t)B * H, H, a->g_w_align, H, a->g_b_align, 2 * B, 2, H);
+    // add into the gradient of the encoder output at the [CLS] rows
+    scatter_cls_grad_kernel<<<R, 256, 0, st>>>(ws + w.dX0, a->cu_seqlens, (__nv_bfloat16*)a->dseq_out, R, H);
+    return check_launch("heads_bwd");
+}

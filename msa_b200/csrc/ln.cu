@@ -50,8 +50,8 @@ drln_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __res
                 const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ res,
                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
                 __nv_bfloat16* __restrict__ d_y, __nv_bfloat16* __restrict__ d_res, float* __restrict__ dgamma,
-                float* __restrict__ dbeta, float* __restrict__ dbias, int M, int H, uint32_t thresh, float inv_keep,
-                uint64_t seed, uint32_t stream) {
+                float* __restrict__ dbeta, float* __restrict__ dbias, const __nv_bfloat16* __restrict__ gelu_aux, int M,
+                int H, uint32_t thresh, float inv_keep, uint64_t seed, uint32_t stream) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nw = gridDim.x * kLnWarps;
@@ -96,6 +96,14 @@ drln_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __res
                         g.v[c][i] = rng_keep(seed, stream, (uint64_t)row * H + e + i, thresh) ? g.v[c][i] * inv_keep : 0.f;
                 }
             }
+        }
+        if (gelu_aux != nullptr) {  // y = gelu(aux): chain through the activation (LM-head transform, :482-484)
+            RowF<NCH> u;
+            row_load_bf16(u, gelu_aux + (size_t)row * H, H, lane);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g.v[c][i] *= gelu_erf_grad(u.v[c][i]);
         }
         row_round_bf16(g);  // the bias gradient sums exactly what the wgrad GEMM will read
         row_store_bf16(g, d_y + (size_t)row * H, H, lane);
@@ -168,8 +176,8 @@ extern "C" int mmb_dropout_residual_ln_bwd(const mmb_drln_bwd_args* a, void* str
     MMB_DISPATCH_NCH(a->H, (drln_bwd_kernel<NCH><<<grid, kLnWarps * 32, smem, (cudaStream_t)stream>>>(
                                (const __nv_bfloat16*)a->g1, (const __nv_bfloat16*)a->g2, (const __nv_bfloat16*)a->y,
                                (const __nv_bfloat16*)a->res, a->mean, a->rstd, a->gamma, (__nv_bfloat16*)a->d_y,
-                               (__nv_bfloat16*)a->d_res, a->dgamma, a->dbeta, a->dbias, a->M, a->H, thresh, inv_keep,
-                               a->seed, a->rng_stream)));
+                               (__nv_bfloat16*)a->d_res, a->dgamma, a->dbeta, a->dbias,
+                               (const __nv_bfloat16*)a->gelu_aux, a->M, a->H, thresh, inv_keep, a->seed, a->rng_stream)));
     return check_launch("drln_bwd_kernel");
 }
 

@@ -1,0 +1,168 @@
+"""Whole-path parity on the B200: msa_b200.api.MMBertForPretraining (CUDA kernels through the C ABI) against
+  (1) the committed golden vectors produced by the unmodified reference, and
+  (2) the CPU oracle (oracle/mmbert_oracle.py, fp64) on seeded inputs at bert-base width.
+Tolerances are BASELINE.json's for the bf16 path: 2e-2 relative on logits / scores / losses
+(relative = max|a-b| / max|b|).  Gradients: 5e-2 relative per tensor (bf16 activations and gradients)."""
+import copy
+
+import pytest
+import torch
+
+from msa_b200 import synth
+from msa_b200.params import NO_GRAD, seeded_state_dict
+from oracle import mmbert_oracle as O
+from tests.helpers import GOLDEN, OUT_NAMES, expand_recipe, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL_OUT, TOL_GRAD = 2e-2, 5e-2
+
+
+def _cfg(ocfg, p_drop=0.0):
+    c = copy.copy(ocfg)
+    c.hidden_dropout_prob = p_drop
+    c.attention_probs_dropout_prob = p_drop
+    c.initializer_range = 0.02
+    return c
+
+
+def _build(ocfg, dataset, sd, p_drop=0.0, p_joint=0.0):
+    from msa_b200.api import MMBertForPretraining
+    m = MMBertForPretraining(_cfg(ocfg, p_drop))
+    m.bert.set_joint_embeddings(dataset)
+    m.bert.jointEmbeddings.dropout.p = p_joint
+    m.load_state_dict(sd, strict=True)
+    return m.cuda()
+
+
+def _check_outputs(out, logits, ref_out, ref_logits):
+    for n, a, b in zip(OUT_NAMES, out, ref_out):
+        if b is None:
+            assert a is None
+            continue
+        assert tuple(a.shape) == tuple(b.shape), n
+        assert rel_err(a.float(), b) < TOL_OUT, (n, rel_err(a.float(), b))
+    assert rel_err(logits.float(), ref_logits) < TOL_OUT
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_forward_backward(name):
+    recipe, g = load_golden(name)
+    ocfg, sd, batch = expand_recipe(recipe)
+    m = _build(ocfg, recipe["dataset"], sd)
+    m.set_alpha_beta(recipe["alpha"], recipe["beta"])
+    dbatch = synth.tree_to(batch, "cuda")
+    m.eval()
+    with torch.no_grad():
+        out, logits = m(**dbatch)
+    ref_out = [None if n is None else g["eval." + n] for n in OUT_NAMES]
+    _check_outputs(out, logits, ref_out, g["eval.logits"])
+    m.train()
+    out, logits = m(**dbatch)
+    assert rel_err(out[0].detach().float(), g["train.joint_loss"]) < TOL_OUT
+    out[0].mean().backward()
+    torch.cuda.synchronize()
+    none = sorted(n for n, p in m.named_parameters() if p.grad is None)
+    assert none == sorted(recipe["none_grads"])
+    worst = {}
+    for n, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        worst[n] = rel_err(p.grad, g["grad." + n], floor=1e-4)
+    bad = {k: v for k, v in worst.items() if not v < TOL_GRAD}
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]
+
+
+def test_oracle_parity_bert_base_width():
+    """hidden 768 / 12 heads / intermediate 3072 / full 30522 vocabulary, 2 layers, MOSI dims, unaligned frames."""
+    ocfg = O.Cfg(num_hidden_layers=2)
+    sd = seeded_state_dict(ocfg, "mosi", seed=5)
+    batch = synth.make_batch(3, 20, 33, 20, 47, 74, seed=17, min_len=5)
+    m = _build(ocfg, "mosi", sd)
+    m.set_alpha_beta(0.5, 0.25)
+    m.train()
+    out, logits = m(**synth.tree_to(batch, "cuda"))
+    out[0].backward()
+    ref_out, ref_logits, ref_grads = O.forward_backward(sd, ocfg, batch, alpha=0.5, beta=0.25)
+    _check_outputs(out, logits, [None if o is None else o.detach() for o in ref_out], ref_logits.detach())
+    bad = {}
+    for n, p in m.named_parameters():
+        if n in NO_GRAD:
+            assert p.grad is None, n
+            continue
+        e = rel_err(p.grad, ref_grads[n], floor=1e-4)
+        if not e < TOL_GRAD:
+            bad[n] = e
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]
+
+
+def test_grad_accumulation_and_zero_grad():
+    """Two backward passes accumulate (PyTorch semantics); zero_grad(set_to_none=True) restarts from zero."""
+    recipe, _ = load_golden(GOLDEN[0])
+    ocfg, sd, batch = expand_recipe(recipe)
+    m = _build(ocfg, recipe["dataset"], sd).train()
+    dbatch = synth.tree_to(batch, "cuda")
+    m(**dbatch)[0][0].backward()
+    g1 = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    m(**dbatch)[0][0].backward()
+    for n, p in m.named_parameters():
+        if p.grad is not None:
+            assert rel_err(p.grad, 2 * g1[n], floor=1e-5) < 1e-2, n
+    for p in m.parameters():
+        p.grad = None
+    m(**dbatch)[0][0].backward()
+    for n, p in m.named_parameters():
+        if p.grad is not None:
+            assert rel_err(p.grad, g1[n], floor=1e-5) < 1e-2, n
+
+
+def test_training_with_dropout_is_finite_and_learns():
+    """Reference dropout rates (0.1 / 0.1 / 0.5): loss and gradients finite; a few fused-AdamW steps on one batch
+    reduce the loss (HF AdamW semantics, msa_b200.optim.FusedAdamW)."""
+    from msa_b200.optim import FusedAdamW
+    ocfg = O.Cfg(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256, vocab_size=512,
+                 max_position_embeddings=64)
+    sd = seeded_state_dict(ocfg, "mosei", seed=9, std=0.02)
+    m = _build(ocfg, "mosei", sd, p_drop=0.1, p_joint=0.5).train()
+    batch = synth.tree_to(synth.make_batch(8, 16, 40, 40, 35, 74, vocab_size=512, seed=3, min_len=5), "cuda")
+    opt = FusedAdamW(m, lr=1e-3)
+    losses = []
+    for _ in range(12):
+        out, _ = m(**batch)
+        out[0].mean().backward()
+        opt.step()
+        opt.zero_grad()
+        losses.append(float(out[0]))
+    assert all(l == l and abs(l) < 1e4 for l in losses), losses
+    assert losses[-1] < losses[0], losses
+
+
+def test_fused_adamw_matches_hf_rule():
+    """One step of mmb_adamw vs a plain torch restatement of transformers(<=4.x).AdamW.step."""
+    from msa_b200 import capi
+    torch.manual_seed(0)
+    n = 4096
+    p, g = torch.randn(n, device="cuda"), torch.randn(n, device="cuda")
+    m, v = torch.rand(n, device="cuda") * 0.1, torch.rand(n, device="cuda") * 0.01
+    lr, b1, b2, eps, wd, t = 5e-4, 0.9, 0.999, 1e-6, 0.01, 7
+    m_ref = m * b1 + (1 - b1) * g
+    v_ref = v * b2 + (1 - b2) * g * g
+    step = lr * (1 - b2 ** t) ** 0.5 / (1 - b1 ** t)
+    p_ref = p - step * m_ref / (v_ref.sqrt() + eps)
+    p_ref = p_ref - lr * wd * p_ref
+    pb = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    capi.call("adamw", capi.fill(capi.AdamwArgs(), p=p, g=g, m=m, v=v, p_bf16=pb, n=n, lr=lr, beta1=b1, beta2=b2, eps=eps,
+                                 weight_decay=wd, grad_scale=1.0, step=t, correct_bias=1))
+    assert rel_err(p, p_ref) < 1e-6 and rel_err(m, m_ref) < 1e-6 and rel_err(v, v_ref) < 1e-6
+    assert rel_err(pb.float(), p_ref) < 2 ** -8
+
+
+def test_missing_library_or_cpu_model_fails_loudly():
+    from msa_b200 import capi
+    from msa_b200.api import MMBertForPretraining
+    ocfg = O.Cfg(hidden_size=128, num_hidden_layers=1, num_attention_heads=2, intermediate_size=256, vocab_size=256,
+                 max_position_embeddings=32)
+    m = MMBertForPretraining(_cfg(ocfg))
+    m.bert.set_joint_embeddings("mosi")
+    batch = synth.make_batch(2, 8, 8, 8, 47, 74, vocab_size=256, seed=1, min_len=4)
+    with pytest.raises(capi.MMBError):
+        m(**batch)       # CPU model: no fallback
