@@ -40,6 +40,9 @@ int mmb_version(void);
 const char* mmb_last_error(void);
 /* MMB_OK when the current device is compute capability 10.x, MMB_EARCH otherwise. */
 int mmb_check_device(void);
+/* Number of CUDA kernels this library has launched in the calling process (monotonic; bench.py reports the
+ * per-step difference as gpu_launches). */
+long long mmb_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense bf16 GEMM on tcgen05 tensor cores (TMA -> smem ring -> tcgen05.mma -> TMEM -> epilogue).

@@ -90,7 +90,7 @@ def _parse_header(path=HEADER_PATH):
                 ctype = ctypes.c_void_p if is_ptr else _SCALARS[base]
                 fields.append((name, ctype * count if count else ctype))
         structs[m.group(3)] = fields
-    funcs = re.findall(r"^\s*(?:int|size_t|const char\*)\s+(mmb_\w+)\s*\(", src, flags=re.M)
+    funcs = re.findall(r"^\s*(?:int|size_t|long long|const char\*)\s+(mmb_\w+)\s*\(", src, flags=re.M)
     return structs, funcs
 
 
@@ -203,6 +203,12 @@ def transpose_f32(src, dst, R, C):
     L = lib()
     L.mmb_transpose_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     check(L.mmb_transpose_f32(src.data_ptr(), dst.data_ptr(), R, C, stream_ptr()), "mmb_transpose_f32")
+
+
+def launch_count():
+    L = lib()
+    L.mmb_launch_count.restype = ctypes.c_longlong
+    return L.mmb_launch_count()
 
 
 def heads_workspace_bytes(B, H):

@@ -13,7 +13,7 @@ namespace mmb {
 
 // ------------------------------------------------------------------ error plumbing (host)
 void set_last_error(const char* fmt, ...);
-int check_launch(const char* what);  // returns MMB_OK / MMB_ECUDA after a kernel launch
+int check_launch(const char* what, int kernels = 1);  // MMB_OK / MMB_ECUDA after kernel launch(es); counts them
 
 #define MMB_REQUIRE(cond, ...)                                   \
     do {                                                         \

@@ -487,7 +487,7 @@ extern "C" int mmb_heads_fwd(const mmb_heads_args* a, void* stream) {
     // user-visible score outputs
     if (a->rel_out) MMB_CUDA(cudaMemcpyAsync(a->rel_out, ws + w.rel, 2 * B * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (a->align_out) MMB_CUDA(cudaMemcpyAsync(a->align_out, ws + w.al, 4 * B * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    return check_launch("heads_fwd");
+    return check_launch("heads_fwd", 21);
 }
 
 extern "C" int mmb_heads_bwd(const mmb_heads_args* a, void* stream) {
@@ -541,5 +541,5 @@ extern "C" int mmb_heads_bwd(const mmb_heads_args* a, void* stream) {
     dw(st, ws + w.dal, 2, ws + w.X0 + (size_t)B * H, H, a->g_w_align, H, a->g_b_align, 2 * B, 2, H);
     // add into the gradient of the encoder output at the [CLS] rows
     scatter_cls_grad_kernel<<<R, 256, 0, st>>>(ws + w.dX0, a->cu_seqlens, (__nv_bfloat16*)a->dseq_out, R, H);
-    return check_launch("heads_bwd");
+    return check_launch("heads_bwd", 36);
 }

@@ -1,6 +1,8 @@
 // Library-wide host plumbing: thread-local error string, device checks, version.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace mmb {
@@ -14,7 +16,10 @@ void set_last_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-int check_launch(const char* what) {
+static std::atomic<long long> g_launches{0};
+
+int check_launch(const char* what, int kernels) {
+    g_launches.fetch_add(kernels, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_last_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -36,6 +41,7 @@ int num_sms() {
 
 }  // namespace mmb
 
+extern "C" long long mmb_launch_count(void) { return mmb::g_launches.load(std::memory_order_relaxed); }
 extern "C" int mmb_version(void) { return MMB_VERSION; }
 extern "C" const char* mmb_last_error(void) { return mmb::g_err; }
 extern "C" int mmb_check_device(void) {

@@ -1,0 +1,107 @@
+"""Data-parallel gradient exchange for the MMBert step: one process per GPU, one SUM
+all-reduce of the gradient per step over NCCL (NVLink 5 / NVSwitch), bucketed and overlapped with backward.
+
+The reference has no distributed code.  Semantics are PyTorch-DDP semantics: every rank runs the packed step
+on its own micro-batch (per-rank CE means, per-rank in-batch CPC negatives) and the parameter gradients are
+averaged; the 1/world factor is folded into the fused AdamW (``FusedAdamW.grad_scale``).
+
+Why the overlap is simple here: the three reference passes are packed into ONE backward sweep, so layer l's
+weight gradients are final the moment its last wgrad GEMM is enqueued — that launch index triggers the
+bucket's all-reduce on NCCL's stream while the compute stream continues with layer l-1.  The wgrad epilogues
+accumulate straight into the flat gradient buffer (msa_b200.store.FlatStore), so a bucket is a contiguous
+slice of that buffer: nothing is copied or re-packed before the collective.
+
+Params without gradient (W_cv, W_cs, cls.seq_relationship) live outside [0, trainable_end) and are never sent.
+"""
+import torch
+import torch.distributed as dist
+
+
+def bucket_schedule(store, num_layers):
+    """Returns [(trigger, [(start, end), ...]), ...] in backward order.  trigger is 'heads', ('layer', l) or
+    'final'; the ranges are element offsets into the flat gradient buffer and partition [0, trainable_end)."""
+    off = store.offsets
+    first_layer = off["bert.encoder.layer.0.attention.self.query.weight"]
+    pooler = off["bert.pooler.dense.weight"]
+    transform = off["cls.predictions.transform.dense.weight"]
+    sched = [("heads", [(transform, store.decay_end)])]
+    for l in range(num_layers - 1, -1, -1):
+        a = off[f"bert.encoder.layer.{l}.attention.self.query.weight"]
+        b = off[f"bert.encoder.layer.{l + 1}.attention.self.query.weight"] if l + 1 < num_layers else pooler
+        sched.append((("layer", l), [(a, b)]))
+    # embeddings (tied decoder gradient + scatter-add finish last), pooler + frame projections, all biases / LayerNorms
+    sched.append(("final", [(0, first_layer), (pooler, transform), (store.decay_end, store.trainable_end)]))
+    return sched
+
+
+def check_partition(sched, trainable_end):
+    """True when the scheduled ranges tile [0, trainable_end) exactly once."""
+    ranges = sorted(r for _, rs in sched for r in rs)
+    pos = 0
+    for a, b in ranges:
+        if a != pos or b <= a:
+            return False
+        pos = b
+    return pos == trainable_end
+
+
+class GradReducer:
+    """Issues the bucketed all-reduces.  ``attach(model)`` wires it into MMBertForPretraining's backward."""
+
+    def __init__(self, store, num_layers, process_group=None):
+        self.store = store
+        self.group = process_group
+        self.sched = bucket_schedule(store, num_layers)
+        assert check_partition(self.sched, store.trainable_end)
+        self.pending = []
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.bytes_per_step = 4 * store.trainable_end
+
+    def reduce_bucket(self, ranges):
+        if self.world == 1:
+            return
+        for a, b in ranges:
+            self.pending.append(dist.all_reduce(self.store.grad[a:b], op=dist.ReduceOp.SUM, group=self.group,
+                                                async_op=True))
+
+    def finish(self):
+        """Makes the current stream wait for every outstanding collective (no host synchronisation on NCCL)."""
+        for w in self.pending:
+            w.wait()
+        self.pending = []
+
+    def hooks_for(self, plan):
+        """launch index in plan.bwd -> callable.  Triggers: the heads_bwd launch, each layer's last wgrad launch."""
+        import ctypes
+        hooks = {}
+        lib_heads = plan._fn("heads_bwd")
+        gemm = plan._fn("gemm")
+        heads_idx = next(i for i, (fn, _) in enumerate(plan.bwd) if fn is lib_heads)
+        by_trigger = dict((t, r) for t, r in self.sched)
+        hooks[heads_idx] = lambda r=by_trigger["heads"]: self.reduce_bucket(r)
+        # each layer's backward ends with the fused-QKV wgrad GEMM: C == grad view of that layer's query weight
+        for l in range(plan.N):
+            gq = self.store.view(f"bert.encoder.layer.{l}.attention.self.query.weight", self.store.grad).data_ptr()
+            idx = next(i for i, (fn, a) in enumerate(plan.bwd) if fn is gemm and a.C == gq)
+            hooks[idx] = lambda r=by_trigger[("layer", l)]: self.reduce_bucket(r)
+        hooks[len(plan.bwd) - 1] = lambda r=by_trigger["final"]: self.reduce_bucket(r)
+        return hooks
+
+    def attach(self, model):
+        cache = {}
+
+        def hooks(plan):
+            if id(plan) not in cache:
+                cache[id(plan)] = self.hooks_for(plan)
+            return cache[id(plan)]
+
+        model._bwd_hooks = hooks
+        model._post_backward = self.finish
+        return self
+
+
+def broadcast_parameters(model, src=0, process_group=None):
+    """Rank ``src``'s flat parameter buffer to every rank (one collective)."""
+    if dist.is_initialized() and dist.get_world_size(process_group) > 1:
+        dist.broadcast(model._store.flat, src=src, group=process_group)
+        model._store._bf16_version = -1

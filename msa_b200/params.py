@@ -102,3 +102,42 @@ def seeded_state_dict(cfg, dataset, seed=0, std=0.05):
     for alias, canon in TIED.items():
         sd[alias] = sd[canon]
     return sd
+
+
+class BertShape:
+    """The BertConfig fields the path reads (defaults = bert-base-uncased, the reference's model).  Any object
+    with these attributes — e.g. ``transformers.BertConfig`` — can be passed to MMBertForPretraining instead."""
+
+    def __init__(self, hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
+                 vocab_size=30522, max_position_embeddings=512, type_vocab_size=2, layer_norm_eps=1e-12,
+                 hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, initializer_range=0.02):
+        self.hidden_size = hidden_size
+        self.num_hidden_layers = num_hidden_layers
+        self.num_attention_heads = num_attention_heads
+        self.intermediate_size = intermediate_size
+        self.vocab_size = vocab_size
+        self.max_position_embeddings = max_position_embeddings
+        self.type_vocab_size = type_vocab_size
+        self.layer_norm_eps = layer_norm_eps
+        self.hidden_dropout_prob = hidden_dropout_prob
+        self.attention_probs_dropout_prob = attention_probs_dropout_prob
+        self.initializer_range = initializer_range
+
+
+def forward_gflop_per_sample(shape, T, Lv, La, Dv, Da):
+    """Algorithmic forward GFLOP of ONE sample (= the reference's three passes), dense-faithful: SURVEY.md §8d."""
+    H, I, V, N = shape.hidden_size, shape.intermediate_size, shape.vocab_size, shape.num_hidden_layers
+    passes = (T, T + Lv, T + La)
+    tok = sum(passes)
+    enc = N * tok * (8 * H * H + 4 * H * I)
+    attn = N * sum(4 * S * S * H for S in passes)
+    mlm = tok * (2 * H * H + 2 * H * V)
+    proj = 2 * H * (Lv * Dv + La * Da)
+    small = 30 * H * H + 20 * H
+    return (enc + attn + mlm + proj + small) / 1e9
+
+
+def train_gflop_per_sample(shape, workload):
+    """train = 3 x forward (backward = 2 x forward, no recompute credit)."""
+    dv, da = workload.dims
+    return 3.0 * forward_gflop_per_sample(shape, workload.T, workload.Lv, workload.La, dv, da)

@@ -125,6 +125,16 @@ def tree_to(obj, device, non_blocking=False):
     return obj
 
 
+def tree_map(fn, obj):
+    if torch.is_tensor(obj):
+        return fn(obj)
+    if isinstance(obj, tuple):
+        return tuple(tree_map(fn, o) for o in obj)
+    if isinstance(obj, dict):
+        return {k: tree_map(fn, v) for k, v in obj.items()}
+    return obj
+
+
 def tree_bytes(obj):
     if torch.is_tensor(obj):
         return obj.numel() * obj.element_size()
