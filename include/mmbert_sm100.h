@@ -94,11 +94,12 @@ int mmb_gemm(const mmb_gemm_args* a, void* stream);
  * (seed, rng_stream, row * H + col): backward regenerates them, nothing is stored.
  */
 typedef struct mmb_drln_fwd_args {
-    const void* y;   /* [M,H] bf16 dense output (bias included) */
-    const void* res; /* [M,H] bf16 residual or NULL */
+    const void* y;    /* [M,H] bf16 dense output (bias included) */
+    const float* res; /* [M,H] f32 residual stream or NULL */
     const float* gamma;
     const float* beta;
-    void* out;   /* [M,H] bf16 */
+    void* out;      /* [M,H] bf16 (GEMM operand copy) */
+    float* out_f32; /* [M,H] f32 residual-stream copy, or NULL */
     float* mean; /* [M] */
     float* rstd; /* [M] */
     int32_t M, H;
@@ -116,15 +117,15 @@ int mmb_dropout_residual_ln_fwd(const mmb_drln_fwd_args* a, void* stream);
  * multiplied by gelu'(aux) so that it is the gradient of the dense output.
  */
 typedef struct mmb_drln_bwd_args {
-    const void* g1; /* [M,H] bf16 gradient of out */
-    const void* g2; /* [M,H] bf16 second gradient of out (residual use by the next block) or NULL */
+    const void* g1;  /* [M,H] bf16 gradient of out (from the consuming GEMM's dgrad) */
+    const float* g2; /* [M,H] f32 gradient of out through the residual stream, or NULL */
     const void* y;
-    const void* res; /* or NULL */
+    const float* res; /* f32 or NULL */
     const float* mean;
     const float* rstd;
     const float* gamma;
     void* d_y;     /* [M,H] bf16 */
-    void* d_res;   /* [M,H] bf16 or NULL */
+    float* d_res;  /* [M,H] f32 or NULL */
     float* dgamma; /* [H] accumulated */
     float* dbeta;  /* [H] accumulated */
     float* dbias;  /* [H] accumulated, or NULL */
@@ -222,12 +223,13 @@ typedef struct mmb_embed_args {
     const float* wb[2]; /* [H] */
     float eps1, eps2, p_drop1, p_drop2;
     uint64_t seed;
-    void* x0; /* [rows,H] bf16 */
+    void* x0;      /* [rows,H] bf16 */
+    float* x0_f32; /* [rows,H] f32 residual-stream copy, or NULL */
     float *mean1, *rstd1, *mean2, *rstd2; /* [rows] */
     void* pframe;                         /* [B*(Lv+La), H] bf16 */
     /* backward */
     const void* dx0;  /* [rows,H] bf16 */
-    const void* dx0b; /* [rows,H] bf16 second gradient to add, or NULL */
+    const float* dx0b; /* [rows,H] f32 residual-stream gradient to add, or NULL */
     void* dpre;      /* [B*(Lv+La), H] bf16 scratch */
     float *g_word, *g_pos, *g_type, *g_ln1_g, *g_ln1_b, *g_ln2_g, *g_ln2_b;
     float* g_w[2];  /* [H,D] */

@@ -158,8 +158,9 @@ def gemm(A, B, C, M, N, K, **kw):
     call("gemm", gemm_args(A, B, C, M, N, K, **kw))
 
 
-def drln_fwd_args(y, res, gamma, beta, out, mean, rstd, eps, p_drop=0.0, seed=0, rng_stream=0):
-    return fill(DrlnFwdArgs(), y=y, res=res, gamma=gamma, beta=beta, out=out, mean=mean, rstd=rstd, M=y.shape[0],
+def drln_fwd_args(y, res, gamma, beta, out, mean, rstd, eps, p_drop=0.0, seed=0, rng_stream=0, out_f32=None):
+    return fill(DrlnFwdArgs(), y=y, res=res, gamma=gamma, beta=beta, out=out, out_f32=out_f32, mean=mean, rstd=rstd,
+                M=y.shape[0],
                 H=y.shape[1], eps=eps, p_drop=p_drop, seed=seed, rng_stream=rng_stream)
 
 

@@ -111,12 +111,13 @@ struct EmbedParams {
     uint64_t seed;
     // outputs / saved
     __nv_bfloat16* x0;             // [rows,H]
+    float* x0_f32;                 // [rows,H] fp32 residual-stream copy (optional)
     float* mean1; float* rstd1;    // [rows] (text rows)
     float* mean2; float* rstd2;    // [rows] (rows of joint passes)
     __nv_bfloat16* pframe;         // [frame_rows,H] relu(W f + b), bf16
     // backward
     const __nv_bfloat16* dx0;      // [rows,H]
-    const __nv_bfloat16* dx0b;     // [rows,H] optional second gradient
+    const float* dx0b;             // [rows,H] optional fp32 residual-stream gradient
     __nv_bfloat16* dpre;           // [frame_rows,H] gradient of the projection pre-activation
     float* g_word; float* g_pos; float* g_type;
     float* g_ln1_g; float* g_ln1_b; float* g_ln2_g; float* g_ln2_b;
@@ -190,6 +191,7 @@ embed_text_fwd_kernel(const EmbedParams p) {
             }
         }
         row_store_bf16(e, p.x0 + (int64_t)row * p.H, p.H, lane);
+        if (p.x0_f32 != nullptr) row_store_f32(e, p.x0_f32 + (int64_t)row * p.H, p.H, lane);
     }
 }
 
@@ -261,6 +263,7 @@ embed_frame_fwd_kernel(const EmbedParams p, int mod) {  // mod 0 = visual (pass 
             p.rstd2[row] = rstd;
         }
         row_store_bf16(z, p.x0 + (int64_t)row * p.H, p.H, lane);
+        if (p.x0_f32 != nullptr) row_store_f32(z, p.x0_f32 + (int64_t)row * p.H, p.H, lane);
     }
 }
 
@@ -305,7 +308,7 @@ embed_text_bwd_kernel(const EmbedParams p) {
         row_load_bf16(g, p.dx0 + (int64_t)row * p.H, p.H, lane);
         if (p.dx0b != nullptr) {
             RowF<NCH> g2;
-            row_load_bf16(g2, p.dx0b + (int64_t)row * p.H, p.H, lane);
+            row_load_f32(g2, p.dx0b + (int64_t)row * p.H, p.H, lane);
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
@@ -359,7 +362,7 @@ embed_frame_bwd_kernel(const EmbedParams p) {
         row_load_bf16(g, p.dx0 + (int64_t)row * p.H, p.H, lane);
         if (p.dx0b != nullptr) {
             RowF<NCH> g2;
-            row_load_bf16(g2, p.dx0b + (int64_t)row * p.H, p.H, lane);
+            row_load_f32(g2, p.dx0b + (int64_t)row * p.H, p.H, lane);
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
@@ -457,10 +460,11 @@ static int fill_embed(EmbedParams& p, const mmb_embed_args* a) {
     p.inv_keep2 = a->p_drop2 > 0.f ? 1.f / (1.f - a->p_drop2) : 1.f;
     p.seed = a->seed;
     p.x0 = (__nv_bfloat16*)a->x0;
+    p.x0_f32 = a->x0_f32;
     p.mean1 = a->mean1; p.rstd1 = a->rstd1; p.mean2 = a->mean2; p.rstd2 = a->rstd2;
     p.pframe = (__nv_bfloat16*)a->pframe;
     p.dx0 = (const __nv_bfloat16*)a->dx0;
-    p.dx0b = (const __nv_bfloat16*)a->dx0b;
+    p.dx0b = a->dx0b;
     p.dpre = (__nv_bfloat16*)a->dpre;
     p.g_word = a->g_word; p.g_pos = a->g_pos; p.g_type = a->g_type;
     p.g_ln1_g = a->g_ln1_g; p.g_ln1_b = a->g_ln1_b; p.g_ln2_g = a->g_ln2_g; p.g_ln2_b = a->g_ln2_b;

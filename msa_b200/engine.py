@@ -60,10 +60,13 @@ class Plan:
         # ---- activations (kept for backward when training; one reused set in eval)
         nsets = N if training else 1
         self.x = [buf(M, H) for _ in range(N + 1)] if training else [buf(M, H), buf(M, H)]
+        # fp32 copies of the residual stream (see csrc/ln.cu: precision note); the last layer's is never read
+        self.x32 = [buf(M, H, dtype=F32) for _ in range(N if training else 2)]
         self.layers = []
         for _ in range(nsets):
             self.layers.append(dict(
                 qkv=buf(M, 3 * H), ctx=buf(M, H), lse=buf(nh, M, dtype=F32), y1=buf(M, H), a=buf(M, H),
+                a32=buf(M, H, dtype=F32),
                 m1=buf(M, dtype=F32), r1=buf(M, dtype=F32), u=buf(M, I), hg=buf(M, I), y2=buf(M, H),
                 m2=buf(M, dtype=F32), r2=buf(M, dtype=F32)))
         self.e_m1, self.e_r1, self.e_m2, self.e_r2 = (buf(M, dtype=F32) for _ in range(4))
@@ -80,7 +83,9 @@ class Plan:
         self.gscale = torch.ones(1, device=dev, dtype=F32)
         if training:
             self.dlogits = buf(M, self.Vp)
-            self.GA, self.GB, self.GC, self.GD = (buf(M, H) for _ in range(4))
+            self.GA, self.GC = buf(M, H), buf(M, H)                          # bf16: dgrad outputs / dense-output grads
+            self.GB, self.GD = buf(M, H, dtype=F32), buf(M, H, dtype=F32)    # fp32: residual-stream gradients
+            self.GT = buf(M, H)                                              # bf16 scratch (LM-head d_tln, dCtx)
             self.dqkv, self.du = buf(M, 3 * H), buf(M, I)
             self.dsum = buf(nh, M, dtype=F32)
             self.dpre = buf(max(nfr, 1), H)
@@ -124,7 +129,7 @@ class Plan:
             ln2_g=self._p(je + "LayerNorm.weight"), ln2_b=self._p(je + "LayerNorm.bias"),
             wT=self.wT, wb=[self._p(je + "Wv.bias"), self._p(je + "Ws.bias")],
             eps1=c.layer_norm_eps, eps2=1e-5, p_drop1=self.p_hidden, p_drop2=self.p_joint, seed=0,
-            x0=self.x[0], mean1=self.e_m1, rstd1=self.e_r1, mean2=self.e_m2, rstd2=self.e_r2, pframe=self.pframe,
+            x0=self.x[0], x0_f32=self.x32[0], mean1=self.e_m1, rstd1=self.e_r1, mean2=self.e_m2, rstd2=self.e_r2, pframe=self.pframe,
             B=self.B, T=self.T, L=[self.Lv, self.La], H=H, V=self.V, max_pos=c.max_position_embeddings)
         if self.training:
             capi.fill(self.embed_args, dpre=self.dpre,
@@ -141,6 +146,8 @@ class Plan:
             L = self.layers[l if self.training else 0]
             xin = self.x[l] if self.training else self.x[l % 2]
             xout = self.x[l + 1] if self.training else self.x[(l + 1) % 2]
+            xin32 = self.x32[l] if self.training else self.x32[l % 2]
+            xout32 = None if l == N - 1 else (self.x32[l + 1] if self.training else self.x32[(l + 1) % 2])
             pre = f"bert.encoder.layer.{l}."
             wqkv = st.span(pre + "attention.self.query.weight", pre + "attention.self.value.weight", st.bf16).view(3 * H, H)
             bqkv = st.span(pre + "attention.self.query.bias", pre + "attention.self.value.bias")
@@ -152,9 +159,10 @@ class Plan:
             f.append((self._fn("attn_fwd"), a))
             self._gemm(f, L["ctx"], self._w(pre + "attention.output.dense.weight"), L["y1"], M, H, H,
                        bias=self._p(pre + "attention.output.dense.bias"))
-            a = capi.drln_fwd_args(L["y1"], xin, self._p(pre + "attention.output.LayerNorm.weight"),
+            a = capi.drln_fwd_args(L["y1"], xin32, self._p(pre + "attention.output.LayerNorm.weight"),
                                    self._p(pre + "attention.output.LayerNorm.bias"), L["a"], L["m1"], L["r1"],
-                                   c.layer_norm_eps, p_drop=self.p_hidden, rng_stream=(l << 8) | ST_OUT1)
+                                   c.layer_norm_eps, p_drop=self.p_hidden, rng_stream=(l << 8) | ST_OUT1,
+                                   out_f32=L["a32"])
             self._seeded.append(a)
             f.append((self._fn("dropout_residual_ln_fwd"), a))
             self._gemm(f, L["a"], self._w(pre + "intermediate.dense.weight"), L["hg"], M, I, H,
@@ -162,9 +170,10 @@ class Plan:
                        bias=self._p(pre + "intermediate.dense.bias"))
             self._gemm(f, L["hg"], self._w(pre + "output.dense.weight"), L["y2"], M, H, I,
                        bias=self._p(pre + "output.dense.bias"))
-            a = capi.drln_fwd_args(L["y2"], L["a"], self._p(pre + "output.LayerNorm.weight"),
+            a = capi.drln_fwd_args(L["y2"], L["a32"], self._p(pre + "output.LayerNorm.weight"),
                                    self._p(pre + "output.LayerNorm.bias"), xout, L["m2"], L["r2"],
-                                   c.layer_norm_eps, p_drop=self.p_hidden, rng_stream=(l << 8) | ST_OUT2)
+                                   c.layer_norm_eps, p_drop=self.p_hidden, rng_stream=(l << 8) | ST_OUT2,
+                                   out_f32=xout32)
             self._seeded.append(a)
             f.append((self._fn("dropout_residual_ln_fwd"), a))
         self.seq_out = self.x[N] if self.training else self.x[N % 2]
@@ -223,14 +232,14 @@ class Plan:
         word_bf = self._w("bert.embeddings.word_embeddings.weight")
         b.append((self._fn("ce_bwd"), self.ce_args))
         # tied decoder: d_tln = dlogits · Wword ; g_word += dlogits^T · t_ln ; g_dec_bias += colsum(dlogits)
-        self._gemm(b, self.dlogits, word_bf, self.GB, M, H, V, b_major=MN)
+        self._gemm(b, self.dlogits, word_bf, self.GT, M, H, V, b_major=MN)
         self._gemm(b, self.dlogits, self.t_ln, self._g("bert.embeddings.word_embeddings.weight"), V, H, M,
                    a_major=MN, b_major=MN, epilogue=ATOM, split_k=_split_k(V, H, M))
         gbias = st.grad[st.offsets["cls.predictions.bias"]:st.offsets["cls.predictions.bias"] + self.Vp]
         b.append((self._fn("colsum_bf16"), capi.colsum_args(self.dlogits, gbias)))
         tp = "cls.predictions.transform."
         b.append((self._fn("dropout_residual_ln_bwd"),
-                  capi.fill(capi.drln_bwd_args(self.GB, None, self.t_g, None, self.t_m, self.t_r,
+                  capi.fill(capi.drln_bwd_args(self.GT, None, self.t_g, None, self.t_m, self.t_r,
                                                self._p(tp + "LayerNorm.weight"), self.GC, None,
                                                self._g(tp + "LayerNorm.weight"), self._g(tp + "LayerNorm.bias"),
                                                self._g(tp + "dense.bias")), gelu_aux=self.t_u)))
@@ -242,7 +251,7 @@ class Plan:
             L = self.layers[l]
             pre = f"bert.encoder.layer.{l}."
             g2 = None if l == N - 1 else self.GB
-            a = capi.drln_bwd_args(self.GA, g2, L["y2"], L["a"], L["m2"], L["r2"], self._p(pre + "output.LayerNorm.weight"),
+            a = capi.drln_bwd_args(self.GA, g2, L["y2"], L["a32"], L["m2"], L["r2"], self._p(pre + "output.LayerNorm.weight"),
                                    self.GC, self.GD, self._g(pre + "output.LayerNorm.weight"),
                                    self._g(pre + "output.LayerNorm.bias"), self._g(pre + "output.dense.bias"),
                                    p_drop=self.p_hidden, rng_stream=(l << 8) | ST_OUT2)
@@ -258,7 +267,7 @@ class Plan:
             self._gemm(b, self.du, self._w(pre + "intermediate.dense.weight"), self.GA, M, H, I, b_major=MN)
             self._gemm(b, self.du, L["a"], self._g(pre + "intermediate.dense.weight"), I, H, M, a_major=MN, b_major=MN,
                        epilogue=ATOM, split_k=_split_k(I, H, M))
-            a = capi.drln_bwd_args(self.GA, self.GD, L["y1"], self.x[l], L["m1"], L["r1"],
+            a = capi.drln_bwd_args(self.GA, self.GD, L["y1"], self.x32[l], L["m1"], L["r1"],
                                    self._p(pre + "attention.output.LayerNorm.weight"), self.GC, self.GB,
                                    self._g(pre + "attention.output.LayerNorm.weight"),
                                    self._g(pre + "attention.output.LayerNorm.bias"),
@@ -267,10 +276,10 @@ class Plan:
             self._seeded.append(a)
             b.append((self._fn("dropout_residual_ln_bwd"), a))
             # attention output projection: dCtx = dY1 · Wo ; gWo += dY1^T · ctx
-            self._gemm(b, self.GC, self._w(pre + "attention.output.dense.weight"), self.GD, M, H, H, b_major=MN)
+            self._gemm(b, self.GC, self._w(pre + "attention.output.dense.weight"), self.GT, M, H, H, b_major=MN)
             self._gemm(b, self.GC, L["ctx"], self._g(pre + "attention.output.dense.weight"), H, H, M, a_major=MN,
                        b_major=MN, epilogue=ATOM, split_k=_split_k(H, H, M))
-            capi.fill(L["attn_args"], dctx=self.GD, dqkv=self.dqkv, dsum=self.dsum)
+            capi.fill(L["attn_args"], dctx=self.GT, dqkv=self.dqkv, dsum=self.dsum)
             b.append((self._fn("attn_bwd"), L["attn_args"]))
             wqkv = st.span(pre + "attention.self.query.weight", pre + "attention.self.value.weight", st.bf16).view(3 * H, H)
             gwqkv = st.span(pre + "attention.self.query.weight", pre + "attention.self.value.weight", st.grad).view(3 * H, H)
