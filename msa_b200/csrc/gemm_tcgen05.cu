@@ -71,6 +71,103 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&
     }
 }
 
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6), a=bf16 [7,10), b=bf16 [10,13),
+// a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------- epilogue
+// One 32-column chunk of one accumulator row (held by one thread) -> global memory.
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[32], int row, int col0, int nvalid) {
+    if (p.bias != nullptr && p.epilogue != MMB_EPI_ATOMIC_ADD_F32 && p.epilogue != MMB_EPI_DGELU_BF16) {
+        if (nvalid == 32) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);
+                v[4 * i] += b.x;
+                v[4 * i + 1] += b.y;
+                v[4 * i + 2] += b.z;
+                v[4 * i + 3] += b.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (i < nvalid) v[i] += __ldg(p.bias + col0 + i);
+        }
+    }
+    switch (p.epilogue) {
+        case MMB_EPI_STORE_BF16: {
+            store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0, v, nvalid);
+        } break;
+        case MMB_EPI_GELU_BF16: {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
+            if (p.aux != nullptr)
+                store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.aux) + (size_t)row * p.ldaux + col0, v, nvalid);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+            store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0, v, nvalid);
+        } break;
+        case MMB_EPI_RELU_BF16: {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0, v, nvalid);
+        } break;
+        case MMB_EPI_STORE_F32: {
+            float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+            if (nvalid == 32) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i < nvalid) dst[i] = v[i];
+            }
+        } break;
+        case MMB_EPI_ATOMIC_ADD_F32: {
+            float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+            if (nvalid == 32) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    ptx::red_add_v4(dst + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i < nvalid) atomicAdd(dst + i, v[i]);
+            }
+        } break;
+        case MMB_EPI_DGELU_BF16: {
+            const __nv_bfloat16* u = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ldaux + col0;
+            if (nvalid == 32) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 q = __ldg(reinterpret_cast<const uint4*>(u) + i);
+                    const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z),
+                                 f3 = unpack_bf16x2(q.w);
+                    v[8 * i + 0] *= gelu_fast_grad(f0.x);
+                    v[8 * i + 1] *= gelu_fast_grad(f0.y);
+                    v[8 * i + 2] *= gelu_fast_grad(f1.x);
+                    v[8 * i + 3] *= gelu_fast_grad(f1.y);
+                    v[8 * i + 4] *= gelu_fast_grad(f2.x);
+                    v[8 * i + 5] *= gelu_fast_grad(f2.y);
+                    v[8 * i + 6] *= gelu_fast_grad(f3.x);
+                    v[8 * i + 7] *= gelu_fast_grad(f3.y);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i < nvalid) v[i] *= gelu_fast_grad(__bfloat162float(u[i]));
+            }
+            store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0, v, nvalid);
+        } break;
+        default: break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- 1-CTA kernel
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -152,13 +249,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp == 1 && lane == 0) {
         // ================================ MMA issuer ================================
-        // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6), a=bf16 [7,10), b=bf16 [10,13),
-        // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
-                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        // K-major SW128: 8-row groups 1024 B apart (SBO); advance 32 B per UMMA_K inside the swizzled row.
-        // MN-major SW128: 64-element MN blocks 8192 B apart (LBO), 8-k groups 1024 B apart (SBO);
-        //                 advance two k-groups (2048 B) per UMMA_K.
+        const uint32_t idesc = make_idesc(BM, BN, p.a_mn, p.b_mn);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
@@ -218,83 +309,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const uint32_t taddr = tmem_base + acc * BN + half * kColsPerWarp + c + ((uint32_t)(quarter * 32) << 16);
                 ptx::tmem_ld_32x32(taddr, raw);
                 ptx::tmem_ld_wait();
-                const int nvalid = min(32, p.N - col0);
                 float v[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
-                if (p.bias != nullptr && p.epilogue != MMB_EPI_ATOMIC_ADD_F32 && p.epilogue != MMB_EPI_DGELU_BF16) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (i < nvalid) v[i] += __ldg(p.bias + col0 + i);
-                }
-                if (row_ok) switch (p.epilogue) {
-                    case MMB_EPI_STORE_BF16: {
-                        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0, v, nvalid);
-                    } break;
-                    case MMB_EPI_GELU_BF16: {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
-                        if (p.aux != nullptr)
-                            store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.aux) + (size_t)row * p.ldaux + col0, v, nvalid);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-                        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0, v, nvalid);
-                    } break;
-                    case MMB_EPI_RELU_BF16: {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-                        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0, v, nvalid);
-                    } break;
-                    case MMB_EPI_STORE_F32: {
-                        float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
-                        if (nvalid == 32) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (i < nvalid) dst[i] = v[i];
-                        }
-                    } break;
-                    case MMB_EPI_ATOMIC_ADD_F32: {
-                        float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
-                        if (nvalid == 32) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                ptx::red_add_v4(dst + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (i < nvalid) atomicAdd(dst + i, v[i]);
-                        }
-                    } break;
-                    case MMB_EPI_DGELU_BF16: {
-                        const __nv_bfloat16* u = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ldaux + col0;
-                        if (nvalid == 32) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const uint4 q = __ldg(reinterpret_cast<const uint4*>(u) + i);
-                                const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z),
-                                             f3 = unpack_bf16x2(q.w);
-                                v[8 * i + 0] *= gelu_erf_grad(f0.x);
-                                v[8 * i + 1] *= gelu_erf_grad(f0.y);
-                                v[8 * i + 2] *= gelu_erf_grad(f1.x);
-                                v[8 * i + 3] *= gelu_erf_grad(f1.y);
-                                v[8 * i + 4] *= gelu_erf_grad(f2.x);
-                                v[8 * i + 5] *= gelu_erf_grad(f2.y);
-                                v[8 * i + 6] *= gelu_erf_grad(f3.x);
-                                v[8 * i + 7] *= gelu_erf_grad(f3.y);
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (i < nvalid) v[i] *= gelu_erf_grad(__bfloat162float(u[i]));
-                        }
-                        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0, v, nvalid);
-                    } break;
-                    default: break;
-                }
+                if (row_ok) epilogue_chunk(p, v, row, col0, min(32, p.N - col0));
                 __syncwarp();  // reconverge before the next .sync.aligned TMEM load
             }
             // all TMEM reads of this warp are complete (tcgen05.wait::ld) -> hand the accumulator back
@@ -309,11 +327,194 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 
     // teardown
+    __syncwarp();
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 2) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- 2-CTA kernel
+// cta_group::2: a cluster of two CTAs (one SM pair) computes one 256 x 256 tile.  Each CTA loads its own 128 rows
+// of A and its own 128 columns of B (32 KB per stage instead of 48 KB), the leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256) which reads both halves of B across the pair, and each CTA's epilogue drains
+// its own 128 accumulator rows from its own TMEM.  Per SM the shared-memory traffic drops from 192 B/cycle
+// (96 B/cycle TMA fill + 96 B/cycle operand reads at full MMA rate; the 1-CTA kernel measured 66-69 % tensor-pipe
+// activity, i.e. the 128 B/cycle shared-memory limit) to 128 B/cycle.
+constexpr int k2Stages = 6;
+constexpr int k2ABytes = 128 * BK * 2;           // this CTA's half of the 256-row A tile
+constexpr int k2BBytes = 128 * BK * 2;           // this CTA's half of the 256-column B tile
+constexpr int k2StageBytes = k2ABytes + k2BBytes;
+constexpr int k2SmemBytes = k2Stages * k2StageBytes + 256 + 1024;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t smem_base = ptx::smem_u32(smem);
+    const uint32_t bar_base = smem_base + k2Stages * k2StageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (k2Stages + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * k2Stages + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * k2Stages + 2 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + k2Stages * k2StageBytes + 8 * (2 * k2Stages + 4));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();   // 0 = leader
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+    constexpr int TM = 256, TN = 256;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < k2Stages; ++s) {
+            ptx::mbar_init(full_bar(s), 1);    // leader's: one arrive.expect_tx covering both CTAs' TMA bytes
+            ptx::mbar_init(empty_bar(s), 1);   // per CTA: multicast tcgen05.commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            ptx::mbar_init(tfull_bar(a), 1);                    // per CTA: multicast tcgen05.commit
+            ptx::mbar_init(tempty_bar(a), 2 * kNumEpiWarps);    // leader's: epilogue warps of both CTAs
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc_2cta<512>(ptx::smem_u32(tmem_slot));
+    ptx::tc_fence_before();
+    ptx::cluster_sync();        // peer barriers initialised, TMEM allocated in both CTAs
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_kb = (p.K + BK - 1) / BK;
+    const int mn_tiles = p.m_tiles * p.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        // ================================ TMA producer (both CTAs) ================================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = cluster_id; t < p.total_tiles; t += num_clusters) {
+            const int ks = t / mn_tiles;
+            const int r = t - ks * mn_tiles;
+            const int n_blk = r / p.m_tiles;
+            const int m_blk = r - n_blk * p.m_tiles;
+            const int kb0 = ks * p.kb_per_split;
+            const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+            const int m0 = m_blk * TM + (int)rank * 128, n0 = n_blk * TN + (int)rank * 128;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+                const uint32_t sa = smem_base + stage * k2StageBytes;
+                const uint32_t sb = sa + k2ABytes;
+                const uint32_t lead_full = full_bar(stage) & kPeerMask;
+                if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * k2StageBytes);
+                if (!p.a_mn) {
+                    ptx::tma_load_2d_2cta(sa, &tmA, lead_full, kb * BK, m0);
+                } else {
+                    ptx::tma_load_2d_2cta(sa, &tmA, lead_full, m0, kb * BK);
+                    ptx::tma_load_2d_2cta(sa + 8192, &tmA, lead_full, m0 + 64, kb * BK);
+                }
+                if (!p.b_mn) {
+                    ptx::tma_load_2d_2cta(sb, &tmB, lead_full, kb * BK, n0);
+                } else {
+                    ptx::tma_load_2d_2cta(sb, &tmB, lead_full, n0, kb * BK);
+                    ptx::tma_load_2d_2cta(sb + 8192, &tmB, lead_full, n0 + 64, kb * BK);
+                }
+                if (++stage == k2Stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ================================ MMA issuer (leader CTA only) ================================
+        const uint32_t idesc = make_idesc(TM, TN, p.a_mn, p.b_mn);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = cluster_id; t < p.total_tiles; t += num_clusters) {
+            const int ks = t / mn_tiles;
+            const int kb0 = ks * p.kb_per_split;
+            const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+            ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * TN;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                ptx::mbar_wait(full_bar(stage), phase);
+                ptx::tc_fence_after();
+                const uint32_t sa = smem_base + stage * k2StageBytes;
+                const uint32_t sb = sa + k2ABytes;
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    const uint64_t da = ptx::umma_desc_sw128(sa + k * p.a_step, p.a_lbo, p.a_sbo);
+                    const uint64_t db = ptx::umma_desc_sw128(sb + k * p.b_step, p.b_lbo, p.b_sbo);
+                    ptx::umma_bf16_2cta(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                }
+                ptx::umma_commit_2cta(empty_bar(stage));   // both CTAs' slots are free once these MMAs retire
+                if (++stage == k2Stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            ptx::umma_commit_2cta(tfull_bar(acc));          // both CTAs' epilogues may drain their half
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ================================ epilogue (both CTAs, own 128 rows) ================================
+        const int ew = warp - kEpiWarp0;
+        const int quarter = warp & 3;
+        const int half = ew >> 2;
+        constexpr int kColsPerWarp = TN / 2;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = cluster_id; t < p.total_tiles; t += num_clusters) {
+            const int ks = t / mn_tiles;
+            const int r = t - ks * mn_tiles;
+            const int n_blk = r / p.m_tiles;
+            const int m_blk = r - n_blk * p.m_tiles;
+            ptx::mbar_wait(tfull_bar(acc), acc_phase);
+            ptx::tc_fence_after();
+            const int row = m_blk * TM + (int)rank * 128 + quarter * 32 + lane;
+            const bool row_ok = row < p.M;
+#pragma unroll 1
+            for (int c = 0; c < kColsPerWarp; c += 32) {
+                const int col0 = n_blk * TN + half * kColsPerWarp + c;
+                if (col0 >= p.N) break;
+                uint32_t raw[32];
+                const uint32_t taddr = tmem_base + acc * TN + half * kColsPerWarp + c + ((uint32_t)(quarter * 32) << 16);
+                ptx::tmem_ld_32x32(taddr, raw);
+                ptx::tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
+                if (row_ok) epilogue_chunk(p, v, row, col0, min(32, p.N - col0));
+                __syncwarp();
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(tempty_bar(acc) & kPeerMask);   // always the leader's barrier
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    // teardown: nobody may exit while the peer can still touch its shared memory / barriers / TMEM
+    __syncwarp();
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc_2cta<512>(tmem_base);
     }
 }
 
@@ -391,23 +592,7 @@ static int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64
     return MMB_OK;
 }
 
-template <int BN>
-static int launch_gemm(const mmb_gemm_args* a, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
-    CUtensorMap tmA, tmB;
-    int rc;
-    if (a->a_major == MMB_MAJOR_K)
-        rc = make_tmap_bf16(&tmA, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BK, BM);
-    else
-        rc = make_tmap_bf16(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BK);
-    if (rc != MMB_OK) return rc;
-    if (a->b_major == MMB_MAJOR_K)
-        rc = make_tmap_bf16(&tmB, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BK, BN);
-    else
-        rc = make_tmap_bf16(&tmB, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BK);
-    if (rc != MMB_OK) return rc;
-
-    GemmParams p;
+static void fill_common(GemmParams& p, const mmb_gemm_args* a, int tile_m, int tile_n) {
     p.C = a->C;
     p.aux = a->aux;
     p.bias = a->bias;
@@ -424,8 +609,8 @@ static int launch_gemm(const mmb_gemm_args* a, cudaStream_t stream) {
     if (split > total_kb) split = total_kb;
     p.kb_per_split = (total_kb + split - 1) / split;
     p.split_k = (total_kb + p.kb_per_split - 1) / p.kb_per_split;  // every split non-empty
-    p.m_tiles = (a->M + BM - 1) / BM;
-    p.n_tiles = (a->N + BN - 1) / BN;
+    p.m_tiles = (a->M + tile_m - 1) / tile_m;
+    p.n_tiles = (a->N + tile_n - 1) / tile_n;
     p.total_tiles = p.m_tiles * p.n_tiles * p.split_k;
     p.alpha = a->alpha;
     // K-major SW128: 8-row groups 1024 B apart (SBO), LBO unused; 32 B per UMMA_K inside the swizzled row.
@@ -439,7 +624,25 @@ static int launch_gemm(const mmb_gemm_args* a, cudaStream_t stream) {
     p.b_lbo = p.b_mn ? (swap ? 1024u : 8192u) : k_lbo;
     p.b_sbo = p.b_mn ? (swap ? 8192u : 1024u) : 1024u;
     p.b_step = p.b_mn ? 2048u : 32u;
+}
 
+template <int BN>
+static int launch_gemm(const mmb_gemm_args* a, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    CUtensorMap tmA, tmB;
+    int rc;
+    if (a->a_major == MMB_MAJOR_K)
+        rc = make_tmap_bf16(&tmA, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BK, BM);
+    else
+        rc = make_tmap_bf16(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BK);
+    if (rc != MMB_OK) return rc;
+    if (a->b_major == MMB_MAJOR_K)
+        rc = make_tmap_bf16(&tmB, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BK, BN);
+    else
+        rc = make_tmap_bf16(&tmB, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BK);
+    if (rc != MMB_OK) return rc;
+    GemmParams p;
+    fill_common(p, a, BM, BN);
     static bool attr_set = false;
     if (!attr_set) {
         MMB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -449,6 +652,33 @@ static int launch_gemm(const mmb_gemm_args* a, cudaStream_t stream) {
     const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
     gemm_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
     return check_launch("gemm_tcgen05_kernel");
+}
+
+// CTA-pair kernel: 256 x 256 tiles, one cluster of 2 per SM pair.
+static int launch_gemm_2cta(const mmb_gemm_args* a, cudaStream_t stream) {
+    CUtensorMap tmA, tmB;
+    int rc;
+    if (a->a_major == MMB_MAJOR_K)
+        rc = make_tmap_bf16(&tmA, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BK, 128);
+    else
+        rc = make_tmap_bf16(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BK);
+    if (rc != MMB_OK) return rc;
+    if (a->b_major == MMB_MAJOR_K)
+        rc = make_tmap_bf16(&tmB, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BK, 128);
+    else
+        rc = make_tmap_bf16(&tmB, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BK);
+    if (rc != MMB_OK) return rc;
+    GemmParams p;
+    fill_common(p, a, 256, 256);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MMB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes));
+        attr_set = true;
+    }
+    const int pairs = num_sms() / 2;
+    const int clusters = p.total_tiles < pairs ? p.total_tiles : pairs;
+    gemm_tcgen05_2cta_kernel<<<2 * clusters, kGemmThreads, k2SmemBytes, stream>>>(tmA, tmB, p);
+    return check_launch("gemm_tcgen05_2cta_kernel");
 }
 
 }  // namespace mmb
@@ -472,7 +702,12 @@ extern "C" int mmb_gemm(const mmb_gemm_args* a, void* stream) {
     const int min_lda = a->a_major == MMB_MAJOR_K ? a->K : a->M;
     const int min_ldb = a->b_major == MMB_MAJOR_K ? a->K : a->N;
     MMB_REQUIRE(a->lda >= min_lda && a->ldb >= min_ldb && a->ldc >= a->N, "mmb_gemm: leading dimension too small");
-    // N <= 128-wide problems (and anything forced by dbg_flags bit 0) use the 128x128 tile
-    const bool bn128 = (a->dbg_flags & 1) || a->N <= 128;
-    return bn128 ? launch_gemm<128>(a, (cudaStream_t)stream) : launch_gemm<256>(a, (cudaStream_t)stream);
+    // Dispatch: the CTA-pair kernel (256 x 256 tiles) whenever the problem has more than one 128-row tile and
+    // more than 128 columns; otherwise the single-CTA kernel (128 x 256, or 128 x 128 for N <= 128).
+    // dbg_flags: bit 0 forces the 128 x 128 tile, bit 3 forces the single-CTA 128 x 256 kernel.
+    if (a->dbg_flags & 1) return launch_gemm<128>(a, (cudaStream_t)stream);
+    if (a->dbg_flags & 8) return launch_gemm<256>(a, (cudaStream_t)stream);
+    if (a->N <= 128) return launch_gemm<128>(a, (cudaStream_t)stream);
+    if (a->M > 128) return launch_gemm_2cta(a, (cudaStream_t)stream);
+    return launch_gemm<256>(a, (cudaStream_t)stream);
 }

@@ -26,6 +26,15 @@ CASES = {
     "mnmn_wgrad": (768, 3072, 16000, 1, 1, "atomic", 8, 0),
     "mnmn_wgrad_ragged": (768, 74, 6400, 1, 1, "atomic", 4, 0),
     "kmn_dgrad": (4096, 768, 3072, 0, 1, "store", 1, 0),
+    # single-CTA kernel forced (dbg bit 3) for A/B timing against the CTA-pair kernel
+    "1cta_qkv": (16000, 2304, 768, 0, 0, "bias", 1, 8),
+    "1cta_ffn1_gelu": (16000, 3072, 768, 0, 0, "gelu", 1, 8),
+    "1cta_ffn2": (16000, 768, 3072, 0, 0, "bias", 1, 8),
+    "kk_big": (16384, 4096, 4096, 0, 0, "store", 1, 0),
+    "1cta_big": (16384, 4096, 4096, 0, 0, "store", 1, 8),
+    "kk_dec_dgrad": (16000, 768, 30522, 0, 1, "store", 1, 0),
+    "mnmn_dec_wgrad": (30522, 768, 16000, 1, 1, "atomic", 1, 0),
+    "kk_c3_ffn1": (73600, 3072, 768, 0, 0, "gelu", 1, 0),
 }
 
 
