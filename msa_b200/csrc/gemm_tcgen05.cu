@@ -33,7 +33,8 @@ struct GemmCfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = 2 * BN;  // 512 or 256: power of two
     static constexpr int kBarBytes = 256;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+    static constexpr int kEpiStageBytes = 8 * 4096;  // per-warp epilogue staging (kNumEpiWarps * kStageBytesPerWarp)
+    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kEpiStageBytes + 1024;  // + alignment slack
 };
 
 struct GemmParams {
@@ -50,6 +51,7 @@ struct GemmParams {
     float alpha;
     // UMMA smem-descriptor parameters per operand (bytes): leading/stride byte offsets, per-UMMA_K advance
     uint32_t a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step;
+    int dbg;  // bring-up only: bit 4 = epilogue skips global stores, bit 5 = epilogue skips the TMEM loads too
 };
 
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], int ncols_valid) {
@@ -79,8 +81,76 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn, int b_mn)
 }
 
 // ---------------------------------------------------------------------------------------------- epilogue
-// One 32-column chunk of one accumulator row (held by one thread) -> global memory.
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[32], int row, int col0, int nvalid) {
+// Each epilogue thread owns one accumulator row (its TMEM lane).  Writing that row straight to global memory
+// makes every warp store touch 32 different 128-byte lines with 16 bytes each; measured on B200 this store
+// pattern, not the math, bounded the K = 768 GEMMs (FFN1+GELU: 166 us with stores, 64 us without).  bf16
+// outputs are therefore transposed through a per-warp shared-memory staging tile (32 rows x 64 B, XOR
+// swizzled: conflict-free both ways) and written as full 64-byte row segments, 8 rows per warp instruction.
+constexpr int kStageBytesPerWarp = 4096;   // [0, 2048): C chunk, [2048, 4096): aux chunk (GELU out / DGELU in)
+
+__device__ __forceinline__ uint32_t stage_off(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
+
+// this lane's 32 values (one row) -> staging tile
+__device__ __forceinline__ void stage_row(uint8_t* st, const float (&v)[32], int lane) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+        u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+        u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        *reinterpret_cast<uint4*>(st + stage_off(lane, j)) = u;
+    }
+}
+// staging tile -> global, coalesced: instruction i writes rows 8i..8i+7, 4 lanes x 16 B per row
+__device__ __forceinline__ void flush_stage(const uint8_t* st, __nv_bfloat16* base, int64_t ld, int row_base, int M, int col0,
+                                            int N, int lane) {
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + (lane >> 2), j = lane & 3;
+        const uint4 q = *reinterpret_cast<const uint4*>(st + stage_off(r, j));
+        const int grow = row_base + r, gcol = col0 + j * 8;
+        if (grow < M && gcol < N) {
+            __nv_bfloat16* dst = base + (size_t)grow * ld + gcol;
+            if (gcol + 8 <= N) {
+                *reinterpret_cast<uint4*>(dst) = q;
+            } else {
+                const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&q);
+                for (int k = 0; k < N - gcol; ++k) dst[k] = e[k];
+            }
+        }
+    }
+    __syncwarp();
+}
+// global -> staging tile, coalesced (DGELU reads the saved pre-activation)
+__device__ __forceinline__ void fill_stage(uint8_t* st, const __nv_bfloat16* base, int64_t ld, int row_base, int M, int col0,
+                                           int N, int lane) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + (lane >> 2), j = lane & 3;
+        const int grow = row_base + r, gcol = col0 + j * 8;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (grow < M && gcol < N) {
+            const __nv_bfloat16* src = base + (size_t)grow * ld + gcol;
+            if (gcol + 8 <= N) {
+                q = __ldg(reinterpret_cast<const uint4*>(src));
+            } else {
+                __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(&q);
+                for (int k = 0; k < N - gcol; ++k) e[k] = src[k];
+            }
+        }
+        *reinterpret_cast<uint4*>(st + stage_off(r, j)) = q;
+    }
+    __syncwarp();
+}
+
+// One 32-column chunk of the warp's 32 accumulator rows.  Warp-collective: every lane must call it.
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[32], int row_base, int lane, int col0,
+                                               uint8_t* st) {
+    const int nvalid = min(32, p.N - col0);
+    const int row = row_base + lane;
+    const bool row_ok = row < p.M;
     if (p.bias != nullptr && p.epilogue != MMB_EPI_ATOMIC_ADD_F32 && p.epilogue != MMB_EPI_DGELU_BF16) {
         if (nvalid == 32) {
 #pragma unroll
@@ -97,71 +167,74 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[3
                 if (i < nvalid) v[i] += __ldg(p.bias + col0 + i);
         }
     }
+    __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(p.C);
     switch (p.epilogue) {
         case MMB_EPI_STORE_BF16: {
-            store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0, v, nvalid);
+            stage_row(st, v, lane);
+            flush_stage(st, Cb, p.ldc, row_base, p.M, col0, p.N, lane);
         } break;
         case MMB_EPI_GELU_BF16: {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
-            if (p.aux != nullptr)
-                store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.aux) + (size_t)row * p.ldaux + col0, v, nvalid);
+            if (p.aux != nullptr) stage_row(st + 2048, v, lane);
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
-            store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0, v, nvalid);
+            stage_row(st, v, lane);
+            if (p.aux != nullptr)
+                flush_stage(st + 2048, reinterpret_cast<__nv_bfloat16*>(p.aux), p.ldaux, row_base, p.M, col0, p.N, lane);
+            flush_stage(st, Cb, p.ldc, row_base, p.M, col0, p.N, lane);
         } break;
         case MMB_EPI_RELU_BF16: {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-            store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0, v, nvalid);
+            stage_row(st, v, lane);
+            flush_stage(st, Cb, p.ldc, row_base, p.M, col0, p.N, lane);
+        } break;
+        case MMB_EPI_DGELU_BF16: {
+            fill_stage(st + 2048, reinterpret_cast<const __nv_bfloat16*>(p.aux), p.ldaux, row_base, p.M, col0, p.N, lane);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint4 q = *reinterpret_cast<const uint4*>(st + 2048 + stage_off(lane, j));
+                const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
+                v[8 * j + 0] *= gelu_fast_grad(f0.x);
+                v[8 * j + 1] *= gelu_fast_grad(f0.y);
+                v[8 * j + 2] *= gelu_fast_grad(f1.x);
+                v[8 * j + 3] *= gelu_fast_grad(f1.y);
+                v[8 * j + 4] *= gelu_fast_grad(f2.x);
+                v[8 * j + 5] *= gelu_fast_grad(f2.y);
+                v[8 * j + 6] *= gelu_fast_grad(f3.x);
+                v[8 * j + 7] *= gelu_fast_grad(f3.y);
+            }
+            stage_row(st, v, lane);
+            flush_stage(st, Cb, p.ldc, row_base, p.M, col0, p.N, lane);
         } break;
         case MMB_EPI_STORE_F32: {
-            float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
-            if (nvalid == 32) {
+            if (row_ok) {
+                float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+                if (nvalid == 32) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            } else {
+                    for (int i = 0; i < 8; ++i)
+                        reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (i < nvalid) dst[i] = v[i];
+                    for (int i = 0; i < 32; ++i)
+                        if (i < nvalid) dst[i] = v[i];
+                }
             }
         } break;
         case MMB_EPI_ATOMIC_ADD_F32: {
-            float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
-            if (nvalid == 32) {
+            if (row_ok) {
+                float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+                if (nvalid == 32) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    ptx::red_add_v4(dst + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            } else {
+                    for (int i = 0; i < 8; ++i)
+                        ptx::red_add_v4(dst + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (i < nvalid) atomicAdd(dst + i, v[i]);
-            }
-        } break;
-        case MMB_EPI_DGELU_BF16: {
-            const __nv_bfloat16* u = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ldaux + col0;
-            if (nvalid == 32) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint4 q = __ldg(reinterpret_cast<const uint4*>(u) + i);
-                    const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z),
-                                 f3 = unpack_bf16x2(q.w);
-                    v[8 * i + 0] *= gelu_fast_grad(f0.x);
-                    v[8 * i + 1] *= gelu_fast_grad(f0.y);
-                    v[8 * i + 2] *= gelu_fast_grad(f1.x);
-                    v[8 * i + 3] *= gelu_fast_grad(f1.y);
-                    v[8 * i + 4] *= gelu_fast_grad(f2.x);
-                    v[8 * i + 5] *= gelu_fast_grad(f2.y);
-                    v[8 * i + 6] *= gelu_fast_grad(f3.x);
-                    v[8 * i + 7] *= gelu_fast_grad(f3.y);
+                    for (int i = 0; i < 32; ++i)
+                        if (i < nvalid) atomicAdd(dst + i, v[i]);
                 }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (i < nvalid) v[i] *= gelu_fast_grad(__bfloat162float(u[i]));
             }
-            store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0, v, nvalid);
         } break;
         default: break;
     }
@@ -183,6 +256,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 4));
+    uint8_t* epi_stage = smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -289,6 +363,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int ew = warp - kEpiWarp0;
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
         const int half = ew >> 2;      // which half of the BN columns
+        uint8_t* stage_buf = epi_stage + ew * kStageBytesPerWarp;
         constexpr int kColsPerWarp = BN / 2;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -299,12 +374,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int m_blk = r - n_blk * p.m_tiles;
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
-            const int row = m_blk * BM + quarter * 32 + lane;
-            const bool row_ok = row < p.M;
+            const int row_base = m_blk * BM + quarter * 32;
 #pragma unroll 1
             for (int c = 0; c < kColsPerWarp; c += 32) {
                 const int col0 = n_blk * BN + half * kColsPerWarp + c;
                 if (col0 >= p.N) break;  // warp-uniform
+                if (p.dbg & 32) continue;
                 uint32_t raw[32];
                 const uint32_t taddr = tmem_base + acc * BN + half * kColsPerWarp + c + ((uint32_t)(quarter * 32) << 16);
                 ptx::tmem_ld_32x32(taddr, raw);
@@ -312,7 +387,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 float v[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
-                if (row_ok) epilogue_chunk(p, v, row, col0, min(32, p.N - col0));
+                if (!(p.dbg & 16)) epilogue_chunk(p, v, row_base, lane, col0, stage_buf);
                 __syncwarp();  // reconverge before the next .sync.aligned TMEM load
             }
             // all TMEM reads of this warp are complete (tcgen05.wait::ld) -> hand the accumulator back
@@ -347,7 +422,7 @@ constexpr int k2Stages = 6;
 constexpr int k2ABytes = 128 * BK * 2;           // this CTA's half of the 256-row A tile
 constexpr int k2BBytes = 128 * BK * 2;           // this CTA's half of the 256-column B tile
 constexpr int k2StageBytes = k2ABytes + k2BBytes;
-constexpr int k2SmemBytes = k2Stages * k2StageBytes + 256 + 1024;
+constexpr int k2SmemBytes = k2Stages * k2StageBytes + 256 + 8 * 4096 + 1024;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
@@ -362,6 +437,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * k2Stages + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * k2Stages + 2 + a); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + k2Stages * k2StageBytes + 8 * (2 * k2Stages + 4));
+    uint8_t* epi_stage = smem + k2Stages * k2StageBytes + 256;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -472,6 +548,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int ew = warp - kEpiWarp0;
         const int quarter = warp & 3;
         const int half = ew >> 2;
+        uint8_t* stage_buf = epi_stage + ew * kStageBytesPerWarp;
         constexpr int kColsPerWarp = TN / 2;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -482,12 +559,12 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const int m_blk = r - n_blk * p.m_tiles;
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
-            const int row = m_blk * TM + (int)rank * 128 + quarter * 32 + lane;
-            const bool row_ok = row < p.M;
+            const int row_base = m_blk * TM + (int)rank * 128 + quarter * 32;
 #pragma unroll 1
             for (int c = 0; c < kColsPerWarp; c += 32) {
                 const int col0 = n_blk * TN + half * kColsPerWarp + c;
                 if (col0 >= p.N) break;
+                if (p.dbg & 32) continue;
                 uint32_t raw[32];
                 const uint32_t taddr = tmem_base + acc * TN + half * kColsPerWarp + c + ((uint32_t)(quarter * 32) << 16);
                 ptx::tmem_ld_32x32(taddr, raw);
@@ -495,7 +572,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 float v[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
-                if (row_ok) epilogue_chunk(p, v, row, col0, min(32, p.N - col0));
+                if (!(p.dbg & 16)) epilogue_chunk(p, v, row_base, lane, col0, stage_buf);
                 __syncwarp();
             }
             ptx::tc_fence_before();
@@ -613,6 +690,7 @@ static void fill_common(GemmParams& p, const mmb_gemm_args* a, int tile_m, int t
     p.n_tiles = (a->N + tile_n - 1) / tile_n;
     p.total_tiles = p.m_tiles * p.n_tiles * p.split_k;
     p.alpha = a->alpha;
+    p.dbg = a->dbg_flags;
     // K-major SW128: 8-row groups 1024 B apart (SBO), LBO unused; 32 B per UMMA_K inside the swizzled row.
     // MN-major SW128: 64-element MN blocks 8192 B apart (LBO), 8-k groups 1024 B apart (SBO); two k-groups
     // (2048 B) per UMMA_K.  dbg_flags bit 1 swaps LBO/SBO of MN-major operands, bit 2 sets K-major LBO = 16 B.

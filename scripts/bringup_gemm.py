@@ -35,6 +35,13 @@ CASES = {
     "kk_dec_dgrad": (16000, 768, 30522, 0, 1, "store", 1, 0),
     "mnmn_dec_wgrad": (30522, 768, 16000, 1, 1, "atomic", 1, 0),
     "kk_c3_ffn1": (73600, 3072, 768, 0, 0, "gelu", 1, 0),
+    # epilogue dissection (results are wrong by construction): 16 = no global stores, 32 = no TMEM loads either
+    "x_qkv_nostore": (16000, 2304, 768, 0, 0, "bias", 1, 16),
+    "x_qkv_nold": (16000, 2304, 768, 0, 0, "bias", 1, 32),
+    "x_ffn1_nostore": (16000, 3072, 768, 0, 0, "gelu", 1, 16),
+    "x_ffn1_nold": (16000, 3072, 768, 0, 0, "gelu", 1, 32),
+    "x_ffn2_nold": (16000, 768, 3072, 0, 0, "bias", 1, 32),
+    "x_big_nold": (16384, 4096, 4096, 0, 0, "store", 1, 32),
 }
 
 
