@@ -89,65 +89,83 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn, int b_mn)
 constexpr int kStageBytesPerWarp = 4096;   // [0, 2048): C chunk, [2048, 4096): aux chunk (GELU out / DGELU in)
 
 __device__ __forceinline__ uint32_t stage_off(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
+// explicit shared-space accesses (the staging pointer is a 32-bit shared address: guarantees STS/LDS, no generic LD/ST)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t& x, uint32_t& y, uint32_t& z, uint32_t& w) {
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(addr) : "memory");
+}
 
 // this lane's 32 values (one row) -> staging tile
-__device__ __forceinline__ void stage_row(uint8_t* st, const float (&v)[32], int lane) {
+__device__ __forceinline__ void stage_row(uint32_t st, const float (&v)[32], int lane) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        uint4 u;
-        u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-        u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-        u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-        u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-        *reinterpret_cast<uint4*>(st + stage_off(lane, j)) = u;
-    }
+    for (int j = 0; j < 4; ++j)
+        sts128(st + stage_off(lane, j), pack_bf16x2(v[8 * j + 0], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
 }
 // staging tile -> global, coalesced: instruction i writes rows 8i..8i+7, 4 lanes x 16 B per row
-__device__ __forceinline__ void flush_stage(const uint8_t* st, __nv_bfloat16* base, int64_t ld, int row_base, int M, int col0,
+__device__ __forceinline__ void flush_stage(uint32_t st, __nv_bfloat16* base, int64_t ld, int row_base, int M, int col0,
                                             int N, int lane) {
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int r = i * 8 + (lane >> 2), j = lane & 3;
-        const uint4 q = *reinterpret_cast<const uint4*>(st + stage_off(r, j));
+        uint32_t w0, w1, w2, w3;
+        lds128(st + stage_off(r, j), w0, w1, w2, w3);
         const int grow = row_base + r, gcol = col0 + j * 8;
         if (grow < M && gcol < N) {
             __nv_bfloat16* dst = base + (size_t)grow * ld + gcol;
             if (gcol + 8 <= N) {
-                *reinterpret_cast<uint4*>(dst) = q;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(w0, w1, w2, w3);
             } else {
-                const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&q);
-                for (int k = 0; k < N - gcol; ++k) dst[k] = e[k];
+                unsigned short* d16 = reinterpret_cast<unsigned short*>(dst);
+                const int n = N - gcol;
+                if (0 < n) d16[0] = (unsigned short)(w0 & 0xFFFFu);
+                if (1 < n) d16[1] = (unsigned short)(w0 >> 16);
+                if (2 < n) d16[2] = (unsigned short)(w1 & 0xFFFFu);
+                if (3 < n) d16[3] = (unsigned short)(w1 >> 16);
+                if (4 < n) d16[4] = (unsigned short)(w2 & 0xFFFFu);
+                if (5 < n) d16[5] = (unsigned short)(w2 >> 16);
+                if (6 < n) d16[6] = (unsigned short)(w3 & 0xFFFFu);
             }
         }
     }
     __syncwarp();
 }
 // global -> staging tile, coalesced (DGELU reads the saved pre-activation)
-__device__ __forceinline__ void fill_stage(uint8_t* st, const __nv_bfloat16* base, int64_t ld, int row_base, int M, int col0,
+__device__ __forceinline__ void fill_stage(uint32_t st, const __nv_bfloat16* base, int64_t ld, int row_base, int M, int col0,
                                            int N, int lane) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int r = i * 8 + (lane >> 2), j = lane & 3;
         const int grow = row_base + r, gcol = col0 + j * 8;
-        uint4 q = make_uint4(0, 0, 0, 0);
+        uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
         if (grow < M && gcol < N) {
             const __nv_bfloat16* src = base + (size_t)grow * ld + gcol;
             if (gcol + 8 <= N) {
-                q = __ldg(reinterpret_cast<const uint4*>(src));
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
+                w0 = q.x; w1 = q.y; w2 = q.z; w3 = q.w;
             } else {
-                __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(&q);
-                for (int k = 0; k < N - gcol; ++k) e[k] = src[k];
+                const unsigned short* s16 = reinterpret_cast<const unsigned short*>(src);
+                const int n = N - gcol;
+                if (0 < n) w0 |= (uint32_t)s16[0];
+                if (1 < n) w0 |= (uint32_t)s16[1] << 16;
+                if (2 < n) w1 |= (uint32_t)s16[2];
+                if (3 < n) w1 |= (uint32_t)s16[3] << 16;
+                if (4 < n) w2 |= (uint32_t)s16[4];
+                if (5 < n) w2 |= (uint32_t)s16[5] << 16;
+                if (6 < n) w3 |= (uint32_t)s16[6];
             }
         }
-        *reinterpret_cast<uint4*>(st + stage_off(r, j)) = q;
+        sts128(st + stage_off(r, j), w0, w1, w2, w3);
     }
     __syncwarp();
 }
 
 // One 32-column chunk of the warp's 32 accumulator rows.  Warp-collective: every lane must call it.
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[32], int row_base, int lane, int col0,
-                                               uint8_t* st) {
+                                               uint32_t st) {
     const int nvalid = min(32, p.N - col0);
     const int row = row_base + lane;
     const bool row_ok = row < p.M;
@@ -194,8 +212,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[3
             fill_stage(st + 2048, reinterpret_cast<const __nv_bfloat16*>(p.aux), p.ldaux, row_base, p.M, col0, p.N, lane);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const uint4 q = *reinterpret_cast<const uint4*>(st + 2048 + stage_off(lane, j));
-                const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
+                uint32_t q0, q1, q2, q3;
+                lds128(st + 2048 + stage_off(lane, j), q0, q1, q2, q3);
+                const float2 f0 = unpack_bf16x2(q0), f1 = unpack_bf16x2(q1), f2 = unpack_bf16x2(q2), f3 = unpack_bf16x2(q3);
                 v[8 * j + 0] *= gelu_fast_grad(f0.x);
                 v[8 * j + 1] *= gelu_fast_grad(f0.y);
                 v[8 * j + 2] *= gelu_fast_grad(f1.x);
@@ -292,8 +311,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             const int ks = t / mn_tiles;
             const int r = t - ks * mn_tiles;
-            const int n_blk = r / p.m_tiles;
-            const int m_blk = r - n_blk * p.m_tiles;
+            const int m_blk = r / p.n_tiles;   // n fastest: the tiles that share an A row-panel run concurrently
+            const int n_blk = r - m_blk * p.n_tiles;
             const int kb0 = ks * p.kb_per_split;
             const int kb1 = min(total_kb, kb0 + p.kb_per_split);
             for (int kb = kb0; kb < kb1; ++kb) {
@@ -363,15 +382,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int ew = warp - kEpiWarp0;
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
         const int half = ew >> 2;      // which half of the BN columns
-        uint8_t* stage_buf = epi_stage + ew * kStageBytesPerWarp;
+        const uint32_t stage_buf = ptx::smem_u32(epi_stage) + ew * kStageBytesPerWarp;
         constexpr int kColsPerWarp = BN / 2;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             const int ks = t / mn_tiles;
             const int r = t - ks * mn_tiles;
-            const int n_blk = r / p.m_tiles;
-            const int m_blk = r - n_blk * p.m_tiles;
+            const int m_blk = r / p.n_tiles;   // n fastest: the tiles that share an A row-panel run concurrently
+            const int n_blk = r - m_blk * p.n_tiles;
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
             const int row_base = m_blk * BM + quarter * 32;
@@ -477,8 +496,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int t = cluster_id; t < p.total_tiles; t += num_clusters) {
             const int ks = t / mn_tiles;
             const int r = t - ks * mn_tiles;
-            const int n_blk = r / p.m_tiles;
-            const int m_blk = r - n_blk * p.m_tiles;
+            const int m_blk = r / p.n_tiles;   // n fastest: the tiles that share an A row-panel run concurrently
+            const int n_blk = r - m_blk * p.n_tiles;
             const int kb0 = ks * p.kb_per_split;
             const int kb1 = min(total_kb, kb0 + p.kb_per_split);
             const int m0 = m_blk * TM + (int)rank * 128, n0 = n_blk * TN + (int)rank * 128;
@@ -548,15 +567,15 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int ew = warp - kEpiWarp0;
         const int quarter = warp & 3;
         const int half = ew >> 2;
-        uint8_t* stage_buf = epi_stage + ew * kStageBytesPerWarp;
+        const uint32_t stage_buf = ptx::smem_u32(epi_stage) + ew * kStageBytesPerWarp;
         constexpr int kColsPerWarp = TN / 2;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = cluster_id; t < p.total_tiles; t += num_clusters) {
             const int ks = t / mn_tiles;
             const int r = t - ks * mn_tiles;
-            const int n_blk = r / p.m_tiles;
-            const int m_blk = r - n_blk * p.m_tiles;
+            const int m_blk = r / p.n_tiles;   // n fastest: the tiles that share an A row-panel run concurrently
+            const int n_blk = r - m_blk * p.n_tiles;
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
             const int row_base = m_blk * TM + (int)rank * 128 + quarter * 32;
