@@ -67,17 +67,27 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     return cdf + x * pdf;
 }
 
-// Fast erf for the GEMM epilogues: Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7 — two orders of magnitude below
-// the bf16 rounding of the outputs it feeds — at ~16 instructions (one MUFU.RCP, one MUFU.EX2) instead of erff's
-// ~40.  gelu_fast / gelu_fast_grad share the exponential: exp(-z^2) with z = x / sqrt(2) is also the Gaussian pdf.
+// Fast erf for the GEMM epilogues: Abramowitz & Stegun 7.1.25, erf(z) = 1 - (a1 t + a2 t^2 + a3 t^3) exp(-z^2),
+// t = 1 / (1 + 0.47047 z), |error| <= 2.5e-5 — two orders of magnitude below the bf16 rounding (2^-9 relative)
+// of the outputs it feeds — in ~14 straight-line instructions (MUFU.RCP + MUFU.EX2 via the .approx.ftz PTX forms;
+// erff and the IEEE __frcp_rn / exp2f forms compile to branchy code with subroutine calls that made the GELU
+// epilogue, not the MMA, the bound of the FFN1 GEMM).  gelu_fast_grad shares the exponential: exp(-z^2) with
+// z = x / sqrt(2) is also the Gaussian density.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void erf_parts(float x, float& erf_abs, float& expmz2) {
-    const float z = fabsf(x) * 0.70710678118654752f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    expmz2 = exp2f(-1.4426950408889634f * z * z);
+    const float t = rcp_approx(fmaf(0.47047f * 0.70710678118654752f, fabsf(x), 1.0f));
+    float poly = fmaf(0.7478556f, t, -0.0958798f);
+    poly = fmaf(poly, t, 0.3480242f);
+    expmz2 = ex2_approx(x * x * -0.72134752044448170f);   // exp(-x^2 / 2)
     erf_abs = fmaf(-poly * t, expmz2, 1.0f);
 }
 __device__ __forceinline__ float gelu_fast(float x) {

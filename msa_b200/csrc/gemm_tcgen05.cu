@@ -192,9 +192,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[3
             flush_stage(st, Cb, p.ldc, row_base, p.M, col0, p.N, lane);
         } break;
         case MMB_EPI_GELU_BF16: {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
-            if (p.aux != nullptr) stage_row(st + 2048, v, lane);
+            if (p.aux != nullptr) stage_row(st + 2048, v, lane);   // pre-activation, rounded to bf16 by the pack
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
             stage_row(st, v, lane);
@@ -405,7 +403,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 ptx::tmem_ld_wait();
                 float v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                if (p.alpha != 1.0f) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+                }
                 if (!(p.dbg & 16)) epilogue_chunk(p, v, row_base, lane, col0, stage_buf);
                 __syncwarp();  // reconverge before the next .sync.aligned TMEM load
             }
@@ -590,7 +592,11 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 ptx::tmem_ld_wait();
                 float v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                if (p.alpha != 1.0f) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+                }
                 if (!(p.dbg & 16)) epilogue_chunk(p, v, row_base, lane, col0, stage_buf);
                 __syncwarp();
             }

@@ -16,86 +16,68 @@ namespace mmb {
 
 enum { ACT_NONE = 0, ACT_TANH = 1, ACT_RELU = 2 };
 
-// Y[r][n] = act(sum_k X[r][k] W[n][k] + b[n]);   grid (ceil(N/8), ceil(R/8)), 8 warps: warp = one column, 8 rows
+// Generic fp32 tiled GEMM for the head linears and their backward (64 x 64 tiles, 16-deep k-steps, 4 x 4 outputs
+// per thread).  C[m][n] (+)= act(sum_k A(m,k) B(k,n) + bias[n]) with A(m,k) = A[m*sam + k*sak] and
+// B(k,n) = B[k*sbk + n*sbn], so that Y = X W^T, dX = dY W and dW = dY^T X are the same kernel.
 __global__ void __launch_bounds__(256)
-sl_linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw, const float* __restrict__ b,
-                 float* __restrict__ Y, int ldy, int R, int N, int K, int act) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.x * 8 + warp;
-    const int r0 = blockIdx.y * 8;
+sgemm64_kernel(const float* __restrict__ A, int sam, int sak, const float* __restrict__ B, int sbk, int sbn,
+               float* __restrict__ C, int ldc, const float* __restrict__ bias, int act, int M, int N, int K, int accumulate) {
+    __shared__ __align__(16) float As[16][68];
+    __shared__ __align__(16) float Bs[16][68];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + i * 256;
+            int m, k;
+            if (sak == 1) { m = idx >> 4; k = idx & 15; } else { m = idx & 63; k = idx >> 6; }
+            As[k][m] = (m0 + m < M && k0 + k < K) ? A[(size_t)(m0 + m) * sam + (size_t)(k0 + k) * sak] : 0.f;
+            int kb, n;
+            if (sbn == 1) { kb = idx >> 6; n = idx & 63; } else { kb = idx & 15; n = idx >> 4; }
+            Bs[kb][n] = (n0 + n < N && k0 + kb < K) ? B[(size_t)(k0 + kb) * sbk + (size_t)(n0 + n) * sbn] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j] + (bias ? bias[n] : 0.f);
+            if (act == ACT_TANH) v = tanhf(v);
+            else if (act == ACT_RELU) v = fmaxf(v, 0.f);
+            float* c = C + (size_t)m * ldc + n;
+            *c = accumulate ? *c + v : v;
+        }
+    }
+}
+// db[n] += sum_r dY[r][n]
+__global__ void bias_grad_kernel(const float* __restrict__ dY, int ldy, float* __restrict__ db, int R, int N) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int k = lane; k < K; k += 32) {
-        const float w = __ldg(W + (size_t)n * ldw + k);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (r0 + i < R) acc[i] = fmaf(w, X[(size_t)(r0 + i) * ldx + k], acc[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
-    if (lane == 0) {
-        const float bias = b ? b[n] : 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (r0 + i < R) {
-                float v = acc[i] + bias;
-                if (act == ACT_TANH) v = tanhf(v);
-                else if (act == ACT_RELU) v = fmaxf(v, 0.f);
-                Y[(size_t)(r0 + i) * ldy + n] = v;
-            }
-        }
-    }
-}
-
-// dX[r][k] (+)= sum_n dY[r][n] W[n][k];   grid (ceil(K/256), ceil(R/8)); thread = one k, 8 rows
-__global__ void __launch_bounds__(256)
-sl_dx_kernel(const float* __restrict__ dY, int ldy, const float* __restrict__ W, int ldw, float* __restrict__ dX, int ldx,
-             int R, int N, int K, int accumulate) {
-    __shared__ float sdy[8][64];
-    const int k = blockIdx.x * 256 + threadIdx.x;
-    const int r0 = blockIdx.y * 8;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int n0 = 0; n0 < N; n0 += 64) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < 8 * 64; i += 256) {
-            const int r = i >> 6, nn = i & 63;
-            sdy[r][nn] = (r0 + r < R && n0 + nn < N) ? dY[(size_t)(r0 + r) * ldy + n0 + nn] : 0.f;
-        }
-        __syncthreads();
-        if (k < K) {
-            const int nmax = min(64, N - n0);
-            for (int nn = 0; nn < nmax; ++nn) {
-                const float w = __ldg(W + (size_t)(n0 + nn) * ldw + k);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] = fmaf(sdy[i][nn], w, acc[i]);
-            }
-        }
-    }
-    if (k < K) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (r0 + i < R) {
-                float* d = dX + (size_t)(r0 + i) * ldx + k;
-                *d = accumulate ? *d + acc[i] : acc[i];
-            }
-        }
-    }
-}
-
-// dW[n][k] += sum_r dY[r][n] X[r][k];  db[n] += sum_r dY[r][n];   grid (ceil(K/256), N); thread = one k
-__global__ void __launch_bounds__(256)
-sl_dw_kernel(const float* __restrict__ dY, int ldy, const float* __restrict__ X, int ldx, float* __restrict__ dW, int ldw,
-             float* __restrict__ db, int R, int N, int K) {
-    const int k = blockIdx.x * 256 + threadIdx.x;
-    const int n = blockIdx.y;
-    float acc = 0.f, bacc = 0.f;
-    for (int r = 0; r < R; ++r) {
-        const float g = dY[(size_t)r * ldy + n];
-        bacc += g;
-        if (k < K) acc = fmaf(g, X[(size_t)r * ldx + k], acc);
-    }
-    if (k < K) dW[(size_t)n * ldw + k] += acc;   // each (n,k) is owned by exactly one thread of this launch
-    if (db && k == 0) db[n] += bacc;
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) s += dY[(size_t)r * ldy + n];
+    db[n] += s;
 }
 
 // ---------------------------------------------------------------- small fused elementwise kernels
@@ -388,20 +370,24 @@ static HeadsWs heads_ws(int B, int H) {
     return w;
 }
 
+// Y[R,N] = act(X[R,K] W[N,K]^T + b)
 static inline void linear(cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy,
                           int R, int N, int K, int act) {
-    dim3 g((N + 7) / 8, (R + 7) / 8);
-    sl_linear_kernel<<<g, 256, 0, st>>>(X, ldx, W, ldw, b, Y, ldy, R, N, K, act);
+    dim3 g((N + 63) / 64, (R + 63) / 64);
+    sgemm64_kernel<<<g, 256, 0, st>>>(X, ldx, 1, W, 1, ldw, Y, ldy, b, act, R, N, K, 0);
 }
+// dX[R,K] (+)= dY[R,N] W[N,K]
 static inline void dx(cudaStream_t st, const float* dY, int ldy, const float* W, int ldw, float* dX, int ldx, int R, int N,
                       int K, int accumulate) {
-    dim3 g((K + 255) / 256, (R + 7) / 8);
-    sl_dx_kernel<<<g, 256, 0, st>>>(dY, ldy, W, ldw, dX, ldx, R, N, K, accumulate);
+    dim3 g((K + 63) / 64, (R + 63) / 64);
+    sgemm64_kernel<<<g, 256, 0, st>>>(dY, ldy, 1, W, ldw, 1, dX, ldx, nullptr, ACT_NONE, R, K, N, accumulate);
 }
+// dW[N,K] += dY[R,N]^T X[R,K] ; db[N] += colsum(dY)
 static inline void dw(cudaStream_t st, const float* dY, int ldy, const float* X, int ldx, float* dW, int ldw, float* db, int R,
                       int N, int K) {
-    dim3 g((K + 255) / 256, N);
-    sl_dw_kernel<<<g, 256, 0, st>>>(dY, ldy, X, ldx, dW, ldw, db, R, N, K);
+    dim3 g((K + 63) / 64, (N + 63) / 64);
+    sgemm64_kernel<<<g, 256, 0, st>>>(dY, 1, ldy, X, ldx, 1, dW, ldw, nullptr, ACT_NONE, N, K, R, 1);
+    if (db) bias_grad_kernel<<<(N + 127) / 128, 128, 0, st>>>(dY, ldy, db, R, N);
 }
 
 }  // namespace mmb
@@ -541,5 +527,5 @@ extern "C" int mmb_heads_bwd(const mmb_heads_args* a, void* stream) {
     dw(st, ws + w.dal, 2, ws + w.X0 + (size_t)B * H, H, a->g_w_align, H, a->g_b_align, 2 * B, 2, H);
     // add into the gradient of the encoder output at the [CLS] rows
     scatter_cls_grad_kernel<<<R, 256, 0, st>>>(ws + w.dX0, a->cu_seqlens, (__nv_bfloat16*)a->dseq_out, R, H);
-    return check_launch("heads_bwd", 36);
+    return check_launch("heads_bwd", 36 + 8);
 }

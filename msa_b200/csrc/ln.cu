@@ -51,21 +51,41 @@ drln_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ r
     }
 }
 
+// Column partials (dgamma, dbeta, dbias) live in per-warp private shared memory instead of registers: that drops
+// the kernel from 151 to <100 registers, doubles the resident warps per SM and with them the loads in flight
+// (the register version was latency-bound at ~2.5x its HBM time).
 template <int NCH>
-__global__ void __launch_bounds__(kLnWarps * 32)
+__device__ __forceinline__ void smem_accumulate(float* __restrict__ acc, const RowF<NCH>& v, int H, int lane) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int e = (c * 32 + lane) * 8;
+        if (e < H) {
+            float4* p = reinterpret_cast<float4*>(acc + e);
+            float4 a = p[0], b = p[1];
+            a.x += v.v[c][0]; a.y += v.v[c][1]; a.z += v.v[c][2]; a.w += v.v[c][3];
+            b.x += v.v[c][4]; b.y += v.v[c][5]; b.z += v.v[c][6]; b.w += v.v[c][7];
+            p[0] = a;
+            p[1] = b;
+        }
+    }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(kLnWarps * 32, 2)
 drln_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ g2,
                 const __nv_bfloat16* __restrict__ y, const float* __restrict__ res,
                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
                 __nv_bfloat16* __restrict__ d_y, float* __restrict__ d_res, float* __restrict__ dgamma,
                 float* __restrict__ dbeta, float* __restrict__ dbias, const __nv_bfloat16* __restrict__ gelu_aux, int M,
                 int H, uint32_t thresh, float inv_keep, uint64_t seed, uint32_t stream) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];   // [kLnWarps][3][H]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nw = gridDim.x * kLnWarps;
-    RowF<NCH> acc_g, acc_b, acc_bias;
-    row_zero(acc_g);
-    row_zero(acc_b);
-    row_zero(acc_bias);
+    float* acc_g = smem + (size_t)warp * 3 * H;
+    float* acc_b = acc_g + H;
+    float* acc_bias = acc_b + H;
+    for (int i = lane; i < 3 * H; i += 32) acc_g[i] = 0.f;
+    __syncwarp();
     for (int row = blockIdx.x * kLnWarps + warp; row < M; row += nw) {
         // recompute the LayerNorm input exactly as the forward did: z = dropout(y) + res
         RowF<NCH> z;
@@ -89,7 +109,49 @@ drln_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ 
 #pragma unroll
                 for (int i = 0; i < 8; ++i) g.v[c][i] += t.v[c][i];
         }
-        row_ln_bwd(z, g, H, lane, mean_in[row], rstd_in[row], gamma, acc_g, acc_b);
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        // dbeta += dy ; dgamma += dy * xhat ; dz = (dy*gamma - mean(dy*gamma) - xhat * mean(dy*gamma*xhat)) * rstd
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int e = (c * 32 + lane) * 8;
+            if (e < H) {
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + e));
+                const float4 g1v = __ldg(reinterpret_cast<const float4*>(gamma + e + 4));
+                const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1v.x, g1v.y, g1v.z, g1v.w};
+                float4* pg = reinterpret_cast<float4*>(acc_g + e);
+                float4* pb = reinterpret_cast<float4*>(acc_b + e);
+                const float4 ag0 = pg[0], ag1 = pg[1], ab0 = pb[0], ab1 = pb[1];
+                float ag[8] = {ag0.x, ag0.y, ag0.z, ag0.w, ag1.x, ag1.y, ag1.z, ag1.w};
+                float ab[8] = {ab0.x, ab0.y, ab0.z, ab0.w, ab1.x, ab1.y, ab1.z, ab1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float xhat = (z.v[c][i] - mean) * rstd;
+                    z.v[c][i] = xhat;
+                    const float dy = g.v[c][i];
+                    ag[i] = fmaf(dy, xhat, ag[i]);
+                    ab[i] += dy;
+                    const float dg = dy * gm[i];
+                    g.v[c][i] = dg;
+                    s1 += dg;
+                    s2 = fmaf(dg, xhat, s2);
+                }
+                pg[0] = make_float4(ag[0], ag[1], ag[2], ag[3]);
+                pg[1] = make_float4(ag[4], ag[5], ag[6], ag[7]);
+                pb[0] = make_float4(ab[0], ab[1], ab[2], ab[3]);
+                pb[1] = make_float4(ab[4], ab[5], ab[6], ab[7]);
+            }
+        }
+        s1 = warp_sum(s1) / (float)H;
+        s2 = warp_sum(s2) / (float)H;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int e = (c * 32 + lane) * 8;
+            if (e < H) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g.v[c][i] = (g.v[c][i] - s1 - z.v[c][i] * s2) * rstd;
+            }
+        }
         // g now holds dz: gradient of the residual branch
         if (d_res != nullptr) row_store_f32(g, d_res + (size_t)row * H, H, lane);
         // gradient of the dense output (pre-dropout): dz * mask / keep
@@ -114,14 +176,22 @@ drln_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ 
         }
         row_round_bf16(g);  // the bias gradient sums exactly what the wgrad GEMM will read
         row_store_bf16(g, d_y + (size_t)row * H, H, lane);
-#pragma unroll
-        for (int c = 0; c < NCH; ++c)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc_bias.v[c][i] += g.v[c][i];
+        if (dbias != nullptr) smem_accumulate(acc_bias, g, H, lane);
     }
-    cta_flush_columns(acc_g, dgamma, H, smem, warp, lane, kLnWarps);
-    cta_flush_columns(acc_b, dbeta, H, smem, warp, lane, kLnWarps);
-    if (dbias != nullptr) cta_flush_columns(acc_bias, dbias, H, smem, warp, lane, kLnWarps);
+    __syncthreads();
+    for (int col = threadIdx.x; col < H; col += kLnWarps * 32) {
+        float sg = 0.f, sb = 0.f, sbias = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLnWarps; ++w) {
+            const float* a = smem + (size_t)w * 3 * H;
+            sg += a[col];
+            sb += a[H + col];
+            sbias += a[2 * H + col];
+        }
+        atomicAdd(dgamma + col, sg);
+        atomicAdd(dbeta + col, sb);
+        if (dbias != nullptr) atomicAdd(dbias + col, sbias);
+    }
 }
 
 // out[n] += sum_m X[m, n]   (X bf16, row stride ld).  Each thread owns 8 adjacent columns.
@@ -178,8 +248,15 @@ extern "C" int mmb_dropout_residual_ln_bwd(const mmb_drln_bwd_args* a, void* str
     MMB_REQUIRE(a->M > 0 && a->H > 0 && a->H % 8 == 0 && a->H <= 1024, "drln_bwd: bad shape M=%d H=%d", a->M, a->H);
     const uint32_t thresh = dropout_threshold(a->p_drop);
     const float inv_keep = a->p_drop > 0.f ? 1.0f / (1.0f - a->p_drop) : 1.0f;
-    const int grid = min((a->M + kLnWarps - 1) / kLnWarps, num_sms());
-    const size_t smem = (size_t)kLnWarps * a->H * sizeof(float);
+    const int grid = min((a->M + kLnWarps - 1) / kLnWarps, num_sms() * 2);
+    const size_t smem = (size_t)kLnWarps * 3 * a->H * sizeof(float);
+    MMB_DISPATCH_NCH(a->H, {
+        static bool attr_set = false;
+        if (!attr_set) {
+            MMB_CUDA(cudaFuncSetAttribute(drln_bwd_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr_set = true;
+        }
+    });
     MMB_DISPATCH_NCH(a->H, (drln_bwd_kernel<NCH><<<grid, kLnWarps * 32, smem, (cudaStream_t)stream>>>(
                                (const __nv_bfloat16*)a->g1, a->g2, (const __nv_bfloat16*)a->y,
                                a->res, a->mean, a->rstd, a->gamma, (__nv_bfloat16*)a->d_y,

@@ -35,6 +35,11 @@ CASES = {
     "kk_dec_dgrad": (16000, 768, 30522, 0, 1, "store", 1, 0),
     "mnmn_dec_wgrad": (30522, 768, 16000, 1, 1, "atomic", 1, 0),
     "kk_c3_ffn1": (73600, 3072, 768, 0, 0, "gelu", 1, 0),
+    "y_ffn1_plain": (16000, 3072, 768, 0, 0, "bias", 1, 0),
+    "y_ffn1_gelu_noaux": (16000, 3072, 768, 0, 0, "gelu_noaux", 1, 0),
+    "y_ffn1_gelu_half": (8000, 3072, 768, 0, 0, "gelu", 1, 0),
+    "y_ffn1_gelu_quarter": (4000, 3072, 768, 0, 0, "gelu", 1, 0),
+    "y_ffn1_plain_c3": (73600, 3072, 768, 0, 0, "bias", 1, 0),
     # epilogue dissection (results are wrong by construction): 16 = no global stores, 32 = no TMEM loads either
     "x_qkv_nostore": (16000, 2304, 768, 0, 0, "bias", 1, 16),
     "x_qkv_nold": (16000, 2304, 768, 0, 0, "bias", 1, 32),
@@ -79,6 +84,10 @@ def run_case(name):
     elif epi == "gelu":
         e = capi.EPI_GELU_BF16; kw["bias"] = bias
         aux = torch.zeros(M, ldc, device=dev, dtype=torch.bfloat16)[:, :N]
+        pre = (ref + bias).to(torch.bfloat16).float()
+        ref = torch.nn.functional.gelu(pre)
+    elif epi == "gelu_noaux":
+        e = capi.EPI_GELU_BF16; kw["bias"] = bias
         pre = (ref + bias).to(torch.bfloat16).float()
         ref = torch.nn.functional.gelu(pre)
     elif epi == "dgelu":
