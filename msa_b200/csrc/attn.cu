@@ -132,9 +132,9 @@ struct AttnParams {
     uint32_t rng_stream;
 };
 
-// element index of probability (q, k) of (seq, head) for the dropout generator
-__device__ __forceinline__ uint64_t prob_index(int seq, int head, int nheads, int S, int q, int k) {
-    return (((uint64_t)seq * nheads + head) * (uint64_t)S + q) * (uint64_t)S + k;
+// dropout generator row id of query q of (seq, head): the probability row; columns are the keys
+__device__ __forceinline__ uint32_t prob_row_id(int seq, int head, int nheads, int S, int q) {
+    return ((uint32_t)seq * (uint32_t)nheads + (uint32_t)head) * (uint32_t)S + (uint32_t)q;
 }
 
 // ================================================================== forward
@@ -231,15 +231,16 @@ attn_fwd_kernel(const AttnParams p) {
         }
         if (p.thresh != 0u) {
             const int q0 = qt * kTile + warp * 16 + g;
+            const uint32_t key_lo = rng_row_key(p.seed, p.rng_stream, prob_row_id(seq, head, p.nheads, S, q0));
+            const uint32_t key_hi = rng_row_key(p.seed, p.rng_stream, prob_row_id(seq, head, p.nheads, S, q0 + 8));
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
-                const int kc = kt * kTile + nt * 8 + 2 * t;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int q = q0 + (j >> 1) * 8, k = kc + (j & 1);
-                    const bool keep = rng_keep(p.seed, p.rng_stream, prob_index(seq, head, p.nheads, S, q, k), p.thresh);
-                    s[nt][j] = keep ? s[nt][j] * p.inv_keep : 0.f;
-                }
+                const uint32_t pair = (uint32_t)(kt * kTile + nt * 8 + 2 * t) >> 1;   // this thread's two adjacent keys
+                const uint32_t b_lo = rng_pair(key_lo, pair), b_hi = rng_pair(key_hi, pair);
+                s[nt][0] = rng_keep_lo(b_lo, p.thresh) ? s[nt][0] * p.inv_keep : 0.f;
+                s[nt][1] = rng_keep_hi(b_lo, p.thresh) ? s[nt][1] * p.inv_keep : 0.f;
+                s[nt][2] = rng_keep_lo(b_hi, p.thresh) ? s[nt][2] * p.inv_keep : 0.f;
+                s[nt][3] = rng_keep_hi(b_hi, p.thresh) ? s[nt][3] * p.inv_keep : 0.f;
             }
         }
         uint32_t pa[4][4];
@@ -304,6 +305,7 @@ attn_bwd_dkv_kernel(const AttnParams p) {
     uint8_t* sdO = sQ + 2 * kTile * 128;          // [2][64][128]
     float (*sL)[kTile] = reinterpret_cast<float (*)[kTile]>(sdO + 2 * kTile * 128);
     float (*sD)[kTile] = sL + 2;
+    uint32_t (*sKey)[kTile] = reinterpret_cast<uint32_t (*)[kTile]>(sD + 2);   // dropout row keys of the q tile
 
     const int seq = blockIdx.z, head = blockIdx.y, kt = blockIdx.x;
     const int row0 = p.cu_seqlens[seq];
@@ -328,6 +330,7 @@ attn_bwd_dkv_kernel(const AttnParams p) {
     if (tid < kTile) {
         sL[0][tid] = tid < S ? Lg[tid] : INFINITY;  // padded queries: P = exp2(-inf) = 0
         sD[0][tid] = tid < S ? Dg[tid] : 0.f;
+        if (p.thresh != 0u) sKey[0][tid] = rng_row_key(p.seed, p.rng_stream, prob_row_id(seq, head, p.nheads, S, tid));
     }
     ptx::cp_async_commit();
 
@@ -350,6 +353,8 @@ attn_bwd_dkv_kernel(const AttnParams p) {
             if (tid < kTile) {
                 sL[st ^ 1][tid] = (q0 + tid) < S ? Lg[q0 + tid] : INFINITY;
                 sD[st ^ 1][tid] = (q0 + tid) < S ? Dg[q0 + tid] : 0.f;
+                if (p.thresh != 0u)
+                    sKey[st ^ 1][tid] = rng_row_key(p.seed, p.rng_stream, prob_row_id(seq, head, p.nheads, S, q0 + tid));
             }
             ptx::cp_async_commit();
             ptx::cp_async_wait<1>();
@@ -382,8 +387,8 @@ attn_bwd_dkv_kernel(const AttnParams p) {
             if (p.thresh != 0u) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int q = qt * kTile + qc + (j & 1), k = (j >> 1) ? k_hi : k_lo;
-                    const bool keep = rng_keep(p.seed, p.rng_stream, prob_index(seq, head, p.nheads, S, q, k), p.thresh);
+                    const int k = (j >> 1) ? k_hi : k_lo;
+                    const bool keep = rng_keep_col(sKey[st][qc + (j & 1)], (uint32_t)k, p.thresh);
                     pd[j] = keep ? pr[j] * p.inv_keep : 0.f;
                     dpj[j] = keep ? dpj[j] * p.inv_keep : 0.f;
                 }
@@ -457,6 +462,8 @@ attn_bwd_dq_kernel(const AttnParams p) {
     const float* Dg = p.dsum + (int64_t)head * p.total_rows + row0;
     const float L_lo = q_lo < S ? Lg[q_lo] : INFINITY, L_hi = q_hi < S ? Lg[q_hi] : INFINITY;
     const float D_lo = q_lo < S ? Dg[q_lo] : 0.f, D_hi = q_hi < S ? Dg[q_hi] : 0.f;
+    const uint32_t rkey_lo = rng_row_key(p.seed, p.rng_stream, prob_row_id(seq, head, p.nheads, S, q_lo));
+    const uint32_t rkey_hi = rng_row_key(p.seed, p.rng_stream, prob_row_id(seq, head, p.nheads, S, q_hi));
 
     uint32_t qa[4][4], doa[4][4];
     float dq[8][4];
@@ -495,12 +502,12 @@ attn_bwd_dq_kernel(const AttnParams p) {
             pr[3] = exp2f(s[nt][3] * p.scale_log2 + b1 - L_hi);
             float dpj[4] = {dp[nt][0], dp[nt][1], dp[nt][2], dp[nt][3]};
             if (p.thresh != 0u) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int q = (j >> 1) ? q_hi : q_lo, k = kt * kTile + kc + (j & 1);
-                    const bool keep = rng_keep(p.seed, p.rng_stream, prob_index(seq, head, p.nheads, S, q, k), p.thresh);
-                    dpj[j] = keep ? dpj[j] * p.inv_keep : 0.f;
-                }
+                const uint32_t pair = (uint32_t)(kt * kTile + kc) >> 1;
+                const uint32_t b_lo = rng_pair(rkey_lo, pair), b_hi = rng_pair(rkey_hi, pair);
+                dpj[0] = rng_keep_lo(b_lo, p.thresh) ? dpj[0] * p.inv_keep : 0.f;
+                dpj[1] = rng_keep_hi(b_lo, p.thresh) ? dpj[1] * p.inv_keep : 0.f;
+                dpj[2] = rng_keep_lo(b_hi, p.thresh) ? dpj[2] * p.inv_keep : 0.f;
+                dpj[3] = rng_keep_hi(b_hi, p.thresh) ? dpj[3] * p.inv_keep : 0.f;
             }
             dp[nt][0] = pr[0] * (dpj[0] - D_lo);
             dp[nt][1] = pr[1] * (dpj[1] - D_lo);
@@ -540,7 +547,7 @@ static int fill_params(AttnParams& p, const mmb_attn_args* a) {
     p.scale = 1.0f / sqrtf((float)kD);
     p.scale_log2 = p.scale * kLog2e;
     p.thresh = dropout_threshold(a->p_drop);
-    p.inv_keep = a->p_drop > 0.f ? 1.0f / (1.0f - a->p_drop) : 1.0f;
+    p.inv_keep = dropout_inv_keep(a->p_drop);
     p.seed = a->seed;
     p.rng_stream = a->rng_stream;
     return MMB_OK;
@@ -571,7 +578,7 @@ extern "C" int mmb_attn_bwd(const mmb_attn_args* a, void* stream) {
     rc = check_launch("attn_bwd_dsum_kernel");
     if (rc != MMB_OK) return rc;
     dim3 grid((a->max_seqlen + kTile - 1) / kTile, a->nheads, a->nseq);
-    constexpr int kBwdSmem = 6 * kTile * 128 + 4 * kTile * (int)sizeof(float);
+    constexpr int kBwdSmem = 6 * kTile * 128 + 6 * kTile * (int)sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         MMB_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));

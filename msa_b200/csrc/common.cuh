@@ -101,28 +101,54 @@ __device__ __forceinline__ float gelu_fast_grad(float x) {
     return fmaf(x * 0.3989422804014327f, g, 0.5f * (1.0f + copysignf(e, x)));
 }
 
-// Counter-based RNG for dropout: a 64-bit counter (stream, element index) mixed with the seed by a
-// splitmix64-style finaliser. Forward and backward regenerate identical masks from (seed, stream, idx);
-// nothing is stored.  Returns 32 uniform bits.
-__device__ __forceinline__ uint32_t rng_bits(uint64_t seed, uint32_t stream, uint64_t idx) {
-    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1) + ((uint64_t)stream << 40) * 0xD1B54A32D192ED03ull;
-    z ^= (uint64_t)stream * 0xA24BAED4963EE407ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z = z ^ (z >> 31);
-    return (uint32_t)(z >> 16);
+// Counter-based RNG for dropout.  Forward and backward regenerate identical masks from (seed, stream, row, column):
+// nothing is stored.  32-bit murmur3-style mixing only (no 64-bit multiplies): a per-row key is hashed once from
+// (seed, stream, row id), then ONE hash per PAIR of adjacent columns yields two 16-bit uniform values, i.e. about
+// 4 integer instructions per dropout decision.  keep iff the 16-bit value >= thresh16 = round(p * 65536).
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    return h;
 }
-// keep-decision for dropout probability p: keep iff bits >= p * 2^32
-__device__ __forceinline__ bool rng_keep(uint64_t seed, uint32_t stream, uint64_t idx, uint32_t thresh) {
-    return rng_bits(seed, stream, idx) >= thresh;
+__device__ __forceinline__ uint32_t rng_row_key(uint64_t seed, uint32_t stream, uint32_t row_id) {
+    uint32_t h = (uint32_t)seed ^ (stream * 0x9E3779B9u);
+    uint32_t k = row_id * 0xcc9e2d51u;
+    k = rotl32(k, 15) * 0x1b873593u;
+    h = rotl32(h ^ k, 13) * 5u + 0xe6546b64u;
+    k = (uint32_t)(seed >> 32) * 0xcc9e2d51u;
+    k = rotl32(k, 15) * 0x1b873593u;
+    h = rotl32(h ^ k, 13) * 5u + 0xe6546b64u;
+    return fmix32(h ^ 12u);
+}
+// 32 random bits for column pair `pair` (columns 2*pair and 2*pair+1) of the row: low 16 bits -> even column
+__device__ __forceinline__ uint32_t rng_pair(uint32_t row_key, uint32_t pair) {
+    uint32_t k = pair * 0xcc9e2d51u;
+    k = rotl32(k, 15) * 0x1b873593u;
+    return fmix32(row_key ^ k);
+}
+__device__ __forceinline__ bool rng_keep_lo(uint32_t bits, uint32_t thresh16) { return (bits & 0xFFFFu) >= thresh16; }
+__device__ __forceinline__ bool rng_keep_hi(uint32_t bits, uint32_t thresh16) { return (bits >> 16) >= thresh16; }
+// decision for a single column
+__device__ __forceinline__ bool rng_keep_col(uint32_t row_key, uint32_t col, uint32_t thresh16) {
+    const uint32_t bits = rng_pair(row_key, col >> 1);
+    return (col & 1u) ? rng_keep_hi(bits, thresh16) : rng_keep_lo(bits, thresh16);
 }
 #endif  // __CUDACC__
 
+// 16-bit dropout threshold and the matching unbiased rescale 1 / (1 - thresh16 / 65536)
 inline uint32_t dropout_threshold(float p) {
     if (p <= 0.f) return 0u;
-    double t = (double)p * 4294967296.0;
-    if (t >= 4294967295.0) return 0xFFFFFFFFu;
+    double t = (double)p * 65536.0 + 0.5;
+    if (t >= 65535.0) return 65535u;
     return (uint32_t)t;
+}
+inline float dropout_inv_keep(float p) {
+    const uint32_t t = dropout_threshold(p);
+    return t == 0u ? 1.0f : (float)(1.0 / (1.0 - (double)t / 65536.0));
 }
 
 }  // namespace mmb

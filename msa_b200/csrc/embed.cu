@@ -456,8 +456,8 @@ static int fill_embed(EmbedParams& p, const mmb_embed_args* a) {
     p.ln2_g = a->ln2_g; p.ln2_b = a->ln2_b; p.eps2 = a->eps2;
     p.thresh1 = dropout_threshold(a->p_drop1);
     p.thresh2 = dropout_threshold(a->p_drop2);
-    p.inv_keep1 = a->p_drop1 > 0.f ? 1.f / (1.f - a->p_drop1) : 1.f;
-    p.inv_keep2 = a->p_drop2 > 0.f ? 1.f / (1.f - a->p_drop2) : 1.f;
+    p.inv_keep1 = dropout_inv_keep(a->p_drop1);
+    p.inv_keep2 = dropout_inv_keep(a->p_drop2);
     p.seed = a->seed;
     p.x0 = (__nv_bfloat16*)a->x0;
     p.x0_f32 = a->x0_f32;

@@ -19,11 +19,12 @@ enum { ACT_NONE = 0, ACT_TANH = 1, ACT_RELU = 2 };
 // Generic fp32 tiled GEMM for the head linears and their backward (64 x 64 tiles, 16-deep k-steps, 4 x 4 outputs
 // per thread).  C[m][n] (+)= act(sum_k A(m,k) B(k,n) + bias[n]) with A(m,k) = A[m*sam + k*sak] and
 // B(k,n) = B[k*sbk + n*sbn], so that Y = X W^T, dX = dY W and dW = dY^T X are the same kernel.
+constexpr int kSgBK = 64;   // deep k-steps: these GEMMs are tiny and latency-bound, so fewer load->sync->compute rounds win
 __global__ void __launch_bounds__(256)
 sgemm64_kernel(const float* __restrict__ A, int sam, int sak, const float* __restrict__ B, int sbk, int sbn,
                float* __restrict__ C, int ldc, const float* __restrict__ bias, int act, int M, int N, int K, int accumulate) {
-    __shared__ __align__(16) float As[16][68];
-    __shared__ __align__(16) float Bs[16][68];
+    __shared__ __align__(16) float As[kSgBK][68];
+    __shared__ __align__(16) float Bs[kSgBK][68];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
     float acc[4][4];
@@ -31,20 +32,31 @@ sgemm64_kernel(const float* __restrict__ A, int sam, int sak, const float* __res
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int k0 = 0; k0 < K; k0 += kSgBK) {
+        float ra[16], rb[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 16; ++i) {      // all 32 loads of this thread are issued before any is consumed
             const int idx = tid + i * 256;
             int m, k;
-            if (sak == 1) { m = idx >> 4; k = idx & 15; } else { m = idx & 63; k = idx >> 6; }
-            As[k][m] = (m0 + m < M && k0 + k < K) ? A[(size_t)(m0 + m) * sam + (size_t)(k0 + k) * sak] : 0.f;
+            if (sak == 1) { m = idx >> 6; k = idx & 63; } else { m = idx & 63; k = idx >> 6; }
+            ra[i] = (m0 + m < M && k0 + k < K) ? __ldg(A + (size_t)(m0 + m) * sam + (size_t)(k0 + k) * sak) : 0.f;
             int kb, n;
-            if (sbn == 1) { kb = idx >> 6; n = idx & 63; } else { kb = idx & 15; n = idx >> 4; }
-            Bs[kb][n] = (n0 + n < N && k0 + kb < K) ? B[(size_t)(k0 + kb) * sbk + (size_t)(n0 + n) * sbn] : 0.f;
+            if (sbn == 1) { kb = idx >> 6; n = idx & 63; } else { kb = idx & 63; n = idx >> 6; }
+            rb[i] = (n0 + n < N && k0 + kb < K) ? __ldg(B + (size_t)(k0 + kb) * sbk + (size_t)(n0 + n) * sbn) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int idx = tid + i * 256;
+            int m, k;
+            if (sak == 1) { m = idx >> 6; k = idx & 63; } else { m = idx & 63; k = idx >> 6; }
+            As[k][m] = ra[i];
+            int kb, n;
+            if (sbn == 1) { kb = idx >> 6; n = idx & 63; } else { kb = idx & 63; n = idx >> 6; }
+            Bs[kb][n] = rb[i];
         }
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
+#pragma unroll 16
+        for (int k = 0; k < kSgBK; ++k) {
             const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
             const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
             const float av[4] = {a.x, a.y, a.z, a.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};

@@ -155,17 +155,7 @@ drln_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ 
         // g now holds dz: gradient of the residual branch
         if (d_res != nullptr) row_store_f32(g, d_res + (size_t)row * H, H, lane);
         // gradient of the dense output (pre-dropout): dz * mask / keep
-        if (thresh != 0u) {
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                const int e = (c * 32 + lane) * 8;
-                if (e < H) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        g.v[c][i] = rng_keep(seed, stream, (uint64_t)row * H + e + i, thresh) ? g.v[c][i] * inv_keep : 0.f;
-                }
-            }
-        }
+        row_dropout(g, H, lane, seed, stream, (uint64_t)row, thresh, inv_keep);   // same mask, same scaling
         if (gelu_aux != nullptr) {  // y = gelu(aux): chain through the activation (LM-head transform, :482-484)
             RowF<NCH> u;
             row_load_bf16(u, gelu_aux + (size_t)row * H, H, lane);
@@ -206,8 +196,20 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, float* __restrict__ out,
     const int r1 = min(M, r0 + rows_per_cta);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (col0 < N) {
-        for (int r = r0 + rr; r < r1; r += 8) {
-            const uint4 q = *reinterpret_cast<const uint4*>(X + (size_t)r * ld + col0);
+        int r = r0 + rr;
+        for (; r + 24 < r1; r += 32) {   // four independent 16-byte loads in flight per thread
+            uint4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(X + (size_t)(r + 8 * u) * ld + col0));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float2 a = unpack_bf16x2(q[u].x), b = unpack_bf16x2(q[u].y), c = unpack_bf16x2(q[u].z), d = unpack_bf16x2(q[u].w);
+                acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+                acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+            }
+        }
+        for (; r < r1; r += 8) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(X + (size_t)r * ld + col0));
             const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
             acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
             acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
@@ -233,7 +235,7 @@ extern "C" int mmb_dropout_residual_ln_fwd(const mmb_drln_fwd_args* a, void* str
     MMB_REQUIRE(a && a->y && a->gamma && a->beta && a->out && a->mean && a->rstd, "drln_fwd: null pointer");
     MMB_REQUIRE(a->M > 0 && a->H > 0 && a->H % 8 == 0 && a->H <= 1024, "drln_fwd: bad shape M=%d H=%d", a->M, a->H);
     const uint32_t thresh = dropout_threshold(a->p_drop);
-    const float inv_keep = a->p_drop > 0.f ? 1.0f / (1.0f - a->p_drop) : 1.0f;
+    const float inv_keep = dropout_inv_keep(a->p_drop);
     const int grid = min((a->M + kLnWarps - 1) / kLnWarps, num_sms() * 4);
     MMB_DISPATCH_NCH(a->H, (drln_fwd_kernel<NCH><<<grid, kLnWarps * 32, 0, (cudaStream_t)stream>>>(
                                (const __nv_bfloat16*)a->y, a->res, a->gamma, a->beta,
@@ -247,7 +249,7 @@ extern "C" int mmb_dropout_residual_ln_bwd(const mmb_drln_bwd_args* a, void* str
                 "drln_bwd: null pointer");
     MMB_REQUIRE(a->M > 0 && a->H > 0 && a->H % 8 == 0 && a->H <= 1024, "drln_bwd: bad shape M=%d H=%d", a->M, a->H);
     const uint32_t thresh = dropout_threshold(a->p_drop);
-    const float inv_keep = a->p_drop > 0.f ? 1.0f / (1.0f - a->p_drop) : 1.0f;
+    const float inv_keep = dropout_inv_keep(a->p_drop);
     const int grid = min((a->M + kLnWarps - 1) / kLnWarps, num_sms() * 2);
     const size_t smem = (size_t)kLnWarps * 3 * a->H * sizeof(float);
     MMB_DISPATCH_NCH(a->H, {

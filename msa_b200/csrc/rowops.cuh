@@ -97,18 +97,22 @@ __device__ __forceinline__ void row_round_bf16(RowF<NCH>& r) {
         for (int i = 0; i < 8; ++i) r.v[c][i] = bf16_round(r.v[c][i]);
 }
 
-// dropout on a row: element index base = row * H; identical in forward and backward.
+// dropout on a row (identical in forward and backward): one hash per column pair
 template <int NCH>
 __device__ __forceinline__ void row_dropout(RowF<NCH>& r, int H, int lane, uint64_t seed, uint32_t stream, uint64_t row,
                                             uint32_t thresh, float inv_keep) {
     if (thresh == 0u) return;
+    const uint32_t key = rng_row_key(seed, stream, (uint32_t)row);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
         const int e = (c * 32 + lane) * 8;
         if (e < H) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                r.v[c][i] = rng_keep(seed, stream, row * (uint64_t)H + e + i, thresh) ? r.v[c][i] * inv_keep : 0.f;
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t bits = rng_pair(key, (uint32_t)(e >> 1) + i);
+                r.v[c][2 * i] = rng_keep_lo(bits, thresh) ? r.v[c][2 * i] * inv_keep : 0.f;
+                r.v[c][2 * i + 1] = rng_keep_hi(bits, thresh) ? r.v[c][2 * i + 1] * inv_keep : 0.f;
+            }
         }
     }
 }

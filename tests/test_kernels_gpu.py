@@ -210,3 +210,28 @@ def test_attention_dropout_consistency():
     assert float(c1.std()) > 0.01     # some dropping actually happened
     c2, _ = run(x1)
     assert torch.equal(c1, c2)        # deterministic in (seed, stream)
+
+
+def test_attention_dropout_forward_backward_use_the_same_mask():
+    """V = identity makes ctx the dropped probability matrix P∘mask/(1-p) itself; the backward must then give
+    dV = (P∘mask/(1-p))^T dO with exactly that matrix."""
+    from msa_b200 import capi
+    torch.manual_seed(11)
+    nh, H, S, p = 1, 64, 64, 0.3
+    qkv = _bf(torch.randn(S, 3 * H, device="cuda") * 0.5)
+    qkv[:, 2 * H:] = torch.eye(S, device="cuda").to(torch.bfloat16)
+    keybias = torch.zeros(S, device="cuda")
+    cu_t = torch.tensor([0, S], device="cuda", dtype=torch.int32)
+    ctx = torch.empty(S, H, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(nh, S, device="cuda")
+    capi.call("attn_fwd", capi.attn_args(qkv, ctx, lse, keybias, cu_t, H, nh, S, p_drop=p, seed=5, rng_stream=2))
+    Pd = ctx.float()                                   # [q, k]
+    drop_rate = float((Pd == 0).float().mean())
+    assert abs(drop_rate - p) < 0.03
+    dctx = _bf(torch.randn(S, H, device="cuda"))
+    dqkv = torch.zeros(S, 3 * H, device="cuda", dtype=torch.bfloat16)
+    dsum = torch.empty(nh, S, device="cuda")
+    capi.call("attn_bwd", capi.attn_args(qkv, ctx, lse, keybias, cu_t, H, nh, S, dctx=dctx, dqkv=dqkv, dsum=dsum,
+                                         p_drop=p, seed=5, rng_stream=2))
+    dV = dqkv[:, 2 * H:].float()
+    assert _rel(dV, Pd.t() @ dctx.float()) < 2e-2
