@@ -19,61 +19,57 @@ enum { ACT_NONE = 0, ACT_TANH = 1, ACT_RELU = 2 };
 // Generic fp32 tiled GEMM for the head linears and their backward (64 x 64 tiles, 16-deep k-steps, 4 x 4 outputs
 // per thread).  C[m][n] (+)= act(sum_k A(m,k) B(k,n) + bias[n]) with A(m,k) = A[m*sam + k*sak] and
 // B(k,n) = B[k*sbk + n*sbn], so that Y = X W^T, dX = dY W and dW = dY^T X are the same kernel.
-constexpr int kSgBK = 64;   // deep k-steps: these GEMMs are tiny and latency-bound, so fewer load->sync->compute rounds win
+constexpr int kSgBK = 64;   // deep k-steps: fewer load -> sync -> compute rounds for these latency-bound GEMMs
+constexpr int kSgT = 32;    // 32 x 32 output tiles: the largest head GEMM (192 x 768) still yields 144 CTAs
 __global__ void __launch_bounds__(256)
 sgemm64_kernel(const float* __restrict__ A, int sam, int sak, const float* __restrict__ B, int sbk, int sbn,
                float* __restrict__ C, int ldc, const float* __restrict__ bias, int act, int M, int N, int K, int accumulate) {
-    __shared__ __align__(16) float As[kSgBK][68];
-    __shared__ __align__(16) float Bs[kSgBK][68];
+    __shared__ __align__(16) float As[kSgBK][kSgT + 2];
+    __shared__ __align__(16) float Bs[kSgBK][kSgT + 2];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int m0 = blockIdx.y * kSgT, n0 = blockIdx.x * kSgT;
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
     for (int k0 = 0; k0 < K; k0 += kSgBK) {
-        float ra[16], rb[16];
+        float ra[8], rb[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {      // all 32 loads of this thread are issued before any is consumed
-            const int idx = tid + i * 256;
+        for (int i = 0; i < 8; ++i) {       // all 16 loads of this thread are issued before any is consumed
+            const int idx = tid + i * 256;  // 2048 = 32 x 64 elements per operand tile
             int m, k;
-            if (sak == 1) { m = idx >> 6; k = idx & 63; } else { m = idx & 63; k = idx >> 6; }
+            if (sak == 1) { m = idx >> 6; k = idx & 63; } else { m = idx & 31; k = idx >> 5; }
             ra[i] = (m0 + m < M && k0 + k < K) ? __ldg(A + (size_t)(m0 + m) * sam + (size_t)(k0 + k) * sak) : 0.f;
             int kb, n;
-            if (sbn == 1) { kb = idx >> 6; n = idx & 63; } else { kb = idx & 63; n = idx >> 6; }
+            if (sbn == 1) { kb = idx >> 5; n = idx & 31; } else { kb = idx & 63; n = idx >> 6; }
             rb[i] = (n0 + n < N && k0 + kb < K) ? __ldg(B + (size_t)(k0 + kb) * sbk + (size_t)(n0 + n) * sbn) : 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
             const int idx = tid + i * 256;
             int m, k;
-            if (sak == 1) { m = idx >> 6; k = idx & 63; } else { m = idx & 63; k = idx >> 6; }
+            if (sak == 1) { m = idx >> 6; k = idx & 63; } else { m = idx & 31; k = idx >> 5; }
             As[k][m] = ra[i];
             int kb, n;
-            if (sbn == 1) { kb = idx >> 6; n = idx & 63; } else { kb = idx & 63; n = idx >> 6; }
+            if (sbn == 1) { kb = idx >> 5; n = idx & 31; } else { kb = idx & 63; n = idx >> 6; }
             Bs[kb][n] = rb[i];
         }
         __syncthreads();
 #pragma unroll 16
         for (int k = 0; k < kSgBK; ++k) {
-            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-            const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bb[j], acc[i][j]);
+            const float2 a = *reinterpret_cast<const float2*>(&As[k][ty * 2]);
+            const float2 bv = *reinterpret_cast<const float2*>(&Bs[k][tx * 2]);
+            acc[0][0] = fmaf(a.x, bv.x, acc[0][0]);
+            acc[0][1] = fmaf(a.x, bv.y, acc[0][1]);
+            acc[1][0] = fmaf(a.y, bv.x, acc[1][0]);
+            acc[1][1] = fmaf(a.y, bv.y, acc[1][1]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
+    for (int i = 0; i < 2; ++i) {
+        const int m = m0 + ty * 2 + i;
         if (m >= M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx * 4 + j;
+        for (int j = 0; j < 2; ++j) {
+            const int n = n0 + tx * 2 + j;
             if (n >= N) continue;
             float v = acc[i][j] + (bias ? bias[n] : 0.f);
             if (act == ACT_TANH) v = tanhf(v);
@@ -385,19 +381,19 @@ static HeadsWs heads_ws(int B, int H) {
 // Y[R,N] = act(X[R,K] W[N,K]^T + b)
 static inline void linear(cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy,
                           int R, int N, int K, int act) {
-    dim3 g((N + 63) / 64, (R + 63) / 64);
+    dim3 g((N + kSgT - 1) / kSgT, (R + kSgT - 1) / kSgT);
     sgemm64_kernel<<<g, 256, 0, st>>>(X, ldx, 1, W, 1, ldw, Y, ldy, b, act, R, N, K, 0);
 }
 // dX[R,K] (+)= dY[R,N] W[N,K]
 static inline void dx(cudaStream_t st, const float* dY, int ldy, const float* W, int ldw, float* dX, int ldx, int R, int N,
                       int K, int accumulate) {
-    dim3 g((K + 63) / 64, (R + 63) / 64);
+    dim3 g((K + kSgT - 1) / kSgT, (R + kSgT - 1) / kSgT);
     sgemm64_kernel<<<g, 256, 0, st>>>(dY, ldy, 1, W, ldw, 1, dX, ldx, nullptr, ACT_NONE, R, K, N, accumulate);
 }
 // dW[N,K] += dY[R,N]^T X[R,K] ; db[N] += colsum(dY)
 static inline void dw(cudaStream_t st, const float* dY, int ldy, const float* X, int ldx, float* dW, int ldw, float* db, int R,
                       int N, int K) {
-    dim3 g((K + 63) / 64, (N + 63) / 64);
+    dim3 g((K + kSgT - 1) / kSgT, (N + kSgT - 1) / kSgT);
     sgemm64_kernel<<<g, 256, 0, st>>>(dY, 1, ldy, X, ldx, 1, dW, ldw, nullptr, ACT_NONE, N, K, R, 1);
     if (db) bias_grad_kernel<<<(N + 127) / 128, 128, 0, st>>>(dY, ldy, db, R, N);
 }

@@ -272,7 +272,7 @@ extern "C" int mmb_colsum_bf16(const mmb_colsum_args* a, void* stream) {
     MMB_REQUIRE(a->M > 0 && a->N > 0 && a->N % 8 == 0 && a->ld % 8 == 0, "colsum: bad shape M=%d N=%d ld=%lld", a->M,
                 a->N, (long long)a->ld);
     const int strips = (a->N + 255) / 256;
-    int ysplit = (num_sms() * 2 + strips - 1) / strips;
+    int ysplit = (num_sms() * 8 + strips - 1) / strips;
     if (ysplit > (a->M + 63) / 64) ysplit = (a->M + 63) / 64;
     if (ysplit < 1) ysplit = 1;
     const int rows_per_cta = (a->M + ysplit - 1) / ysplit;
