@@ -170,6 +170,7 @@ typedef struct mmb_attn_args {
     float p_drop;
     uint64_t seed;
     uint32_t rng_stream;
+    uint32_t flags; /* bit 0: forward on the legacy mma.sync kernel instead of the tcgen05 one */
 } mmb_attn_args;
 int mmb_attn_fwd(const mmb_attn_args* a, void* stream);
 int mmb_attn_bwd(const mmb_attn_args* a, void* stream);

@@ -553,6 +553,8 @@ static int fill_params(AttnParams& p, const mmb_attn_args* a) {
     return MMB_OK;
 }
 
+int launch_attn_fwd_tc(const mmb_attn_args* a, cudaStream_t stream);   // attn_tc.cu
+
 }  // namespace mmb
 
 using namespace mmb;
@@ -562,6 +564,8 @@ extern "C" int mmb_attn_fwd(const mmb_attn_args* a, void* stream) {
     int rc = fill_params(p, a);
     if (rc != MMB_OK) return rc;
     MMB_REQUIRE(a->ctx != nullptr, "attn_fwd: null ctx");
+    // tcgen05 / TMEM kernel by default; flags bit 0 selects the legacy mma.sync kernel (kept for A/B checks)
+    if (!(a->flags & 1)) return launch_attn_fwd_tc(a, (cudaStream_t)stream);
     dim3 grid((a->max_seqlen + kTile - 1) / kTile, a->nheads, a->nseq);
     attn_fwd_kernel<<<grid, kAttnThreads, 0, (cudaStream_t)stream>>>(p);
     return check_launch("attn_fwd_kernel");

@@ -658,8 +658,7 @@ struct TmapKeyHash {
 
 // bf16 2-D tensor map, SWIZZLE_128B: dims {d0 (contiguous), d1 (rows)}, row stride ld elements, box {b0, b1}.
 // Cached: the encode is pure host work but the engine issues ~150 GEMMs per step over a fixed buffer set.
-static int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0,
-                          uint32_t b1) {
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0, uint32_t b1) {
     static std::mutex mu;
     static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
     TmapKey key{ptr, d0, d1, ld, b0, b1};

@@ -138,6 +138,38 @@ def _attn_ref(qkv, keybias, cu, H, nh):
     return torch.cat(outs)
 
 
+@pytest.mark.parametrize("lens,nh", [([50, 100, 100, 7], 2), ([129, 128, 1, 300], 3), ([550, 3, 201], 4)])
+def test_attention_tcgen05_forward_matches_legacy_kernel(lens, nh):
+    """The tcgen05/TMEM forward and the mma.sync forward implement the same contract (context + log2 LSE)."""
+    from msa_b200 import capi
+    torch.manual_seed(16)
+    H, rows = nh * 64, sum(lens)
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    qkv = _bf(torch.randn(rows, 3 * H, device="cuda"))
+    keybias = torch.where(torch.rand(rows, device="cuda") < 0.3, -10000.0, 0.0)
+    cu_t = torch.tensor(cu, device="cuda", dtype=torch.int32)
+    outs = []
+    for flags in (0, 1):
+        ctx = torch.zeros(rows, H, device="cuda", dtype=torch.bfloat16)
+        lse = torch.zeros(nh, rows, device="cuda")
+        capi.call("attn_fwd", capi.attn_args(qkv, ctx, lse, keybias, cu_t, H, nh, max(lens), flags=flags))
+        outs.append((ctx.float(), lse))
+    ref = _attn_ref(qkv.float(), keybias, cu, H, nh)
+    assert _rel(outs[0][0], ref) < 3 * BF16_EPS
+    assert _rel(outs[0][0], outs[1][0]) < 3 * BF16_EPS
+    assert _rel(outs[0][1], outs[1][1]) < 1e-4
+    # dropout: both kernels draw the same mask from (seed, stream, row, key pair)
+    for flags in (0, 1):
+        ctx = torch.zeros(rows, H, device="cuda", dtype=torch.bfloat16)
+        lse = torch.zeros(nh, rows, device="cuda")
+        capi.call("attn_fwd", capi.attn_args(qkv, ctx, lse, keybias, cu_t, H, nh, max(lens), p_drop=0.2, seed=3,
+                                             rng_stream=9, flags=flags))
+        outs.append(ctx.float())
+    assert _rel(outs[2], outs[3]) < 4 * BF16_EPS
+
+
 @pytest.mark.parametrize("lens,nh", [([50, 100, 100, 7], 2), ([64, 128, 65], 12), ([550, 3, 201], 4)])
 def test_attention_fwd_bwd(lens, nh):
     from msa_b200 import capi
