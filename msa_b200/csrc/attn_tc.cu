@@ -21,7 +21,7 @@ namespace mmb {
 constexpr int kTQ = 128;   // queries per CTA
 constexpr int kTK = 128;   // keys per tile
 constexpr int kHD = 64;    // head dim
-constexpr int kTcThreads = 128;
+constexpr int kTcThreads = 256;
 constexpr float kLog2eTc = 1.4426950408889634f;
 
 constexpr int kQBytes = kTQ * kHD * 2;        // 16 KB
@@ -29,7 +29,7 @@ constexpr int kKBytes = kTK * kHD * 2;        // 16 KB
 constexpr int kPBytes = kTQ * kTK * 2;        // 32 KB: two 64-key SWIZZLE_128B slabs
 // Q 16 KB + K 16 KB (single buffer: free again as soon as S = Q K^T has retired, i.e. reloaded under the softmax)
 // + V 2 x 16 KB + P 32 KB + key bias 1 KB + barriers: ~98 KB, two CTAs per SM
-constexpr int kTcSmem = kQBytes + kKBytes + 2 * kKBytes + kPBytes + 2 * kTK * 4 + 128 + 1024;
+constexpr int kTcSmem = kQBytes + kKBytes + 2 * kKBytes + kPBytes + 4 * kTK * 4 + 128 + 1024;
 
 struct AttnTcParams {
     __nv_bfloat16* ctx;
@@ -57,10 +57,18 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ float ptx_ex2(float x) {   // MUFU.EX2 (flush-to-zero): ex2(-inf) = 0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void sts128_tc(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 
+// 256 threads: warps 0-3 own key columns 0-63 of the score tile, warps 4-7 columns 64-127 (a warp may only touch
+// the TMEM lane quarter 32*(warp%4)..+31, so the two groups share the rows and split the columns); 2 CTAs per SM
+// = 16 resident warps, which is what hides the tcgen05.ld / MUFU / LDS latencies of the softmax.
 __global__ void __launch_bounds__(kTcThreads, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -70,15 +78,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
     const uint32_t sV = sK + kKBytes;                 // [2][16 KB]
     const uint32_t sP = sV + 2 * kKBytes;             // 32 KB
     float* sBias = reinterpret_cast<float*>(smem + kQBytes + 3 * kKBytes + kPBytes);   // [2][128]
-    const uint32_t bars = sP + kPBytes + 2 * kTK * 4;
+    float* sMax = sBias + 2 * kTK;                                                      // [2][128] partial row maxima
+    const uint32_t bars = sP + kPBytes + 4 * kTK * 4;
     const uint32_t bar_q = bars, bar_k = bars + 8, bar_v0 = bars + 16, bar_v1 = bars + 24, bar_s = bars + 32, bar_o = bars + 40;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kQBytes + 3 * kKBytes + kPBytes + 2 * kTK * 4 + 64);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kQBytes + 3 * kKBytes + kPBytes + 4 * kTK * 4 + 64);
 
     const int seq = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
     const int row0 = p.cu_seqlens[seq];
     const int S = p.cu_seqlens[seq + 1] - row0;
     if (qt * kTQ >= S) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int half = warp >> 2;                       // which 64 key columns of the tile
+    const int r = (warp & 3) * 32 + lane;             // query row inside the tile = TMEM lane
     const int nkv = (S + kTK - 1) / kTK;
 
     if (tid == 0) {
@@ -96,8 +107,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tS = tmem, tO = tmem + 128;
-    const uint32_t lane_bits = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_bits = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem + lane_bits + half * 64;          // this thread's 64 score columns
+    const uint32_t tO = tmem + 128 + lane_bits + half * 32;    // this thread's 32 output columns
 
     const int col_q = head * kHD, col_k = p.H + head * kHD, col_v = 2 * p.H + head * kHD;
     auto load_k = [&](int kt) {    // thread 0 only
@@ -116,11 +128,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         load_v(0);
         if (nkv > 1) load_v(1);
     }
-    // key bias (log2 domain) of the first tiles; keys beyond the sequence are -inf
-    for (int i = tid; i < 2 * kTK; i += kTcThreads) {
-        const int k = i;   // tile (i / 128), key (i % 128)
-        sBias[i] = k < S ? p.keybias[row0 + k] * kLog2eTc : -INFINITY;
-    }
+    // key bias (log2 domain) of the first two tiles; keys beyond the sequence are -inf
+    sBias[tid] = tid < S ? p.keybias[row0 + tid] * kLog2eTc : -INFINITY;
     __syncthreads();
 
     // instruction descriptors: S: M=128,N=128, both K-major; PV: M=128,N=64, A K-major (P), B MN-major (V)
@@ -128,10 +137,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
     const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(kHD >> 3) << 17) |
                              ((uint32_t)(kTQ >> 4) << 24);
 
-    const int q = qt * kTQ + tid;   // this thread's query row
-    float m_run = -INFINITY, l_run = 0.f;
+    const int q = qt * kTQ + r;     // this thread's query row in the sequence
+    float m_run = -INFINITY, l_run = 0.f;   // l_run: partial sum over this thread's column half
     const uint32_t row_key = p.thresh ? rng_row_key(p.seed, p.rng_stream, (uint32_t)(((uint32_t)seq * p.nheads + head) * (uint32_t)S + q)) : 0u;
-    const int r7 = tid & 7;
+    const int r7 = r & 7;
 
     for (int kt = 0; kt < nkv; ++kt) {
         const int st = kt & 1;
@@ -144,7 +153,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
             for (int k = 0; k < kHD / 16; ++k) {
                 const uint64_t da = ptx::umma_desc_sw128(sQ + k * 32, 0, 1024);
                 const uint64_t db = ptx::umma_desc_sw128(sK + k * 32, 0, 1024);
-                ptx::umma_bf16(tS, da, db, idesc_s, k > 0 ? 1u : 0u);
+                ptx::umma_bf16(tmem, da, db, idesc_s, k > 0 ? 1u : 0u);
             }
             ptx::umma_commit(bar_s);
         }
@@ -153,66 +162,82 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         ptx::tc_fence_after();
         if (tid == 0 && kt + 1 < nkv) load_k(kt + 1);   // K is free again: fetch the next tile under the softmax
         __syncwarp();
-        const float* bias = sBias + st * kTK;
-        // ---- pass 1: row maximum of the scaled + biased scores
-        float m_tile = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < kTK; c += 32) {
+        const float4* bias4 = reinterpret_cast<const float4*>(sBias + st * kTK + half * 64);
+        // ---- pass 1: partial row maximum over this thread's 64 columns, combined with the other half via smem
+        float m_part = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 64; c += 32) {
             uint32_t raw[32];
-            ptx::tmem_ld_32x32(tS + lane_bits + c, raw);
+            ptx::tmem_ld_32x32(tS + c, raw);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, fmaf(__uint_as_float(raw[i]), p.scale_log2, bias[c + i]));
+            for (int i = 0; i < 8; ++i) {
+                const float4 b = bias4[(c >> 2) + i];
+                m_part = fmaxf(m_part, fmaf(__uint_as_float(raw[4 * i + 0]), p.scale_log2, b.x));
+                m_part = fmaxf(m_part, fmaf(__uint_as_float(raw[4 * i + 1]), p.scale_log2, b.y));
+                m_part = fmaxf(m_part, fmaf(__uint_as_float(raw[4 * i + 2]), p.scale_log2, b.z));
+                m_part = fmaxf(m_part, fmaf(__uint_as_float(raw[4 * i + 3]), p.scale_log2, b.w));
+            }
         }
-        const float m_new = fmaxf(m_run, m_tile);
-        const float corr = exp2f(m_run - m_new);
-        // ---- previous P V must have retired before O is rescaled and P is overwritten
+        sMax[half * kTK + r] = m_part;
+        // previous P V must have retired before O is rescaled and P is overwritten (waited before the barrier so
+        // that thread 0 can refill the freed V stage right after it)
         if (kt > 0) {
             ptx::mbar_wait(bar_o, (kt - 1) & 1);
             ptx::tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < kHD; c += 32) {
-                uint32_t raw[32];
-                ptx::tmem_ld_32x32(tO + lane_bits + c, raw);
-                ptx::tmem_ld_wait();
+        }
+        __syncthreads();
+        const float m_new = fmaxf(m_run, fmaxf(sMax[r], sMax[kTK + r]));
+        // a fully masked-so-far row (all -inf) keeps m = -inf: use 0 as the reference to avoid inf - inf
+        const float m_ref = m_new == -INFINITY ? 0.f : m_new;
+        const float corr = ptx_ex2(m_run - m_ref);
+        if (kt > 0) {
+            uint32_t raw[32];
+            ptx::tmem_ld_32x32(tO, raw);
+            ptx::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * corr);
-                tmem_st_32x32(tO + lane_bits + c, raw);
-            }
+            for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * corr);
+            tmem_st_32x32(tO, raw);
             tmem_st_wait();
-            // the V stage consumed by tile kt-1 is free: prefetch tile kt+1 into it
-            if (tid == 0 && kt + 1 < nkv) load_v(kt + 1);
-            if (kt + 1 < nkv) {
+            if (tid == 0 && kt + 1 < nkv) load_v(kt + 1);      // the V stage consumed by tile kt-1 is free
+            if (kt + 1 < nkv && tid < kTK) {
                 const int k0 = (kt + 1) * kTK;
                 sBias[(st ^ 1) * kTK + tid] = (k0 + tid) < S ? p.keybias[row0 + k0 + tid] * kLog2eTc : -INFINITY;
             }
+        } else if (nkv > 1 && tid < kTK) {
+            sBias[kTK + tid] = (kTK + tid) < S ? p.keybias[row0 + kTK + tid] * kLog2eTc : -INFINITY;
         }
-        // ---- pass 2: probabilities -> bf16 P in shared memory (K-major SWIZZLE_128B slabs), running sum
+        // ---- pass 2: probabilities -> bf16 P row of slab `half` (K-major SWIZZLE_128B), partial running sum
         float l_tile = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < kTK; c += 32) {
+        const uint32_t prow = sP + half * (kTQ * 128) + r * 128;
+#pragma unroll
+        for (int c = 0; c < 64; c += 32) {
             uint32_t raw[32];
-            ptx::tmem_ld_32x32(tS + lane_bits + c, raw);
+            ptx::tmem_ld_32x32(tS + c, raw);
             ptx::tmem_ld_wait();
             float pv[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                pv[i] = exp2f(fmaf(__uint_as_float(raw[i]), p.scale_log2, bias[c + i]) - m_new);
-                l_tile += pv[i];
+            for (int i = 0; i < 8; ++i) {
+                const float4 b = bias4[(c >> 2) + i];
+                pv[4 * i + 0] = ptx_ex2(fmaf(__uint_as_float(raw[4 * i + 0]), p.scale_log2, b.x - m_ref));
+                pv[4 * i + 1] = ptx_ex2(fmaf(__uint_as_float(raw[4 * i + 1]), p.scale_log2, b.y - m_ref));
+                pv[4 * i + 2] = ptx_ex2(fmaf(__uint_as_float(raw[4 * i + 2]), p.scale_log2, b.z - m_ref));
+                pv[4 * i + 3] = ptx_ex2(fmaf(__uint_as_float(raw[4 * i + 3]), p.scale_log2, b.w - m_ref));
             }
-            if (p.thresh != 0u) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) l_tile += pv[i];
+            if (p.thresh != 0u) {     // dropped entries become 0; the 1/(1-p) rescale is applied once in the epilogue
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const uint32_t bits = rng_pair(row_key, (uint32_t)(kt * kTK + c + 2 * i) >> 1);
-                    pv[2 * i] = rng_keep_lo(bits, p.thresh) ? pv[2 * i] * p.inv_keep : 0.f;
-                    pv[2 * i + 1] = rng_keep_hi(bits, p.thresh) ? pv[2 * i + 1] * p.inv_keep : 0.f;
+                    const uint32_t bits = rng_pair(row_key, (uint32_t)(kt * kTK + half * 64 + c + 2 * i) >> 1);
+                    pv[2 * i] = rng_keep_lo(bits, p.thresh) ? pv[2 * i] : 0.f;
+                    pv[2 * i + 1] = rng_keep_hi(bits, p.thresh) ? pv[2 * i + 1] : 0.f;
                 }
             }
-            const uint32_t slab = sP + (c >> 6) * (kTQ * 128) + tid * 128;
-            const int ch0 = (c & 63) >> 3;   // first 16-byte chunk of this 32-key group inside the 64-key slab
+            const int ch0 = c >> 3;   // first 16-byte chunk of this 32-key group inside the 64-key slab row
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                sts128_tc(slab + (((ch0 + j) ^ r7) << 4), pack_bf16x2(pv[8 * j + 0], pv[8 * j + 1]),
+                sts128_tc(prow + (((ch0 + j) ^ r7) << 4), pack_bf16x2(pv[8 * j + 0], pv[8 * j + 1]),
                           pack_bf16x2(pv[8 * j + 2], pv[8 * j + 3]), pack_bf16x2(pv[8 * j + 4], pv[8 * j + 5]),
                           pack_bf16x2(pv[8 * j + 6], pv[8 * j + 7]));
         }
@@ -229,23 +254,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
             for (int k = 0; k < kTK / 16; ++k) {
                 const uint64_t da = ptx::umma_desc_sw128(sP + (k >> 2) * (kTQ * 128) + (k & 3) * 32, 0, 1024);
                 const uint64_t db = ptx::umma_desc_sw128(sV + st * kKBytes + k * 2048, 8192, 1024);
-                ptx::umma_bf16(tO, da, db, idesc_o, (kt > 0 || k > 0) ? 1u : 0u);
+                ptx::umma_bf16(tmem + 128, da, db, idesc_o, (kt > 0 || k > 0) ? 1u : 0u);
             }
             ptx::umma_commit(bar_o);
         }
         __syncwarp();
     }
-    // ---- epilogue: O / l -> bf16 context row, LSE
+    // ---- epilogue: O * inv_keep / l -> bf16 context row (this thread: 32 of the 64 columns), LSE
+    sMax[half * kTK + r] = l_run;          // combine the two column halves' partial sums
     ptx::mbar_wait(bar_o, (nkv - 1) & 1);
     ptx::tc_fence_after();
-    const float inv_l = 1.f / l_run;
-    __nv_bfloat16* out = p.ctx + (int64_t)(row0 + q) * p.H + head * kHD;
-#pragma unroll 1
-    for (int c = 0; c < kHD; c += 32) {
+    __syncthreads();
+    const float l_tot = sMax[r] + sMax[kTK + r];
+    const float inv_l = p.inv_keep / l_tot;
+    {
         uint32_t raw[32];
-        ptx::tmem_ld_32x32(tO + lane_bits + c, raw);
+        ptx::tmem_ld_32x32(tO, raw);
         ptx::tmem_ld_wait();
         if (q < S) {
+            __nv_bfloat16* out = p.ctx + (int64_t)(row0 + q) * p.H + head * kHD + half * 32;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint4 u;
@@ -253,12 +280,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
                 u.y = pack_bf16x2(__uint_as_float(raw[8 * j + 2]) * inv_l, __uint_as_float(raw[8 * j + 3]) * inv_l);
                 u.z = pack_bf16x2(__uint_as_float(raw[8 * j + 4]) * inv_l, __uint_as_float(raw[8 * j + 5]) * inv_l);
                 u.w = pack_bf16x2(__uint_as_float(raw[8 * j + 6]) * inv_l, __uint_as_float(raw[8 * j + 7]) * inv_l);
-                *reinterpret_cast<uint4*>(out + c + 8 * j) = u;
+                *reinterpret_cast<uint4*>(out + 8 * j) = u;
             }
         }
-        __syncwarp();
     }
-    if (q < S && p.lse != nullptr) p.lse[(int64_t)head * p.total_rows + row0 + q] = m_run + log2f(l_run);
+    if (half == 0 && q < S && p.lse != nullptr) p.lse[(int64_t)head * p.total_rows + row0 + q] = m_run + log2f(l_tot);
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) {
