@@ -166,6 +166,9 @@ typedef struct mmb_attn_args {
     const void* dctx;       /* bwd: [rows, H] bf16 */
     void* dqkv;             /* bwd: [rows, 3H] bf16 */
     float* dsum;            /* bwd scratch: [heads, rows] */
+    const int32_t* kv_end;  /* [nseq] or NULL: keys at index >= kv_end[seq] are all masked (bias -10000) and are
+                               skipped in whole tiles — exact in fp32: exp(-10000 + x - max) == 0 whenever an
+                               unmasked key exists; a sequence with kv_end == 0 is processed in full */
     int32_t H, nheads, nseq, max_seqlen, total_rows;
     float p_drop;
     uint64_t seed;
@@ -197,6 +200,7 @@ typedef struct mmb_pack_args {
     float* keybias;        /* [rows] */
     int32_t* cu_seqlens;   /* [3B+1] */
     int32_t* label_count;  /* [3] */
+    int32_t* kv_end;       /* [3B] or NULL: 1 + index of the last key whose mask is set, per sequence */
     int32_t B, T;
     int32_t L[2];
 } mmb_pack_args;

@@ -188,9 +188,9 @@ def colsum(X, out):
 
 
 def attn_args(qkv, ctx, lse, keybias, cu_seqlens, H, nheads, max_seqlen, dctx=None, dqkv=None, dsum=None,
-              p_drop=0.0, seed=0, rng_stream=0, flags=0):
+              p_drop=0.0, seed=0, rng_stream=0, flags=0, kv_end=None):
     return fill(AttnArgs(), qkv=qkv, ctx=ctx, lse=lse, keybias=keybias, cu_seqlens=cu_seqlens, dctx=dctx, dqkv=dqkv,
-                dsum=dsum, H=H, nheads=nheads, nseq=cu_seqlens.numel() - 1, max_seqlen=max_seqlen,
+                dsum=dsum, kv_end=kv_end, H=H, nheads=nheads, nseq=cu_seqlens.numel() - 1, max_seqlen=max_seqlen,
                 total_rows=qkv.shape[0], p_drop=p_drop, seed=seed, rng_stream=rng_stream, flags=flags)
 
 

@@ -119,6 +119,7 @@ struct AttnParams {
     float* lse;                 // [heads, rows]  log2-domain logsumexp of the scaled+biased scores
     const float* keybias;       // [rows] additive mask per key ((1-m) * -10000)
     const int* cu_seqlens;      // [nseq + 1]
+    const int* kv_end;          // [nseq] or null (see mmb_attn_args)
     // backward
     const __nv_bfloat16* dctx;  // [rows, H]
     __nv_bfloat16* dqkv;        // [rows, 3H]
@@ -133,6 +134,12 @@ struct AttnParams {
 };
 
 // dropout generator row id of query q of (seq, head): the probability row; columns are the keys
+// number of leading keys that can carry probability mass (everything behind is masked in whole tiles)
+__device__ __forceinline__ int effective_keys(const int* kv_end, int seq, int S) {
+    if (kv_end == nullptr) return S;
+    const int e = kv_end[seq];
+    return (e <= 0 || e > S) ? S : e;
+}
 __device__ __forceinline__ uint32_t prob_row_id(int seq, int head, int nheads, int S, int q) {
     return ((uint32_t)seq * (uint32_t)nheads + (uint32_t)head) * (uint32_t)S + (uint32_t)q;
 }
@@ -156,7 +163,7 @@ attn_fwd_kernel(const AttnParams p) {
     const __nv_bfloat16* Kg = p.qkv + (int64_t)row0 * ld + p.H + head * kD;
     const __nv_bfloat16* Vg = Kg + p.H;
     const uint32_t sQa = ptx::smem_u32(sQ), sKa = ptx::smem_u32(sK), sVa = ptx::smem_u32(sV);
-    const int nkv = (S + kTile - 1) / kTile;
+    const int nkv = (effective_keys(p.kv_end, seq, S) + kTile - 1) / kTile;
 
     tile_load_async(sQa, Qg, ld, S - qt * kTile, tid);
     tile_load_async(sKa, Kg, ld, S, tid);
@@ -314,6 +321,16 @@ attn_bwd_dkv_kernel(const AttnParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int64_t ld = 3 * (int64_t)p.H;
+    if (kt * kTile >= effective_keys(p.kv_end, seq, S)) {
+        // every key of this tile is masked: P == 0 exactly, so dK = dV = 0
+        __nv_bfloat16* dKz = p.dqkv + (int64_t)(row0 + kt * kTile) * ld + p.H + head * kD;
+        const int nrows = min(kTile, S - kt * kTile);
+        for (int i = tid; i < nrows * 16; i += kAttnThreads) {      // 16 x 16 B = dK row (128 B) + dV row (128 B)
+            const int r = i >> 4, c = i & 15;
+            *reinterpret_cast<uint4*>(dKz + (int64_t)r * ld + (c >> 3) * p.H + (c & 7) * 8) = make_uint4(0, 0, 0, 0);
+        }
+        return;
+    }
     const __nv_bfloat16* Qg = p.qkv + (int64_t)row0 * ld + head * kD;
     const __nv_bfloat16* Kg = Qg + p.H + (int64_t)kt * kTile * ld;
     const __nv_bfloat16* Vg = Kg + p.H;
@@ -448,7 +465,7 @@ attn_bwd_dq_kernel(const AttnParams p) {
     const __nv_bfloat16* Vg = Kg + p.H;
     const __nv_bfloat16* dOg = p.dctx + (int64_t)(row0 + qt * kTile) * p.H + head * kD;
     const uint32_t sQa = ptx::smem_u32(sQ), sdOa = ptx::smem_u32(sdO), sKa = ptx::smem_u32(sK), sVa = ptx::smem_u32(sV);
-    const int nkv = (S + kTile - 1) / kTile;
+    const int nkv = (effective_keys(p.kv_end, seq, S) + kTile - 1) / kTile;
 
     tile_load_async(sQa, Qg, ld, S - qt * kTile, tid);
     tile_load_async(sdOa, dOg, p.H, S - qt * kTile, tid);
@@ -538,6 +555,7 @@ static int fill_params(AttnParams& p, const mmb_attn_args* a) {
     p.lse = a->lse;
     p.keybias = a->keybias;
     p.cu_seqlens = a->cu_seqlens;
+    p.kv_end = a->kv_end;
     p.dctx = (const __nv_bfloat16*)a->dctx;
     p.dqkv = (__nv_bfloat16*)a->dqkv;
     p.dsum = a->dsum;

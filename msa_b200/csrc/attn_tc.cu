@@ -36,6 +36,7 @@ struct AttnTcParams {
     float* lse;
     const float* keybias;
     const int* cu_seqlens;
+    const int* kv_end;
     int H, nheads, total_rows;
     float scale_log2;
     uint32_t thresh;
@@ -90,7 +91,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int half = warp >> 2;                       // which 64 key columns of the tile
     const int r = (warp & 3) * 32 + lane;             // query row inside the tile = TMEM lane
-    const int nkv = (S + kTK - 1) / kTK;
+    int s_eff = S;                                    // keys behind kv_end are masked in whole tiles: skipped (exact)
+    if (p.kv_end != nullptr) {
+        const int e = p.kv_end[seq];
+        if (e > 0 && e < S) s_eff = e;
+    }
+    const int nkv = (s_eff + kTK - 1) / kTK;
 
     if (tid == 0) {
         ptx::prefetch_tensormap(&tm_qkv);
@@ -304,6 +310,7 @@ int launch_attn_fwd_tc(const mmb_attn_args* a, cudaStream_t stream) {
     p.lse = a->lse;
     p.keybias = a->keybias;
     p.cu_seqlens = a->cu_seqlens;
+    p.kv_end = a->kv_end;
     p.H = a->H;
     p.nheads = a->nheads;
     p.total_rows = a->total_rows;

@@ -59,6 +59,7 @@ struct PrepParams {
     float* keybias;             // [rows]
     int* cu_seqlens;            // [3B + 1]
     int* label_count;           // [3]
+    int* kv_end;                // [3B] or null
 };
 
 __global__ void pack_prepare_kernel(const PrepParams p) {
@@ -74,6 +75,7 @@ __global__ void pack_prepare_kernel(const PrepParams p) {
             m = load_as_float(p.mask_frame[c.pass - 1], p.mask_frame_dt[c.pass - 1], ((int64_t)c.b * L + (c.s - p.d.T)) * D);
         }
         p.keybias[row] = (1.0f - m) * -10000.0f;
+        if (p.kv_end != nullptr && m >= 0.5f) atomicMax(p.kv_end + c.pass * p.d.B + c.b, c.s + 1);
         if (p.labels[c.pass] != nullptr && p.labels[c.pass][(int64_t)c.b * p.d.S(c.pass) + c.s] != -100) cnt[c.pass]++;
     }
 #pragma unroll
@@ -495,7 +497,9 @@ extern "C" int mmb_pack_prepare(const mmb_pack_args* a, void* stream) {
     p.keybias = a->keybias;
     p.cu_seqlens = a->cu_seqlens;
     p.label_count = a->label_count;
+    p.kv_end = a->kv_end;
     MMB_CUDA(cudaMemsetAsync(a->label_count, 0, 3 * sizeof(int), (cudaStream_t)stream));
+    if (a->kv_end) MMB_CUDA(cudaMemsetAsync(a->kv_end, 0, 3 * (size_t)a->B * sizeof(int), (cudaStream_t)stream));
     const int rows = p.d.rows();
     const int grid = min((rows + 255) / 256, num_sms() * 2);
     pack_prepare_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);

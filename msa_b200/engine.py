@@ -57,6 +57,7 @@ class Plan:
         # ---- packed metadata
         self.keybias, self.cu = buf(M, dtype=F32), buf(3 * B + 1, dtype=I32)
         self.label_count = buf(4, dtype=I32)
+        self.kv_end = buf(3 * B, dtype=I32)     # per sequence: 1 + last unmasked key (attention skips the masked tail)
         # ---- activations (kept for backward when training; one reused set in eval)
         nsets = N if training else 1
         self.x = [buf(M, H) for _ in range(N + 1)] if training else [buf(M, H), buf(M, H)]
@@ -116,7 +117,7 @@ class Plan:
         st = self.store
         f = []
         self.pack_args = capi.fill(capi.PackArgs(), keybias=self.keybias, cu_seqlens=self.cu,
-                                   label_count=self.label_count, B=self.B, T=self.T, L=[self.Lv, self.La],
+                                   label_count=self.label_count, kv_end=self.kv_end, B=self.B, T=self.T, L=[self.Lv, self.La],
                                    frame_dim=[self.Dv, self.Da])
         f.append((self._fn("pack_prepare"), self.pack_args))
         je = "bert.jointEmbeddings."
@@ -153,7 +154,7 @@ class Plan:
             bqkv = st.span(pre + "attention.self.query.bias", pre + "attention.self.value.bias")
             self._gemm(f, xin, wqkv, L["qkv"], M, 3 * H, H, bias=bqkv)
             a = capi.attn_args(L["qkv"], L["ctx"], L["lse"], self.keybias, self.cu, H, self.nh, self.max_S,
-                               p_drop=self.p_attn, rng_stream=(l << 8) | ST_ATTN)
+                               p_drop=self.p_attn, rng_stream=(l << 8) | ST_ATTN, kv_end=self.kv_end)
             L["attn_args"] = a
             self._seeded.append(a)
             f.append((self._fn("attn_fwd"), a))

@@ -267,3 +267,35 @@ def test_attention_dropout_forward_backward_use_the_same_mask():
                                          p_drop=p, seed=5, rng_stream=2))
     dV = dqkv[:, 2 * H:].float()
     assert _rel(dV, Pd.t() @ dctx.float()) < 2e-2
+
+
+def test_attention_masked_tail_skipping_is_exact():
+    """kv_end lets the kernels skip whole key tiles behind the last unmasked key; results must be identical to the
+    full computation (forward context / LSE and all three gradients)."""
+    from msa_b200 import capi
+    torch.manual_seed(21)
+    nh, lens = 2, [550, 300, 40]
+    valid = [131, 300, 0]          # seq 0: masked tail from key 131; seq 1: nothing masked; seq 2: everything masked
+    H, rows = nh * 64, sum(lens)
+    cu = [0, 550, 850, 890]
+    qkv = _bf(torch.randn(rows, 3 * H, device="cuda"))
+    keybias = torch.zeros(rows, device="cuda")
+    keybias[131:550] = -10000.0
+    keybias[850:890] = -10000.0
+    kv_end = torch.tensor(valid, device="cuda", dtype=torch.int32)
+    cu_t = torch.tensor(cu, device="cuda", dtype=torch.int32)
+    dctx = _bf(torch.randn(rows, H, device="cuda"))
+    res = []
+    for kv in (None, kv_end):
+        ctx = torch.zeros(rows, H, device="cuda", dtype=torch.bfloat16)
+        lse = torch.zeros(nh, rows, device="cuda")
+        dqkv = torch.full((rows, 3 * H), 7.0, device="cuda", dtype=torch.bfloat16)
+        dsum = torch.empty(nh, rows, device="cuda")
+        a = capi.attn_args(qkv, ctx, lse, keybias, cu_t, H, nh, max(lens), dctx=dctx, dqkv=dqkv, dsum=dsum, kv_end=kv,
+                           p_drop=0.1, seed=4, rng_stream=1)
+        capi.call("attn_fwd", a)
+        capi.call("attn_bwd", a)
+        res.append((ctx.float(), lse.clone(), dqkv.float()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert torch.equal(res[0][2], res[1][2])
+    assert float(res[1][2][131:550, H:].abs().max()) == 0.0        # dK, dV of masked keys

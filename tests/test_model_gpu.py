@@ -188,3 +188,56 @@ def test_missing_library_or_cpu_model_fails_loudly():
     batch = synth.make_batch(2, 8, 8, 8, 47, 74, vocab_size=256, seed=1, min_len=4)
     with pytest.raises(capi.MMBError):
         m(**batch)       # CPU model: no fallback
+
+
+def test_sentiment_mae_after_k_steps_matches_cpu_training():
+    """BASELINE.json: 'bf16 path within ... 1e-2 absolute on sentiment MAE after a fixed number of steps'.
+    K = 8 optimizer steps on one batch, dropout off: the CUDA path with the fused AdamW vs the fp64 CPU oracle
+    trained with a plain torch restatement of transformers(<=4.x).AdamW (train.py:76-92 grouping: no weight decay
+    for names containing 'bias' / 'LayerNorm.weight'; parameters without gradient are skipped)."""
+    from msa_b200.optim import FusedAdamW
+    ocfg = O.Cfg(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256, vocab_size=512,
+                 max_position_embeddings=64)
+    sd = seeded_state_dict(ocfg, "mosi", seed=31, std=0.03)
+    batch = synth.make_batch(6, 12, 12, 12, 47, 74, vocab_size=512, seed=13, min_len=5)
+    K, lr, wd, b1, b2, eps = 8, 2e-3, 0.01, 0.9, 0.999, 1e-6
+    # ---- CUDA path
+    m = _build(ocfg, "mosi", sd).train()
+    opt = FusedAdamW(m, lr=lr, weight_decay=wd)
+    dbatch = synth.tree_to(batch, "cuda")
+    for _ in range(K):
+        out, logits = m(**dbatch)
+        out[0].mean().backward()
+        opt.step()
+        opt.zero_grad()
+    m.eval()
+    with torch.no_grad():
+        _, logits = m(**dbatch)
+    mae_gpu = float((logits.view(-1).float().cpu() - batch["sentiment"]).abs().mean())
+    # ---- CPU oracle training
+    params = {k: v.double().clone() for k, v in sd.items() if k not in O.TIED}
+    mom = {k: torch.zeros_like(v) for k, v in params.items()}
+    var = {k: torch.zeros_like(v) for k, v in params.items()}
+    for t in range(1, K + 1):
+        full = dict(params)
+        for alias, canon in O.TIED.items():
+            full[alias] = params[canon]
+        _, _, grads = O.forward_backward(full, ocfg, batch)
+        step = lr * (1 - b2 ** t) ** 0.5 / (1 - b1 ** t)
+        for k, g in grads.items():
+            if g is None:
+                continue
+            mom[k] = mom[k] * b1 + (1 - b1) * g
+            var[k] = var[k] * b2 + (1 - b2) * g * g
+            params[k] = params[k] - step * mom[k] / (var[k].sqrt() + eps)
+            if not ("bias" in k or "LayerNorm.weight" in k):
+                params[k] = params[k] - lr * wd * params[k]
+    full = dict(params)
+    for alias, canon in O.TIED.items():
+        full[alias] = params[canon]
+    with torch.no_grad():
+        _, ref_logits = O.forward(full, ocfg, **batch)
+    mae_ref = float((ref_logits.view(-1) - batch["sentiment"].double()).abs().mean())
+    mae0 = float((O.forward(sd, ocfg, **batch)[1].view(-1) - batch["sentiment"].double()).abs().mean())
+    assert mae_ref < mae0                       # training moved the regression head at all
+    assert abs(mae_gpu - mae_ref) < 1e-2, (mae_gpu, mae_ref, mae0)
