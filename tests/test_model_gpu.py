@@ -192,7 +192,8 @@ def test_missing_library_or_cpu_model_fails_loudly():
 
 def test_sentiment_mae_after_k_steps_matches_cpu_training():
     """BASELINE.json: 'bf16 path within ... 1e-2 absolute on sentiment MAE after a fixed number of steps'.
-    K = 8 optimizer steps on one batch, dropout off: the CUDA path with the fused AdamW vs the fp64 CPU oracle
+    K = 12 optimizer steps at the reference's default learning rate (train.py:30, 5e-4) on one batch, dropout off:
+    the CUDA path with the fused AdamW vs the fp64 CPU oracle
     trained with a plain torch restatement of transformers(<=4.x).AdamW (train.py:76-92 grouping: no weight decay
     for names containing 'bias' / 'LayerNorm.weight'; parameters without gradient are skipped)."""
     from msa_b200.optim import FusedAdamW
@@ -200,7 +201,11 @@ def test_sentiment_mae_after_k_steps_matches_cpu_training():
                  max_position_embeddings=64)
     sd = seeded_state_dict(ocfg, "mosi", seed=31, std=0.03)
     batch = synth.make_batch(6, 12, 12, 12, 47, 74, vocab_size=512, seed=13, min_len=5)
-    K, lr, wd, b1, b2, eps = 8, 2e-3, 0.01, 0.9, 0.999, 1e-6
+    # (Calibration, scripts/debug_mae.py: at lr 2e-3 the joint loss - which subtracts the unbounded NCE term -
+    # collapses from 5.2 to 0.45 in 8 steps and Adam's sign-like first steps amplify bf16 gradient noise on
+    # zero-gradient parameters chaotically (0.035 MAE gap by step 8); at the reference's lr the two runs track to
+    # 1.2e-4 over 12 steps.)
+    K, lr, wd, b1, b2, eps = 12, 5e-4, 0.01, 0.9, 0.999, 1e-6
     # ---- CUDA path
     m = _build(ocfg, "mosi", sd).train()
     opt = FusedAdamW(m, lr=lr, weight_decay=wd)
@@ -241,3 +246,5 @@ def test_sentiment_mae_after_k_steps_matches_cpu_training():
     mae0 = float((O.forward(sd, ocfg, **batch)[1].view(-1) - batch["sentiment"].double()).abs().mean())
     assert mae_ref < mae0                       # training moved the regression head at all
     assert abs(mae_gpu - mae_ref) < 1e-2, (mae_gpu, mae_ref, mae0)
+    # and the agreement is meaningful relative to how far training moved the MAE
+    assert abs(mae_gpu - mae_ref) < 0.2 * (mae0 - mae_ref), (mae_gpu, mae_ref, mae0)
