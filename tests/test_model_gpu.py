@@ -192,7 +192,7 @@ def test_missing_library_or_cpu_model_fails_loudly():
 
 def test_sentiment_mae_after_k_steps_matches_cpu_training():
     """BASELINE.json: 'bf16 path within ... 1e-2 absolute on sentiment MAE after a fixed number of steps'.
-    K = 12 optimizer steps at the reference's default learning rate (train.py:30, 5e-4) on one batch, dropout off:
+    K = 12 optimizer steps at the reference's default learning rate (train.py:29, 5e-4) on one batch, dropout off:
     the CUDA path with the fused AdamW vs the fp64 CPU oracle
     trained with a plain torch restatement of transformers(<=4.x).AdamW (train.py:76-92 grouping: no weight decay
     for names containing 'bias' / 'LayerNorm.weight'; parameters without gradient are skipped)."""
