@@ -572,6 +572,7 @@ static int fill_params(AttnParams& p, const mmb_attn_args* a) {
 }
 
 int launch_attn_fwd_tc(const mmb_attn_args* a, cudaStream_t stream);   // attn_tc.cu
+int launch_attn_bwd_tc(const mmb_attn_args* a, cudaStream_t stream);   // attn_bwd_tc.cu
 
 }  // namespace mmb
 
@@ -599,6 +600,7 @@ extern "C" int mmb_attn_bwd(const mmb_attn_args* a, void* stream) {
                                                                                      a->H, a->nheads);
     rc = check_launch("attn_bwd_dsum_kernel");
     if (rc != MMB_OK) return rc;
+    if (!(a->flags & 1)) return launch_attn_bwd_tc(a, (cudaStream_t)stream);
     dim3 grid((a->max_seqlen + kTile - 1) / kTile, a->nheads, a->nseq);
     constexpr int kBwdSmem = 6 * kTile * 128 + 6 * kTile * (int)sizeof(float);
     static bool attr_set = false;

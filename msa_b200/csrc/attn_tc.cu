@@ -29,7 +29,7 @@ constexpr int kKBytes = kTK * kHD * 2;        // 16 KB
 constexpr int kPBytes = kTQ * kTK * 2;        // 32 KB: two 64-key SWIZZLE_128B slabs
 // Q 16 KB + K 16 KB (single buffer: free again as soon as S = Q K^T has retired, i.e. reloaded under the softmax)
 // + V 2 x 16 KB + P 32 KB + key bias 1 KB + barriers: ~98 KB, two CTAs per SM
-constexpr int kTcSmem = kQBytes + kKBytes + 2 * kKBytes + kPBytes + 4 * kTK * 4 + 128 + 1024;
+constexpr int kTcSmem = kQBytes + kKBytes + 2 * kKBytes + kPBytes + 6 * kTK * 4 + 128 + 1024;
 
 struct AttnTcParams {
     __nv_bfloat16* ctx;
@@ -80,9 +80,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
     const uint32_t sP = sV + 2 * kKBytes;             // 32 KB
     float* sBias = reinterpret_cast<float*>(smem + kQBytes + 3 * kKBytes + kPBytes);   // [2][128]
     float* sMax = sBias + 2 * kTK;                                                      // [2][128] partial row maxima
-    const uint32_t bars = sP + kPBytes + 4 * kTK * 4;
+    uint32_t* sKk = reinterpret_cast<uint32_t*>(sMax + 2 * kTK);                       // [2][128] dropout key-column keys
+    const uint32_t bars = sP + kPBytes + 6 * kTK * 4;
     const uint32_t bar_q = bars, bar_k = bars + 8, bar_v0 = bars + 16, bar_v1 = bars + 24, bar_s = bars + 32, bar_o = bars + 40;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kQBytes + 3 * kKBytes + kPBytes + 4 * kTK * 4 + 64);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kQBytes + 3 * kKBytes + kPBytes + 6 * kTK * 4 + 64);
 
     const int seq = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
     const int row0 = p.cu_seqlens[seq];
@@ -135,7 +136,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         if (nkv > 1) load_v(1);
     }
     // key bias (log2 domain) of the first two tiles; keys beyond the sequence are -inf
+    const uint32_t prob_base = ((uint32_t)seq * (uint32_t)p.nheads + (uint32_t)head) * (uint32_t)S;
     sBias[tid] = tid < S ? p.keybias[row0 + tid] * kLog2eTc : -INFINITY;
+    if (p.thresh != 0u) sKk[tid] = attn_drop_kkey(p.seed, p.rng_stream, prob_base + (uint32_t)tid);
     __syncthreads();
 
     // instruction descriptors: S: M=128,N=128, both K-major; PV: M=128,N=64, A K-major (P), B MN-major (V)
@@ -145,7 +148,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
 
     const int q = qt * kTQ + r;     // this thread's query row in the sequence
     float m_run = -INFINITY, l_run = 0.f;   // l_run: partial sum over this thread's column half
-    const uint32_t row_key = p.thresh ? rng_row_key(p.seed, p.rng_stream, (uint32_t)(((uint32_t)seq * p.nheads + head) * (uint32_t)S + q)) : 0u;
+    const uint32_t qkey = p.thresh ? attn_drop_qkey(p.seed, p.rng_stream, prob_base + (uint32_t)q) : 0u;
+    const uint32_t thresh32 = p.thresh << 16;
     const int r7 = r & 7;
 
     for (int kt = 0; kt < nkv; ++kt) {
@@ -209,9 +213,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
             if (kt + 1 < nkv && tid < kTK) {
                 const int k0 = (kt + 1) * kTK;
                 sBias[(st ^ 1) * kTK + tid] = (k0 + tid) < S ? p.keybias[row0 + k0 + tid] * kLog2eTc : -INFINITY;
+                if (p.thresh != 0u) sKk[(st ^ 1) * kTK + tid] = attn_drop_kkey(p.seed, p.rng_stream, prob_base + (uint32_t)(k0 + tid));
             }
         } else if (nkv > 1 && tid < kTK) {
-            sBias[kTK + tid] = (kTK + tid) < S ? p.keybias[row0 + kTK + tid] * kLog2eTc : -INFINITY;
+            // (already filled by the prologue: tiles 0 and 1 are loaded up front)
         }
         // ---- pass 2: probabilities -> bf16 P row of slab `half` (K-major SWIZZLE_128B), partial running sum
         float l_tile = 0.f;
@@ -233,11 +238,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
 #pragma unroll
             for (int i = 0; i < 32; ++i) l_tile += pv[i];
             if (p.thresh != 0u) {     // dropped entries become 0; the 1/(1-p) rescale is applied once in the epilogue
+                const uint4* kk4 = reinterpret_cast<const uint4*>(sKk + st * kTK + half * 64 + c);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const uint32_t bits = rng_pair(row_key, (uint32_t)(kt * kTK + half * 64 + c + 2 * i) >> 1);
-                    pv[2 * i] = rng_keep_lo(bits, p.thresh) ? pv[2 * i] : 0.f;
-                    pv[2 * i + 1] = rng_keep_hi(bits, p.thresh) ? pv[2 * i + 1] : 0.f;
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 kk = kk4[i];
+                    pv[4 * i + 0] = attn_keep(qkey, kk.x, thresh32) ? pv[4 * i + 0] : 0.f;
+                    pv[4 * i + 1] = attn_keep(qkey, kk.y, thresh32) ? pv[4 * i + 1] : 0.f;
+                    pv[4 * i + 2] = attn_keep(qkey, kk.z, thresh32) ? pv[4 * i + 2] : 0.f;
+                    pv[4 * i + 3] = attn_keep(qkey, kk.w, thresh32) ? pv[4 * i + 3] : 0.f;
                 }
             }
             const int ch0 = c >> 3;   // first 16-byte chunk of this 32-key group inside the 64-key slab row

@@ -137,6 +137,41 @@ __device__ __forceinline__ bool rng_keep_col(uint32_t row_key, uint32_t col, uin
     const uint32_t bits = rng_pair(row_key, col >> 1);
     return (col & 1u) ? rng_keep_hi(bits, thresh16) : rng_keep_lo(bits, thresh16);
 }
+
+// Attention-probability dropout (tcgen05 kernels): the decision for (query q, key k) is
+//     keep  <=>  (qkey[q] * kkey[k]) mod 2^32  >=  thresh16 << 16
+// with two ODD 32-bit keys hashed once per query row / key column of a (sequence, head).  One IMAD + one compare
+// per probability, and — unlike a per-row stream — equally cheap whether a thread walks along the keys of one
+// query (forward, dQ) or along the queries of one key (dK/dV).  For a fixed odd qkey the map kkey -> product is a
+// bijection of the odd residues, so every row (and every column) of the mask is an independent uniform draw.
+__device__ __forceinline__ uint32_t attn_drop_qkey(uint64_t seed, uint32_t stream, uint32_t prob_row) {
+    return rng_row_key(seed, stream, prob_row) | 1u;
+}
+__device__ __forceinline__ uint32_t attn_drop_kkey(uint64_t seed, uint32_t stream, uint32_t prob_row) {
+    return rng_row_key(seed ^ 0x9E3779B97F4A7C15ull, stream ^ 0x5bd1e995u, prob_row) | 1u;
+}
+__device__ __forceinline__ bool attn_keep(uint32_t qkey, uint32_t kkey, uint32_t thresh32) { return qkey * kkey >= thresh32; }
+
+// packed fp32 x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2 — half the issue slots of the scalar forms)
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
 #endif  // __CUDACC__
 
 // 16-bit dropout threshold and the matching unbiased rescale 1 / (1 - thresh16 / 65536)
