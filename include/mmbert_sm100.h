@@ -155,7 +155,11 @@ int mmb_colsum_bf16(const mmb_colsum_args* a, void* stream);
  * Q|K|V are read in place from the fused projection output qkv [rows, 3H] (Q at column h*64, K at
  * H + h*64, V at 2H + h*64); keybias[row] = (1 - mask) * -10000 for the key stored at that packed row.
  * lse ([heads, rows] f32, log2 domain) is saved for backward.  mmb_attn_bwd writes dQ|dK|dV into dqkv with
- * the same layout (autograd of the same lines); dsum [heads, rows] f32 is caller-provided scratch.
+ * the same layout (autograd of the same lines); bwd_ws is caller-provided scratch of
+ * mmb_attn_bwd_workspace_bytes(total_rows, nheads) bytes, 16-byte aligned (per-(head, row) records: -LSE,
+ * -rowsum(dO * O), dropout keys and the scaled key bias, laid out for the kernels' TMA producer).
+ * Dropout masks are a function of (seed, rng_stream, head, packed row of the query, packed row of the key): forward
+ * and backward regenerate identical masks, nothing is stored.
  */
 typedef struct mmb_attn_args {
     const void* qkv;        /* [rows, 3H] bf16 */
@@ -165,7 +169,7 @@ typedef struct mmb_attn_args {
     const int32_t* cu_seqlens; /* [nseq + 1] row offsets */
     const void* dctx;       /* bwd: [rows, H] bf16 */
     void* dqkv;             /* bwd: [rows, 3H] bf16 */
-    float* dsum;            /* bwd scratch: [heads, rows] */
+    void* bwd_ws;           /* bwd scratch: mmb_attn_bwd_workspace_bytes(total_rows, nheads) bytes */
     const int32_t* kv_end;  /* [nseq] or NULL: keys at index >= kv_end[seq] are all masked (bias -10000) and are
                                skipped in whole tiles — exact in fp32: exp(-10000 + x - max) == 0 whenever an
                                unmasked key exists; a sequence with kv_end == 0 is processed in full */
@@ -173,8 +177,9 @@ typedef struct mmb_attn_args {
     float p_drop;
     uint64_t seed;
     uint32_t rng_stream;
-    uint32_t flags; /* bit 0: forward on the legacy mma.sync kernel instead of the tcgen05 one */
+    uint32_t flags; /* reserved, must be 0 */
 } mmb_attn_args;
+size_t mmb_attn_bwd_workspace_bytes(int total_rows, int nheads);
 int mmb_attn_fwd(const mmb_attn_args* a, void* stream);
 int mmb_attn_bwd(const mmb_attn_args* a, void* stream);
 

@@ -15,7 +15,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
-]
+] + os.environ.get("MMB_NVCC_EXTRA", "").split()      # bring-up only, e.g. MMB_NVCC_EXTRA=-DMMB_ATTN_TRACE
 
 
 def _sources():

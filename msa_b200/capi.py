@@ -187,10 +187,18 @@ def colsum(X, out):
     call("colsum_bf16", colsum_args(X, out))
 
 
-def attn_args(qkv, ctx, lse, keybias, cu_seqlens, H, nheads, max_seqlen, dctx=None, dqkv=None, dsum=None,
+def attn_bwd_workspace(total_rows, nheads, device):
+    """Scratch tensor for mmb_attn_bwd (size from mmb_attn_bwd_workspace_bytes)."""
+    L = lib()
+    L.mmb_attn_bwd_workspace_bytes.restype = ctypes.c_size_t
+    L.mmb_attn_bwd_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+    return torch.empty(L.mmb_attn_bwd_workspace_bytes(total_rows, nheads) // 4, device=device, dtype=torch.float32)
+
+
+def attn_args(qkv, ctx, lse, keybias, cu_seqlens, H, nheads, max_seqlen, dctx=None, dqkv=None, bwd_ws=None,
               p_drop=0.0, seed=0, rng_stream=0, flags=0, kv_end=None):
     return fill(AttnArgs(), qkv=qkv, ctx=ctx, lse=lse, keybias=keybias, cu_seqlens=cu_seqlens, dctx=dctx, dqkv=dqkv,
-                dsum=dsum, kv_end=kv_end, H=H, nheads=nheads, nseq=cu_seqlens.numel() - 1, max_seqlen=max_seqlen,
+                bwd_ws=bwd_ws, kv_end=kv_end, H=H, nheads=nheads, nseq=cu_seqlens.numel() - 1, max_seqlen=max_seqlen,
                 total_rows=qkv.shape[0], p_drop=p_drop, seed=seed, rng_stream=rng_stream, flags=flags)
 
 

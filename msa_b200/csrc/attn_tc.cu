@@ -136,7 +136,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         if (nkv > 1) load_v(1);
     }
     // key bias (log2 domain) of the first two tiles; keys beyond the sequence are -inf
-    const uint32_t prob_base = ((uint32_t)seq * (uint32_t)p.nheads + (uint32_t)head) * (uint32_t)S;
+    const uint32_t prob_base = (uint32_t)head * (uint32_t)p.total_rows + (uint32_t)row0;   // + index in the sequence
     sBias[tid] = tid < S ? p.keybias[row0 + tid] * kLog2eTc : -INFINITY;
     if (p.thresh != 0u) sKk[tid] = attn_drop_kkey(p.seed, p.rng_stream, prob_base + (uint32_t)tid);
     __syncthreads();

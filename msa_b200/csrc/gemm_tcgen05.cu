@@ -756,6 +756,32 @@ static int launch_gemm(const mmb_gemm_args* a, cudaStream_t stream) {
     return check_launch("gemm_tcgen05_kernel");
 }
 
+// Planes of 16-byte records [planes][records], box = {nbox records, 1 plane}, no swizzle: the per-(head, row) records of
+// the attention backward (attn.cu) copied next to the operand tiles.  Encoded as pairs of 64-bit elements so that a
+// 128-record box stays within the 256-element box limit and every record offset is a 16-byte aligned address.
+int make_tmap_rec16(CUtensorMap* out, const void* ptr, uint64_t records, uint64_t planes, uint32_t nbox) {
+    const uint64_t d0 = 2 * records, d1 = planes, ld = 2 * records;
+    const uint32_t b0 = 2 * nbox;
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) {
+        set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+        return MMB_ECUDA;
+    }
+    cuuint64_t dims[2] = {d0, d1};
+    cuuint64_t strides[1] = {ld * 8};
+    cuuint32_t box[2] = {b0, 1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled (16-byte records) failed (%d) ptr=%p dims=(%llu,%llu) ld=%llu box=%u", (int)r, ptr,
+                       (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)ld, b0);
+        return MMB_ECUDA;
+    }
+    return MMB_OK;
+}
+
 // CTA-pair kernel: 256 x 256 tiles, one cluster of 2 per SM pair.
 static int launch_gemm_2cta(const mmb_gemm_args* a, cudaStream_t stream) {
     CUtensorMap tmA, tmB;

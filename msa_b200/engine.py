@@ -88,7 +88,7 @@ class Plan:
             self.GB, self.GD = buf(M, H, dtype=F32), buf(M, H, dtype=F32)    # fp32: residual-stream gradients
             self.GT = buf(M, H)                                              # bf16 scratch (LM-head d_tln, dCtx)
             self.dqkv, self.du = buf(M, 3 * H), buf(M, I)
-            self.dsum = buf(nh, M, dtype=F32)
+            self.attn_ws = capi.attn_bwd_workspace(M, nh, dev)
             self.dpre = buf(max(nfr, 1), H)
         self._seeded = []      # arg structs carrying a dropout seed
         self._build_forward()
@@ -280,7 +280,7 @@ class Plan:
             self._gemm(b, self.GC, self._w(pre + "attention.output.dense.weight"), self.GT, M, H, H, b_major=MN)
             self._gemm(b, self.GC, L["ctx"], self._g(pre + "attention.output.dense.weight"), H, H, M, a_major=MN,
                        b_major=MN, epilogue=ATOM, split_k=_split_k(H, H, M))
-            capi.fill(L["attn_args"], dctx=self.GT, dqkv=self.dqkv, dsum=self.dsum)
+            capi.fill(L["attn_args"], dctx=self.GT, dqkv=self.dqkv, bwd_ws=self.attn_ws)
             b.append((self._fn("attn_bwd"), L["attn_args"]))
             wqkv = st.span(pre + "attention.self.query.weight", pre + "attention.self.value.weight", st.bf16).view(3 * H, H)
             gwqkv = st.span(pre + "attention.self.query.weight", pre + "attention.self.value.weight", st.grad).view(3 * H, H)

@@ -30,10 +30,10 @@ ctx = torch.empty(rows, H, device=dev, dtype=torch.bfloat16)
 lse = torch.empty(nh, rows, device=dev)
 dctx = torch.randn(rows, H, device=dev).to(torch.bfloat16)
 dqkv = torch.empty(rows, 3 * H, device=dev, dtype=torch.bfloat16)
-dsum = torch.empty(nh, rows, device=dev)
+bwd_ws = capi.attn_bwd_workspace(rows, nh, dev)
 flops_fwd = sum(4.0 * n * n * H for n in lens)           # dense S x S, as the reference computes
-for flags in (0, 1):
-    a = capi.attn_args(qkv, ctx, lse, keybias, cu_t, H, nh, max(lens), dctx=dctx, dqkv=dqkv, dsum=dsum, kv_end=kv_end,
+for flags in (0,):
+    a = capi.attn_args(qkv, ctx, lse, keybias, cu_t, H, nh, max(lens), dctx=dctx, dqkv=dqkv, bwd_ws=bwd_ws, kv_end=kv_end,
                        p_drop=p_drop, seed=1, rng_stream=1, flags=flags)
     for name in ("attn_fwd", "attn_bwd"):
         for _ in range(3):
@@ -47,4 +47,4 @@ for flags in (0, 1):
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
         fl = flops_fwd * (1.0 if name == "attn_fwd" else 2.5)
-        print(f"{shape} p={p_drop} {'legacy' if flags else 'tcgen05'} {name}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s (dense-equivalent)")
+        print(f"{shape} p={p_drop} {name}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s (dense-equivalent)")

@@ -138,31 +138,8 @@ def _attn_ref(qkv, keybias, cu, H, nh):
     return torch.cat(outs)
 
 
-@pytest.mark.parametrize("lens,nh", [([50, 100, 100, 7], 2), ([129, 128, 1, 300], 3), ([550, 3, 201], 4)])
-def test_attention_tcgen05_forward_matches_legacy_kernel(lens, nh):
-    """The tcgen05/TMEM forward and the mma.sync forward implement the same contract (context + log2 LSE)."""
-    from msa_b200 import capi
-    torch.manual_seed(16)
-    H, rows = nh * 64, sum(lens)
-    cu = [0]
-    for n in lens:
-        cu.append(cu[-1] + n)
-    qkv = _bf(torch.randn(rows, 3 * H, device="cuda"))
-    keybias = torch.where(torch.rand(rows, device="cuda") < 0.3, -10000.0, 0.0)
-    cu_t = torch.tensor(cu, device="cuda", dtype=torch.int32)
-    outs = []
-    for flags in (0, 1):
-        ctx = torch.zeros(rows, H, device="cuda", dtype=torch.bfloat16)
-        lse = torch.zeros(nh, rows, device="cuda")
-        capi.call("attn_fwd", capi.attn_args(qkv, ctx, lse, keybias, cu_t, H, nh, max(lens), flags=flags))
-        outs.append((ctx.float(), lse))
-    ref = _attn_ref(qkv.float(), keybias, cu, H, nh)
-    assert _rel(outs[0][0], ref) < 3 * BF16_EPS
-    assert _rel(outs[0][0], outs[1][0]) < 3 * BF16_EPS
-    assert _rel(outs[0][1], outs[1][1]) < 1e-4
-
-
-@pytest.mark.parametrize("lens,nh", [([50, 100, 100, 7], 2), ([64, 128, 65], 12), ([550, 3, 201], 4)])
+@pytest.mark.parametrize("lens,nh", [([50, 100, 100, 7], 2), ([64, 128, 65], 12), ([550, 3, 201], 4), ([129, 128, 1, 300], 3),
+                                     ([2048, 1], 1)])
 def test_attention_fwd_bwd(lens, nh):
     from msa_b200 import capi
     torch.manual_seed(6)
@@ -185,8 +162,8 @@ def test_attention_fwd_bwd(lens, nh):
     dctx = _bf(torch.randn(rows, H, device="cuda"))
     ref.backward(dctx.float())
     dqkv = torch.zeros(rows, 3 * H, device="cuda", dtype=torch.bfloat16)
-    dsum = torch.empty(nh, rows, device="cuda")
-    capi.call("attn_bwd", capi.attn_args(qkv, ctx, lse, keybias, cu_t, H, nh, max(lens), dctx=dctx, dqkv=dqkv, dsum=dsum))
+    bwd_ws = capi.attn_bwd_workspace(rows, nh, "cuda")
+    capi.call("attn_bwd", capi.attn_args(qkv, ctx, lse, keybias, cu_t, H, nh, max(lens), dctx=dctx, dqkv=dqkv, bwd_ws=bwd_ws))
     for j, name in enumerate("QKV"):
         got, want = dqkv[:, j * H:(j + 1) * H].float(), x.grad[:, j * H:(j + 1) * H]
         assert _rel(got, want) < 2e-2, name   # P and dS are rounded to bf16 before the second MMA
@@ -254,8 +231,8 @@ def test_attention_dropout_forward_backward_use_the_same_mask():
     assert abs(drop_rate - p) < 0.03
     dctx = _bf(torch.randn(S, H, device="cuda"))
     dqkv = torch.zeros(S, 3 * H, device="cuda", dtype=torch.bfloat16)
-    dsum = torch.empty(nh, S, device="cuda")
-    capi.call("attn_bwd", capi.attn_args(qkv, ctx, lse, keybias, cu_t, H, nh, S, dctx=dctx, dqkv=dqkv, dsum=dsum,
+    bwd_ws = capi.attn_bwd_workspace(S, nh, "cuda")
+    capi.call("attn_bwd", capi.attn_args(qkv, ctx, lse, keybias, cu_t, H, nh, S, dctx=dctx, dqkv=dqkv, bwd_ws=bwd_ws,
                                          p_drop=p, seed=5, rng_stream=2))
     dV = dqkv[:, 2 * H:].float()
     assert _rel(dV, Pd.t() @ dctx.float()) < 2e-2
@@ -282,8 +259,8 @@ def test_attention_masked_tail_skipping_is_exact():
         ctx = torch.zeros(rows, H, device="cuda", dtype=torch.bfloat16)
         lse = torch.zeros(nh, rows, device="cuda")
         dqkv = torch.full((rows, 3 * H), 7.0, device="cuda", dtype=torch.bfloat16)
-        dsum = torch.empty(nh, rows, device="cuda")
-        a = capi.attn_args(qkv, ctx, lse, keybias, cu_t, H, nh, max(lens), dctx=dctx, dqkv=dqkv, dsum=dsum, kv_end=kv,
+        bwd_ws = capi.attn_bwd_workspace(rows, nh, "cuda")
+        a = capi.attn_args(qkv, ctx, lse, keybias, cu_t, H, nh, max(lens), dctx=dctx, dqkv=dqkv, bwd_ws=bwd_ws, kv_end=kv,
                            p_drop=0.1, seed=4, rng_stream=1)
         capi.call("attn_fwd", a)
         capi.call("attn_bwd", a)
