@@ -64,7 +64,11 @@ enum {
     MMB_EPI_RELU_BF16 = 2,      /* C(bf16) = relu(acc + bias)                                        */
     MMB_EPI_STORE_F32 = 3,      /* C(f32)  = acc + bias                                              */
     MMB_EPI_ATOMIC_ADD_F32 = 4, /* C(f32) += acc   (red.global.add; split-K capable; bias ignored)   */
-    MMB_EPI_DGELU_BF16 = 5      /* C(bf16) = acc * gelu_erf'(aux[m,n]); aux is an INPUT (pre-act)    */
+    MMB_EPI_DGELU_BF16 = 5,     /* C(bf16) = acc * gelu_erf'(aux[m,n]); aux is an INPUT (pre-act)    */
+    MMB_EPI_GELU_GRAD_BF16 = 6, /* C(bf16) = gelu_erf(acc + bias); aux(bf16, out) = gelu_erf'(acc + bias): the
+                                   forward of BertIntermediate saves the activation's derivative instead of the
+                                   pre-activation, so that its backward is a plain multiply (next mode)   */
+    MMB_EPI_MUL_AUX_BF16 = 7    /* C(bf16) = acc * aux[m,n]; aux is an INPUT                           */
 };
 
 typedef struct mmb_gemm_args {

@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmmbert_sm100.so")
 
 MMB_OK, MMB_EINVAL, MMB_EARCH, MMB_ECUDA = 0, -1, -2, -3
 MAJOR_K, MAJOR_MN = 0, 1
-EPI_STORE_BF16, EPI_GELU_BF16, EPI_RELU_BF16, EPI_STORE_F32, EPI_ATOMIC_ADD_F32, EPI_DGELU_BF16 = range(6)
+(EPI_STORE_BF16, EPI_GELU_BF16, EPI_RELU_BF16, EPI_STORE_F32, EPI_ATOMIC_ADD_F32, EPI_DGELU_BF16, EPI_GELU_GRAD_BF16,
+ EPI_MUL_AUX_BF16) = range(8)
 
 _lib = None
 

@@ -172,6 +172,23 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
         : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
     return *reinterpret_cast<float2*>(&d);
 }
+// Packed (two values per instruction) erf-GELU and its derivative, same approximation as gelu_fast / gelu_fast_grad:
+// the GEMM epilogues that apply them are bound by issue slots, not by the MMA.
+__device__ __forceinline__ void gelu_fast2(float2 x, float2& g, float2& dg) {
+    const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+    const float2 den = fma2(make_float2(0.47047f * 0.70710678118654752f, 0.47047f * 0.70710678118654752f), ax,
+                            make_float2(1.0f, 1.0f));
+    const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+    float2 poly = fma2(make_float2(0.7478556f, 0.7478556f), t, make_float2(-0.0958798f, -0.0958798f));
+    poly = fma2(poly, t, make_float2(0.3480242f, 0.3480242f));
+    const float2 xx = mul2(x, mul2(x, make_float2(-0.72134752044448170f, -0.72134752044448170f)));
+    const float2 e = make_float2(ex2_approx(xx.x), ex2_approx(xx.y));                       // exp(-x^2 / 2)
+    const float2 erf_abs = fma2(mul2(poly, t), make_float2(-e.x, -e.y), make_float2(1.0f, 1.0f));
+    const float2 serf = make_float2(copysignf(erf_abs.x, x.x), copysignf(erf_abs.y, x.y));
+    const float2 cdf = fma2(serf, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));      // Phi(x)
+    g = mul2(x, cdf);
+    dg = fma2(mul2(x, make_float2(0.3989422804014327f, 0.3989422804014327f)), e, cdf);     // Phi(x) + x phi(x)
+}
 #endif  // __CUDACC__
 
 // 16-bit dropout threshold and the matching unbiased rescale 1 / (1 - thresh16 / 65536)

@@ -169,15 +169,18 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[3
     const int nvalid = min(32, p.N - col0);
     const int row = row_base + lane;
     const bool row_ok = row < p.M;
-    if (p.bias != nullptr && p.epilogue != MMB_EPI_ATOMIC_ADD_F32 && p.epilogue != MMB_EPI_DGELU_BF16) {
+    if (p.bias != nullptr && p.epilogue != MMB_EPI_ATOMIC_ADD_F32 && p.epilogue != MMB_EPI_DGELU_BF16 &&
+        p.epilogue != MMB_EPI_MUL_AUX_BF16) {
         if (nvalid == 32) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);
-                v[4 * i] += b.x;
-                v[4 * i + 1] += b.y;
-                v[4 * i + 2] += b.z;
-                v[4 * i + 3] += b.w;
+                const float2 lo = add2(make_float2(v[4 * i], v[4 * i + 1]), make_float2(b.x, b.y));
+                const float2 hi = add2(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(b.z, b.w));
+                v[4 * i] = lo.x;
+                v[4 * i + 1] = lo.y;
+                v[4 * i + 2] = hi.x;
+                v[4 * i + 3] = hi.y;
             }
         } else {
 #pragma unroll
@@ -194,10 +197,50 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[3
         case MMB_EPI_GELU_BF16: {
             if (p.aux != nullptr) stage_row(st + 2048, v, lane);   // pre-activation, rounded to bf16 by the pack
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+            for (int i = 0; i < 32; i += 2) {
+                float2 g, dg;
+                gelu_fast2(make_float2(v[i], v[i + 1]), g, dg);
+                v[i] = g.x;
+                v[i + 1] = g.y;
+            }
             stage_row(st, v, lane);
             if (p.aux != nullptr)
                 flush_stage(st + 2048, reinterpret_cast<__nv_bfloat16*>(p.aux), p.ldaux, row_base, p.M, col0, p.N, lane);
+            flush_stage(st, Cb, p.ldc, row_base, p.M, col0, p.N, lane);
+        } break;
+        case MMB_EPI_GELU_GRAD_BF16: {
+            float d[32];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                float2 g, dg;
+                gelu_fast2(make_float2(v[i], v[i + 1]), g, dg);
+                v[i] = g.x;
+                v[i + 1] = g.y;
+                d[i] = dg.x;
+                d[i + 1] = dg.y;
+            }
+            stage_row(st + 2048, d, lane);
+            stage_row(st, v, lane);
+            flush_stage(st + 2048, reinterpret_cast<__nv_bfloat16*>(p.aux), p.ldaux, row_base, p.M, col0, p.N, lane);
+            flush_stage(st, Cb, p.ldc, row_base, p.M, col0, p.N, lane);
+        } break;
+        case MMB_EPI_MUL_AUX_BF16: {
+            fill_stage(st + 2048, reinterpret_cast<const __nv_bfloat16*>(p.aux), p.ldaux, row_base, p.M, col0, p.N, lane);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t q0, q1, q2, q3;
+                lds128(st + 2048 + stage_off(lane, j), q0, q1, q2, q3);
+                const float2 f0 = unpack_bf16x2(q0), f1 = unpack_bf16x2(q1), f2 = unpack_bf16x2(q2), f3 = unpack_bf16x2(q3);
+                v[8 * j + 0] *= f0.x;
+                v[8 * j + 1] *= f0.y;
+                v[8 * j + 2] *= f1.x;
+                v[8 * j + 3] *= f1.y;
+                v[8 * j + 4] *= f2.x;
+                v[8 * j + 5] *= f2.y;
+                v[8 * j + 6] *= f3.x;
+                v[8 * j + 7] *= f3.y;
+            }
+            stage_row(st, v, lane);
             flush_stage(st, Cb, p.ldc, row_base, p.M, col0, p.N, lane);
         } break;
         case MMB_EPI_RELU_BF16: {
@@ -578,11 +621,49 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const int r = t - ks * mn_tiles;
             const int m_blk = r / p.n_tiles;   // n fastest: the tiles that share an A row-panel run concurrently
             const int n_blk = r - m_blk * p.n_tiles;
+            const int row_base = m_blk * TM + (int)rank * 128 + quarter * 32;
+            // MUL_AUX: this thread's 128 aux values (its row, the warp's column half) are fetched BEFORE waiting for the
+            // accumulator, so the global-load latency hides under the tile's MMAs instead of stalling every chunk
+            const int colw = n_blk * TN + half * kColsPerWarp;
+            const bool aux_pref = p.epilogue == MMB_EPI_MUL_AUX_BF16 && colw + kColsPerWarp <= p.N && !(p.dbg & 48);
+            uint4 auxr[kColsPerWarp / 8];
+            if (aux_pref) {
+                const int row = row_base + lane;
+                const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) +
+                                                                  (size_t)(row < p.M ? row : 0) * p.ldaux + colw);
+#pragma unroll
+                for (int j = 0; j < kColsPerWarp / 8; ++j) auxr[j] = __ldg(src + j);
+            }
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
-            const int row_base = m_blk * TM + (int)rank * 128 + quarter * 32;
+            if (aux_pref) {
+                __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(p.C);
+#pragma unroll
+                for (int ci = 0; ci < kColsPerWarp / 32; ++ci) {
+                    uint32_t raw[32];
+                    const uint32_t taddr = tmem_base + acc * TN + half * kColsPerWarp + ci * 32 + ((uint32_t)(quarter * 32) << 16);
+                    ptx::tmem_ld_32x32(taddr, raw);
+                    ptx::tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 q = auxr[4 * ci + j];
+                        const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
+                        v[8 * j + 0] = __uint_as_float(raw[8 * j + 0]) * p.alpha * f0.x;
+                        v[8 * j + 1] = __uint_as_float(raw[8 * j + 1]) * p.alpha * f0.y;
+                        v[8 * j + 2] = __uint_as_float(raw[8 * j + 2]) * p.alpha * f1.x;
+                        v[8 * j + 3] = __uint_as_float(raw[8 * j + 3]) * p.alpha * f1.y;
+                        v[8 * j + 4] = __uint_as_float(raw[8 * j + 4]) * p.alpha * f2.x;
+                        v[8 * j + 5] = __uint_as_float(raw[8 * j + 5]) * p.alpha * f2.y;
+                        v[8 * j + 6] = __uint_as_float(raw[8 * j + 6]) * p.alpha * f3.x;
+                        v[8 * j + 7] = __uint_as_float(raw[8 * j + 7]) * p.alpha * f3.y;
+                    }
+                    stage_row(stage_buf, v, lane);
+                    flush_stage(stage_buf, Cb, p.ldc, row_base, p.M, colw + ci * 32, p.N, lane);
+                }
+            }
 #pragma unroll 1
-            for (int c = 0; c < kColsPerWarp; c += 32) {
+            for (int c = aux_pref ? kColsPerWarp : 0; c < kColsPerWarp; c += 32) {
                 const int col0 = n_blk * TN + half * kColsPerWarp + c;
                 if (col0 >= p.N) break;
                 if (p.dbg & 32) continue;
@@ -822,10 +903,10 @@ extern "C" int mmb_gemm(const mmb_gemm_args* a, void* stream) {
     MMB_REQUIRE((a->ldc % (f32_out ? 4 : 8)) == 0, "mmb_gemm: ldc=%lld misaligned", (long long)a->ldc);
     MMB_REQUIRE(((uintptr_t)a->A % 16) == 0 && ((uintptr_t)a->B % 16) == 0 && ((uintptr_t)a->C % 16) == 0,
                 "mmb_gemm: operands must be 16-byte aligned");
-    MMB_REQUIRE(a->epilogue >= 0 && a->epilogue <= MMB_EPI_DGELU_BF16, "mmb_gemm: bad epilogue %d", a->epilogue);
+    MMB_REQUIRE(a->epilogue >= 0 && a->epilogue <= MMB_EPI_MUL_AUX_BF16, "mmb_gemm: bad epilogue %d", a->epilogue);
     MMB_REQUIRE(a->split_k <= 1 || a->epilogue == MMB_EPI_ATOMIC_ADD_F32, "mmb_gemm: split_k needs ATOMIC_ADD_F32");
-    if (a->epilogue == MMB_EPI_DGELU_BF16)
-        MMB_REQUIRE(a->aux != nullptr && (a->ldaux % 8) == 0, "mmb_gemm: DGELU needs aux with ldaux %% 8 == 0");
+    if (a->epilogue == MMB_EPI_DGELU_BF16 || a->epilogue == MMB_EPI_GELU_GRAD_BF16 || a->epilogue == MMB_EPI_MUL_AUX_BF16)
+        MMB_REQUIRE(a->aux != nullptr && (a->ldaux % 8) == 0, "mmb_gemm: this epilogue needs aux with ldaux %% 8 == 0");
     if (a->epilogue == MMB_EPI_GELU_BF16 && a->aux) MMB_REQUIRE((a->ldaux % 8) == 0, "mmb_gemm: ldaux %% 8 != 0");
     const int min_lda = a->a_major == MMB_MAJOR_K ? a->K : a->M;
     const int min_ldb = a->b_major == MMB_MAJOR_K ? a->K : a->N;

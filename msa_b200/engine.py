@@ -166,9 +166,10 @@ class Plan:
                                    out_f32=L["a32"])
             self._seeded.append(a)
             f.append((self._fn("dropout_residual_ln_fwd"), a))
+            # training: the epilogue also saves gelu'(u) (in the "u" buffer) so that the backward is a plain multiply
             self._gemm(f, L["a"], self._w(pre + "intermediate.dense.weight"), L["hg"], M, I, H,
-                       epilogue=capi.EPI_GELU_BF16, aux=L["u"] if self.training else None,
-                       bias=self._p(pre + "intermediate.dense.bias"))
+                       epilogue=capi.EPI_GELU_GRAD_BF16 if self.training else capi.EPI_GELU_BF16,
+                       aux=L["u"] if self.training else None, bias=self._p(pre + "intermediate.dense.bias"))
             self._gemm(f, L["hg"], self._w(pre + "output.dense.weight"), L["y2"], M, H, I,
                        bias=self._p(pre + "output.dense.bias"))
             a = capi.drln_fwd_args(L["y2"], L["a32"], self._p(pre + "output.LayerNorm.weight"),
@@ -258,9 +259,9 @@ class Plan:
                                    p_drop=self.p_hidden, rng_stream=(l << 8) | ST_OUT2)
             self._seeded.append(a)
             b.append((self._fn("dropout_residual_ln_bwd"), a))
-            # FFN2: du = (dY2 · W2) ∘ gelu'(u) ; gW2 += dY2^T · hg
+            # FFN2: du = (dY2 · W2) ∘ gelu'(u) ; gW2 += dY2^T · hg     (L["u"] holds gelu'(u), see the forward)
             self._gemm(b, self.GC, self._w(pre + "output.dense.weight"), self.du, M, I, H, b_major=MN,
-                       epilogue=capi.EPI_DGELU_BF16, aux=L["u"])
+                       epilogue=capi.EPI_MUL_AUX_BF16, aux=L["u"])
             self._gemm(b, self.GC, L["hg"], self._g(pre + "output.dense.weight"), H, I, M, a_major=MN, b_major=MN,
                        epilogue=ATOM, split_k=_split_k(H, I, M))
             b.append((self._fn("colsum_bf16"), capi.colsum_args(self.du, self._g(pre + "intermediate.dense.bias"))))

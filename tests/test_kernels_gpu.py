@@ -53,6 +53,15 @@ def test_gemm_epilogues():
     torch.nn.functional.gelu(u).sum().backward()
     capi.gemm(A, B, C, M, N, K, epilogue=capi.EPI_DGELU_BF16, aux=aux)
     assert _rel(C.float(), (A.float() @ B.float().t()) * u.grad) < 2 * BF16_EPS
+    # forward that saves gelu'(pre) instead of pre, and the plain-multiply backward that consumes it
+    dg = torch.empty_like(C)
+    capi.gemm(A, B, C, M, N, K, epilogue=capi.EPI_GELU_GRAD_BF16, bias=bias, aux=dg)
+    p32 = pre.clone().requires_grad_(True)
+    torch.nn.functional.gelu(p32).sum().backward()
+    assert _rel(C.float(), torch.nn.functional.gelu(pre)) < 2 * BF16_EPS
+    assert _rel(dg.float(), p32.grad) < 2 * BF16_EPS
+    capi.gemm(A, B, C, M, N, K, epilogue=capi.EPI_MUL_AUX_BF16, aux=dg)
+    assert _rel(C.float(), (A.float() @ B.float().t()) * dg.float()) < 2 * BF16_EPS
     acc = torch.ones(M, N, device="cuda")
     capi.gemm(A, B, acc, M, N, K, epilogue=capi.EPI_ATOMIC_ADD_F32, split_k=4, alpha=0.5)
     assert _rel(acc, 1 + 0.5 * (A.float() @ B.float().t())) < 1e-5
