@@ -111,6 +111,7 @@ typedef struct mmb_drln_fwd_args {
     float p_drop;
     uint64_t seed;
     uint32_t rng_stream;
+    int32_t y_f32; /* fp32 validation path: y is [M,H] f32 and out may be NULL (only out_f32 is written) */
 } mmb_drln_fwd_args;
 int mmb_dropout_residual_ln_fwd(const mmb_drln_fwd_args* a, void* stream);
 
@@ -251,6 +252,7 @@ typedef struct mmb_embed_args {
     int32_t B, T;
     int32_t L[2];
     int32_t H, V, max_pos;
+    int32_t exact_frames; /* fp32 validation path: keep relu(W f + b) in fp32 (no bf16 rounding) on the way into x0_f32 */
 } mmb_embed_args;
 int mmb_embed_fwd(const mmb_embed_args* a, void* stream);
 int mmb_embed_bwd(const mmb_embed_args* a, void* stream);
@@ -277,6 +279,7 @@ typedef struct mmb_ce_args {
     int32_t B, T;
     int32_t L[2];
     int32_t dense;
+    int32_t logits_f32; /* fp32 validation path (mmb_ce_fwd only): logits are f32, ldl in f32 elements */
 } mmb_ce_args;
 int mmb_ce_fwd(const mmb_ce_args* a, void* stream);
 int mmb_ce_bwd(const mmb_ce_args* a, void* stream);
@@ -317,10 +320,43 @@ typedef struct mmb_heads_args {
     const float* gscale; /* device scalar upstream gradient, NULL = 1 */
     float alpha, beta;
     int32_t B, H, num_labels;
+    int32_t seq_out_f32; /* fp32 validation path (mmb_heads_fwd only): seq_out is f32 */
 } mmb_heads_args;
 size_t mmb_heads_workspace_bytes(int B, int H);
 int mmb_heads_fwd(const mmb_heads_args* a, void* stream);
 int mmb_heads_bwd(const mmb_heads_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * fp32 validation path (forward only).  BASELINE.json asks for an fp32 path within 1e-4 relative of the reference on
+ * logits and loss; the tensor-core path above is bf16 by construction, so the same forward can also be run with fp32
+ * storage and plain fp32 CUDA-core arithmetic: mmb_embed_fwd (exact_frames), mmb_linear_f32, mmb_attn_f32_fwd,
+ * mmb_dropout_residual_ln_fwd (y_f32), mmb_ce_fwd (logits_f32), mmb_heads_fwd (seq_out_f32).  Correctness-first
+ * kernels for parity checks at small sizes; they are not on the benchmarked path and have no backward.
+ *
+ * mmb_linear_f32: Y[M,N] = act(X[M,K] W[N,K]^T + bias[N])   (nn.Linear layout; modeling_bert.py:179-181, :295, :340, :353,
+ * :482, :500) with act = MMB_ACT_*.   mmb_attn_f32_fwd: softmax(Q K^T / 8 + keybias) V per (sequence, head), no dropout
+ * (modeling_bert.py:115-140), Q|K|V read from qkv [rows, 3H] f32 as in mmb_attn_fwd.
+ */
+enum { MMB_ACT_NONE = 0, MMB_ACT_TANH = 1, MMB_ACT_RELU = 2, MMB_ACT_GELU = 3 };
+typedef struct mmb_linear_f32_args {
+    const float* X;
+    const float* W;
+    const float* bias; /* [N] or NULL */
+    float* Y;
+    int64_t ldx, ldw, ldy;
+    int32_t M, N, K;
+    int32_t act;
+} mmb_linear_f32_args;
+int mmb_linear_f32(const mmb_linear_f32_args* a, void* stream);
+
+typedef struct mmb_attn_f32_args {
+    const float* qkv;          /* [rows, 3H] */
+    float* ctx;                /* [rows, H] */
+    const float* keybias;      /* [rows] */
+    const int32_t* cu_seqlens; /* [nseq + 1] */
+    int32_t H, nheads, nseq, max_seqlen, total_rows;
+} mmb_attn_f32_args;
+int mmb_attn_f32_fwd(const mmb_attn_f32_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Weight maintenance.  mmb_cast_bf16 refreshes the bf16 GEMM operand copies from the fp32 master

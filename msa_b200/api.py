@@ -149,6 +149,9 @@ class MMBertForPretraining(_Node):
         self._bwd_hooks = None
         self.launches = 0          # kernel-launching C calls issued so far (bench.py reports the per-step count)
         self.dense_mlm = True
+        # "bf16": tcgen05 tensor-core path (training and inference).  "fp32": validation path, forward only, fp32
+        # storage and CUDA-core arithmetic (engine_f32.PlanF32) for the reference's 1e-4 fp32 tolerance.
+        self.precision = "bf16"
         H = config.hidden_size
         std = getattr(config, "initializer_range", 0.02)
         # every parameter except bert.jointEmbeddings.* (created by set_joint_embeddings, as in the reference)
@@ -230,8 +233,22 @@ class MMBertForPretraining(_Node):
         return self._bwd_hooks(plan) if self._bwd_hooks is not None else None
 
     def _plan(self, B, T, Lv, La, device):
-        key = (B, T, Lv, La, self.training)
+        if self.precision not in ("bf16", "fp32"):
+            raise capi.MMBError(f"precision must be 'bf16' or 'fp32', not {self.precision!r}")
+        fp32 = self.precision == "fp32"
+        key = (B, T, Lv, La, self.training, fp32)
         plan = self._plans.get(key)
+        if plan is None and fp32:
+            if len(self._plans) >= 4:
+                self._plans.clear()
+            p_any = max(float(self.config.hidden_dropout_prob), float(self.config.attention_probs_dropout_prob),
+                        float(self.bert.jointEmbeddings.dropout.p))
+            if self.training and p_any > 0:
+                raise capi.MMBError("the fp32 validation path is dropout-free: call .eval() or set the dropout "
+                                    "probabilities to 0 (the reference parity recipe)")
+            from .engine_f32 import PlanF32
+            plan = PlanF32(self.config, self.bert.dataset, self._store, B, T, Lv, La, device)
+            self._plans[key] = plan
         if plan is None:
             if len(self._plans) >= 4:          # bound the activation memory held by stale shapes
                 self._plans.clear()
@@ -265,12 +282,17 @@ class MMBertForPretraining(_Node):
         if plan._frame_sig != sig:
             plan.refresh_frame_weights()
             plan._frame_sig = sig
-        if self.training:
+        if self.precision == "fp32":           # forward only: the losses carry no autograd graph
+            Plan.run(plan.fwd)
+            self.launches += len(plan.fwd)
+            joint = plan.losses[0].clone()
+        elif torch.is_grad_enabled() and self.training:
             plan.set_seed(int(torch.randint(0, 2 ** 62, (1,)).item()))
-        if torch.is_grad_enabled() and self.training:
             anchor = self._params["classifier1_2.bias"]
             joint = _StepFn.apply(anchor, self, plan)
         else:
+            if self.training:
+                plan.set_seed(int(torch.randint(0, 2 ** 62, (1,)).item()))
             Plan.run(plan.fwd)
             self.launches += len(plan.fwd)
             joint = plan.losses[0].clone()

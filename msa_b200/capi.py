@@ -112,6 +112,9 @@ EmbedArgs = _make_struct("mmb_embed_args")
 CeArgs = _make_struct("mmb_ce_args")
 HeadsArgs = _make_struct("mmb_heads_args")
 AdamwArgs = _make_struct("mmb_adamw_args")
+LinearF32Args = _make_struct("mmb_linear_f32_args")
+AttnF32Args = _make_struct("mmb_attn_f32_args")
+ACT_NONE, ACT_TANH, ACT_RELU, ACT_GELU = range(4)
 
 DT_F32, DT_F64, DT_I64, DT_I32, DT_U8 = range(5)
 _DT = {torch.float32: DT_F32, torch.float64: DT_F64, torch.int64: DT_I64, torch.int32: DT_I32, torch.uint8: DT_U8,

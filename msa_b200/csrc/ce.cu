@@ -125,10 +125,51 @@ ce_bwd_kernel(const CeParams p) {
     }
 }
 
+// fp32 validation path: the same statistics on f32 logits (one CTA per labelled row)
+__global__ void __launch_bounds__(256)
+ce_fwd_f32_kernel(const CeParams p) {
+    const int row = blockIdx.x;
+    int pass;
+    const long long label = row_label(p, row, pass);
+    if (label == -100) return;
+    const float* x = reinterpret_cast<const float*>(p.logits) + (int64_t)row * p.ldl;
+    float m = -INFINITY, s = 0.f;
+    for (int i = threadIdx.x; i < p.V; i += 256) {
+        const float v = x[i];
+        const float mn = fmaxf(m, v);
+        s = (m == -INFINITY ? 0.f : s * expf(m - mn)) + expf(v - mn);
+        m = mn;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        const float mn = fmaxf(m, m2);
+        s = (m == -INFINITY ? 0.f : s * expf(m - mn)) + (m2 == -INFINITY ? 0.f : s2 * expf(m2 - mn));
+        m = mn;
+    }
+    __shared__ float sm[8], ss[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        sm[warp] = m;
+        ss[warp] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) {
+            const float mn = fmaxf(m, sm[w]);
+            s = (m == -INFINITY ? 0.f : s * expf(m - mn)) + (sm[w] == -INFINITY ? 0.f : ss[w] * expf(sm[w] - mn));
+            m = mn;
+        }
+        const float lse = m + logf(s);
+        p.row_lse[row] = lse;
+        atomicAdd(p.loss_sum + pass, lse - x[label]);
+    }
+}
+
 static int fill(CeParams& p, const mmb_ce_args* a) {
     MMB_REQUIRE(a && a->logits && a->label_count && a->row_lse, "ce: null pointer");
-    MMB_REQUIRE(a->V > 0 && a->ldl >= (a->V + 7) / 8 * 8 && a->ldl % 8 == 0, "ce: ldl=%lld must be a multiple of 8 >= V=%d",
-                (long long)a->ldl, a->V);
+    MMB_REQUIRE(a->V > 0 && a->ldl >= (a->logits_f32 ? a->V : (a->V + 7) / 8 * 8) && (a->logits_f32 || a->ldl % 8 == 0),
+                "ce: ldl=%lld must be a multiple of 8 >= V=%d", (long long)a->ldl, a->V);
     p.logits = (const __nv_bfloat16*)a->logits;
     p.dlogits = (__nv_bfloat16*)a->dlogits;
     for (int i = 0; i < 3; ++i) p.labels[i] = (const long long*)a->labels[i];
@@ -158,6 +199,10 @@ extern "C" int mmb_ce_fwd(const mmb_ce_args* a, void* stream) {
     if (rc != MMB_OK) return rc;
     MMB_REQUIRE(a->loss_sum != nullptr, "ce_fwd: null loss_sum");
     MMB_CUDA(cudaMemsetAsync(a->loss_sum, 0, 3 * sizeof(float), (cudaStream_t)stream));
+    if (a->logits_f32) {
+        ce_fwd_f32_kernel<<<p.pass_base[3], 256, 0, (cudaStream_t)stream>>>(p);
+        return check_launch("ce_fwd_f32_kernel");
+    }
     ce_fwd_kernel<<<p.pass_base[3], 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("ce_fwd_kernel");
 }
@@ -167,6 +212,7 @@ extern "C" int mmb_ce_bwd(const mmb_ce_args* a, void* stream) {
     int rc = fill(p, a);
     if (rc != MMB_OK) return rc;
     MMB_REQUIRE(a->dlogits != nullptr, "ce_bwd: null dlogits");
+    MMB_REQUIRE(!a->logits_f32, "ce_bwd: the fp32 validation path is forward-only");
     ce_bwd_kernel<<<p.pass_base[3], 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("ce_bwd_kernel");
 }

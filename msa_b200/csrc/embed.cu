@@ -117,6 +117,7 @@ struct EmbedParams {
     float* mean1; float* rstd1;    // [rows] (text rows)
     float* mean2; float* rstd2;    // [rows] (rows of joint passes)
     __nv_bfloat16* pframe;         // [frame_rows,H] relu(W f + b), bf16
+    int exact_frames;              // fp32 validation path: no bf16 rounding of the projection
     // backward
     const __nv_bfloat16* dx0;      // [rows,H]
     const float* dx0b;             // [rows,H] optional fp32 residual-stream gradient
@@ -243,7 +244,10 @@ embed_frame_fwd_kernel(const EmbedParams p, int mod) {  // mod 0 = visual (pass 
         if (c < p.H) {
             const float bias = __ldg(p.wb[mod] + c);
 #pragma unroll
-            for (int r = 0; r < kFrameRows; ++r) sO[r * p.H + c] = bf16_round(fmaxf(acc[r][j] + bias, 0.f));
+            for (int r = 0; r < kFrameRows; ++r) {
+                const float v = fmaxf(acc[r][j] + bias, 0.f);
+                sO[r * p.H + c] = p.exact_frames ? v : bf16_round(v);
+            }
         }
     }
     __syncthreads();
@@ -465,6 +469,7 @@ static int fill_embed(EmbedParams& p, const mmb_embed_args* a) {
     p.x0_f32 = a->x0_f32;
     p.mean1 = a->mean1; p.rstd1 = a->rstd1; p.mean2 = a->mean2; p.rstd2 = a->rstd2;
     p.pframe = (__nv_bfloat16*)a->pframe;
+    p.exact_frames = a->exact_frames;
     p.dx0 = (const __nv_bfloat16*)a->dx0;
     p.dx0b = a->dx0b;
     p.dpre = (__nv_bfloat16*)a->dpre;

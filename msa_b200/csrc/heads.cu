@@ -14,7 +14,7 @@
 
 namespace mmb {
 
-enum { ACT_NONE = 0, ACT_TANH = 1, ACT_RELU = 2 };
+enum { ACT_NONE = MMB_ACT_NONE, ACT_TANH = MMB_ACT_TANH, ACT_RELU = MMB_ACT_RELU, ACT_GELU = MMB_ACT_GELU };
 
 // Generic fp32 tiled GEMM for the head linears and their backward (64 x 64 tiles, 16-deep k-steps, 4 x 4 outputs
 // per thread).  C[m][n] (+)= act(sum_k A(m,k) B(k,n) + bias[n]) with A(m,k) = A[m*sam + k*sak] and
@@ -74,6 +74,7 @@ sgemm64_kernel(const float* __restrict__ A, int sam, int sak, const float* __res
             float v = acc[i][j] + (bias ? bias[n] : 0.f);
             if (act == ACT_TANH) v = tanhf(v);
             else if (act == ACT_RELU) v = fmaxf(v, 0.f);
+            else if (act == ACT_GELU) v = gelu_erf(v);
             float* c = C + (size_t)m * ldc + n;
             *c = accumulate ? *c + v : v;
         }
@@ -94,6 +95,12 @@ __global__ void gather_cls_kernel(const __nv_bfloat16* __restrict__ seq, const i
     const int r = blockIdx.x;
     const __nv_bfloat16* src = seq + (size_t)cu[r] * H;
     for (int j = threadIdx.x; j < H; j += blockDim.x) X0[(size_t)r * H + j] = __bfloat162float(src[j]);
+}
+__global__ void gather_cls_f32_kernel(const float* __restrict__ seq, const int* __restrict__ cu, float* __restrict__ X0, int R,
+                                      int H) {
+    const int r = blockIdx.x;
+    const float* src = seq + (size_t)cu[r] * H;
+    for (int j = threadIdx.x; j < H; j += blockDim.x) X0[(size_t)r * H + j] = src[j];
 }
 __global__ void scatter_cls_grad_kernel(const float* __restrict__ dX0, const int* __restrict__ cu, __nv_bfloat16* __restrict__ g,
                                         int R, int H) {
@@ -457,7 +464,8 @@ extern "C" int mmb_heads_fwd(const mmb_heads_args* a, void* stream) {
     float* ws = (float*)a->workspace;
     const VPtrs vp = vptrs(a);
 
-    gather_cls_kernel<<<R, 256, 0, st>>>((const __nv_bfloat16*)a->seq_out, a->cu_seqlens, ws + w.X0, R, H);
+    if (a->seq_out_f32) gather_cls_f32_kernel<<<R, 256, 0, st>>>((const float*)a->seq_out, a->cu_seqlens, ws + w.X0, R, H);
+    else gather_cls_kernel<<<R, 256, 0, st>>>((const __nv_bfloat16*)a->seq_out, a->cu_seqlens, ws + w.X0, R, H);
     linear(st, ws + w.X0, H, a->w_pooler, H, a->b_pooler, ws + w.P, H, R, H, H, ACT_TANH);
     if (a->w_seqrel && a->b_seqrel) linear(st, ws + w.P, H, a->w_seqrel, H, a->b_seqrel, ws + w.rel, 2, B, 2, H, ACT_NONE);
     linear(st, ws + w.X0 + (size_t)B * H, H, a->w_align, H, a->b_align, ws + w.al, 2, 2 * B, 2, H, ACT_NONE);
@@ -536,4 +544,15 @@ extern "C" int mmb_heads_bwd(const mmb_heads_args* a, void* stream) {
     // add into the gradient of the encoder output at the [CLS] rows
     scatter_cls_grad_kernel<<<R, 256, 0, st>>>(ws + w.dX0, a->cu_seqlens, (__nv_bfloat16*)a->dseq_out, R, H);
     return check_launch("heads_bwd", 36 + 8);
+}
+
+// fp32 validation path: nn.Linear forward on fp32 activations (include/mmbert_sm100.h: mmb_linear_f32)
+extern "C" int mmb_linear_f32(const mmb_linear_f32_args* a, void* stream) {
+    MMB_REQUIRE(a && a->X && a->W && a->Y, "linear_f32: null pointer");
+    MMB_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->ldx >= a->K && a->ldw >= a->K && a->ldy >= a->N, "linear_f32: bad shape");
+    MMB_REQUIRE(a->act >= MMB_ACT_NONE && a->act <= MMB_ACT_GELU, "linear_f32: bad activation %d", a->act);
+    dim3 g((a->N + kSgT - 1) / kSgT, (a->M + kSgT - 1) / kSgT);
+    sgemm64_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(a->X, (int)a->ldx, 1, a->W, 1, (int)a->ldw, a->Y, (int)a->ldy, a->bias,
+                                                       a->act, a->M, a->N, a->K, 0);
+    return check_launch("sgemm64_kernel");
 }

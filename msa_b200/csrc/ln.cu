@@ -19,9 +19,9 @@ namespace mmb {
 
 constexpr int kLnWarps = 8;
 
-template <int NCH>
+template <int NCH, bool kYF32 = false>
 __global__ void __launch_bounds__(kLnWarps * 32)
-drln_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ res,
+drln_fwd_kernel(const void* __restrict__ y_, const float* __restrict__ res,
                 const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                 float* __restrict__ out_f32, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int H, float eps, uint32_t thresh,
                 float inv_keep, uint64_t seed, uint32_t stream) {
@@ -29,7 +29,8 @@ drln_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ r
     const int nw = gridDim.x * kLnWarps;
     for (int row = blockIdx.x * kLnWarps + warp; row < M; row += nw) {
         RowF<NCH> z;
-        row_load_bf16(z, y + (size_t)row * H, H, lane);
+        if (kYF32) row_load_f32(z, reinterpret_cast<const float*>(y_) + (size_t)row * H, H, lane);
+        else row_load_bf16(z, reinterpret_cast<const __nv_bfloat16*>(y_) + (size_t)row * H, H, lane);
         row_dropout(z, H, lane, seed, stream, (uint64_t)row, thresh, inv_keep);
         if (res != nullptr) {
             RowF<NCH> r;
@@ -42,9 +43,9 @@ drln_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ r
         float mean, rstd;
         row_stats(z, H, lane, eps, mean, rstd);
         row_affine(z, H, lane, mean, rstd, gamma, beta);
-        row_store_bf16(z, out + (size_t)row * H, H, lane);
+        if (out != nullptr) row_store_bf16(z, out + (size_t)row * H, H, lane);
         if (out_f32 != nullptr) row_store_f32(z, out_f32 + (size_t)row * H, H, lane);
-        if (lane == 0) {
+        if (lane == 0 && mean_out != nullptr) {
             mean_out[row] = mean;
             rstd_out[row] = rstd;
         }
@@ -232,13 +233,20 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, float* __restrict__ out,
 using namespace mmb;
 
 extern "C" int mmb_dropout_residual_ln_fwd(const mmb_drln_fwd_args* a, void* stream) {
-    MMB_REQUIRE(a && a->y && a->gamma && a->beta && a->out && a->mean && a->rstd, "drln_fwd: null pointer");
+    MMB_REQUIRE(a && a->y && a->gamma && a->beta, "drln_fwd: null pointer");
+    MMB_REQUIRE(a->y_f32 ? (a->out_f32 != nullptr) : (a->out && a->mean && a->rstd), "drln_fwd: null output");
     MMB_REQUIRE(a->M > 0 && a->H > 0 && a->H % 8 == 0 && a->H <= 1024, "drln_fwd: bad shape M=%d H=%d", a->M, a->H);
     const uint32_t thresh = dropout_threshold(a->p_drop);
     const float inv_keep = dropout_inv_keep(a->p_drop);
     const int grid = min((a->M + kLnWarps - 1) / kLnWarps, num_sms() * 4);
+    if (a->y_f32) {
+        MMB_DISPATCH_NCH(a->H, (drln_fwd_kernel<NCH, true><<<grid, kLnWarps * 32, 0, (cudaStream_t)stream>>>(
+                                   a->y, a->res, a->gamma, a->beta, (__nv_bfloat16*)a->out, a->out_f32, a->mean, a->rstd, a->M,
+                                   a->H, a->eps, thresh, inv_keep, a->seed, a->rng_stream)));
+        return check_launch("drln_fwd_kernel<f32>");
+    }
     MMB_DISPATCH_NCH(a->H, (drln_fwd_kernel<NCH><<<grid, kLnWarps * 32, 0, (cudaStream_t)stream>>>(
-                               (const __nv_bfloat16*)a->y, a->res, a->gamma, a->beta,
+                               a->y, a->res, a->gamma, a->beta,
                                (__nv_bfloat16*)a->out, a->out_f32, a->mean, a->rstd, a->M, a->H, a->eps, thresh, inv_keep, a->seed,
                                a->rng_stream)));
     return check_launch("drln_fwd_kernel");

@@ -117,6 +117,61 @@ def test_oracle_parity_bert_base_width():
     assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]
 
 
+TOL_FP32 = 1e-4     # BASELINE.json: "the fp32 path within 1e-4 relative on logits and loss"
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_fp32_path_matches_reference_golden_1e4(name):
+    """fp32 validation path (model.precision = "fp32": fp32 storage, fp32 CUDA-core arithmetic, forward only) against
+    the golden vectors of the UNMODIFIED reference (which ran in fp32): every output within 1e-4 relative."""
+    recipe, g = load_golden(name)
+    ocfg, sd, batch = expand_recipe(recipe)
+    m = _build(ocfg, recipe["dataset"], sd)
+    m.set_alpha_beta(recipe["alpha"], recipe["beta"])
+    m.precision = "fp32"
+    m.eval()
+    with torch.no_grad():
+        out, logits = m(**synth.tree_to(batch, "cuda"))
+    for n, a in zip(OUT_NAMES, out):
+        if n is None:
+            assert a is None
+            continue
+        b = g["eval." + n]
+        assert a.dtype == torch.float32 and tuple(a.shape) == tuple(b.shape), n
+        assert rel_err(a, b) < TOL_FP32, (n, rel_err(a, b))
+    assert rel_err(logits, g["eval.logits"]) < TOL_FP32
+
+
+def test_fp32_path_bert_base_12_layers_1e4():
+    """Full bert-base (12 layers, hidden 768, 30522 vocabulary), MOSI dims, vs the fp64 oracle: 1e-4 on logits and loss.
+    The same model instance then runs the bf16 tensor-core path on the same weights (2e-2)."""
+    ocfg = O.Cfg(num_hidden_layers=12)
+    sd = seeded_state_dict(ocfg, "mosi", seed=9, std=0.02)
+    batch = synth.make_batch(2, 12, 17, 12, 47, 74, seed=23, min_len=5)
+    m = _build(ocfg, "mosi", sd)
+    m.set_alpha_beta(1.0, 1.0)
+    with torch.no_grad():
+        ref_out, ref_logits = O.forward(sd, ocfg, **batch)
+    dbatch = synth.tree_to(batch, "cuda")
+    m.precision = "fp32"
+    m.eval()
+    with torch.no_grad():
+        out, logits = m(**dbatch)
+    for n, a, b in zip(OUT_NAMES, out, ref_out):
+        if n is not None:
+            assert rel_err(a, b) < TOL_FP32, (n, rel_err(a, b))
+    assert rel_err(logits, ref_logits) < TOL_FP32
+    m.precision = "bf16"
+    with torch.no_grad():
+        out, logits = m(**dbatch)
+    _check_outputs(out, logits, [None if o is None else o.detach() for o in ref_out], ref_logits.detach())
+    # the fp32 path is forward-only and dropout-free
+    m.precision = "fp32"
+    m.train()
+    out, _ = m(**dbatch)          # dropout probabilities are 0 in _build: allowed
+    assert not out[0].requires_grad
+
+
 def test_grad_accumulation_and_zero_grad():
     """Two backward passes accumulate (PyTorch semantics); zero_grad(set_to_none=True) restarts from zero."""
     recipe, _ = load_golden(GOLDEN[0])
