@@ -88,28 +88,22 @@ drln_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ 
     for (int i = lane; i < 3 * H; i += 32) acc_g[i] = 0.f;
     __syncwarp();
     for (int row = blockIdx.x * kLnWarps + warp; row < M; row += nw) {
+        // every load of the row goes in flight before the first one is consumed (the kernel is latency-bound otherwise)
+        RowRawB<NCH> y_raw, g1_raw;
+        RowRawF<NCH> res_raw, g2_raw;
+        row_fetch_bf16(y_raw, y + (size_t)row * H, H, lane);
+        if (res != nullptr) row_fetch_f32(res_raw, res + (size_t)row * H, H, lane);
+        row_fetch_bf16(g1_raw, g1 + (size_t)row * H, H, lane);
+        if (g2 != nullptr) row_fetch_f32(g2_raw, g2 + (size_t)row * H, H, lane);
+        const uint32_t mask = row_dropout_mask<NCH>(H, lane, seed, stream, (uint64_t)row, thresh);   // hashed under the loads
         // recompute the LayerNorm input exactly as the forward did: z = dropout(y) + res
         RowF<NCH> z;
-        row_load_bf16(z, y + (size_t)row * H, H, lane);
-        row_dropout(z, H, lane, seed, stream, (uint64_t)row, thresh, inv_keep);
-        if (res != nullptr) {
-            RowF<NCH> r;
-            row_load_f32(r, res + (size_t)row * H, H, lane);
-#pragma unroll
-            for (int c = 0; c < NCH; ++c)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) z.v[c][i] += r.v[c][i];
-        }
+        row_unpack_bf16(z, y_raw);
+        row_apply_mask(z, mask, inv_keep);
+        if (res != nullptr) row_add_f32(z, res_raw);
         RowF<NCH> g;
-        row_load_bf16(g, g1 + (size_t)row * H, H, lane);
-        if (g2 != nullptr) {
-            RowF<NCH> t;
-            row_load_f32(t, g2 + (size_t)row * H, H, lane);
-#pragma unroll
-            for (int c = 0; c < NCH; ++c)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) g.v[c][i] += t.v[c][i];
-        }
+        row_unpack_bf16(g, g1_raw);
+        if (g2 != nullptr) row_add_f32(g, g2_raw);
         const float mean = mean_in[row], rstd = rstd_in[row];
         // dbeta += dy ; dgamma += dy * xhat ; dz = (dy*gamma - mean(dy*gamma) - xhat * mean(dy*gamma*xhat)) * rstd
         float s1 = 0.f, s2 = 0.f;
@@ -156,7 +150,7 @@ drln_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ 
         // g now holds dz: gradient of the residual branch
         if (d_res != nullptr) row_store_f32(g, d_res + (size_t)row * H, H, lane);
         // gradient of the dense output (pre-dropout): dz * mask / keep
-        row_dropout(g, H, lane, seed, stream, (uint64_t)row, thresh, inv_keep);   // same mask, same scaling
+        row_apply_mask(g, mask, inv_keep);   // same mask, same scaling
         if (gelu_aux != nullptr) {  // y = gelu(aux): chain through the activation (LM-head transform, :482-484)
             RowF<NCH> u;
             row_load_bf16(u, gelu_aux + (size_t)row * H, H, lane);

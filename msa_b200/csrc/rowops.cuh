@@ -47,6 +47,53 @@ __device__ __forceinline__ void row_load_bf16(RowF<NCH>& r, const __nv_bfloat16*
         }
     }
 }
+// Split loads: row_fetch_* only ISSUES the 16-byte loads (raw vectors), row_unpack_* converts them later, so a kernel can
+// put every load of a row in flight before it consumes the first one.
+template <int NCH>
+struct RowRawB {
+    uint4 q[NCH];
+};
+template <int NCH>
+struct RowRawF {
+    float4 a[NCH], b[NCH];
+};
+template <int NCH>
+__device__ __forceinline__ void row_fetch_bf16(RowRawB<NCH>& r, const __nv_bfloat16* __restrict__ p, int H, int lane) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int e = (c * 32 + lane) * 8;
+        r.q[c] = e < H ? __ldg(reinterpret_cast<const uint4*>(p + e)) : make_uint4(0, 0, 0, 0);
+    }
+}
+template <int NCH>
+__device__ __forceinline__ void row_fetch_f32(RowRawF<NCH>& r, const float* __restrict__ p, int H, int lane) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int e = (c * 32 + lane) * 8;
+        const bool ok = e < H;
+        r.a[c] = ok ? __ldg(reinterpret_cast<const float4*>(p + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        r.b[c] = ok ? __ldg(reinterpret_cast<const float4*>(p + e + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+template <int NCH>
+__device__ __forceinline__ void row_unpack_bf16(RowF<NCH>& r, const RowRawB<NCH>& raw) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const float2 a = unpack_bf16x2(raw.q[c].x), b = unpack_bf16x2(raw.q[c].y), cc = unpack_bf16x2(raw.q[c].z),
+                     d = unpack_bf16x2(raw.q[c].w);
+        r.v[c][0] = a.x; r.v[c][1] = a.y; r.v[c][2] = b.x; r.v[c][3] = b.y;
+        r.v[c][4] = cc.x; r.v[c][5] = cc.y; r.v[c][6] = d.x; r.v[c][7] = d.y;
+    }
+}
+template <int NCH>
+__device__ __forceinline__ void row_add_f32(RowF<NCH>& r, const RowRawF<NCH>& raw) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        r.v[c][0] += raw.a[c].x; r.v[c][1] += raw.a[c].y; r.v[c][2] += raw.a[c].z; r.v[c][3] += raw.a[c].w;
+        r.v[c][4] += raw.b[c].x; r.v[c][5] += raw.b[c].y; r.v[c][6] += raw.b[c].z; r.v[c][7] += raw.b[c].w;
+    }
+}
+
 template <int NCH>
 __device__ __forceinline__ void row_load_f32(RowF<NCH>& r, const float* __restrict__ p, int H, int lane) {
 #pragma unroll
@@ -115,6 +162,37 @@ __device__ __forceinline__ void row_dropout(RowF<NCH>& r, int H, int lane, uint6
             }
         }
     }
+}
+
+// The same decisions as row_dropout, as one bit per element of this lane (bit c * 8 + i), so that a kernel that needs
+// the mask twice (backward: rebuild the LayerNorm input, then mask the gradient) hashes once.
+template <int NCH>
+__device__ __forceinline__ uint32_t row_dropout_mask(int H, int lane, uint64_t seed, uint32_t stream, uint64_t row,
+                                                     uint32_t thresh) {
+    if (thresh == 0u) return 0xFFFFFFFFu;
+    const uint32_t key = rng_row_key(seed, stream, (uint32_t)row);
+    uint32_t m = 0u;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int e = (c * 32 + lane) * 8;
+        if (e < H) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t bits = rng_pair(key, (uint32_t)(e >> 1) + i);
+                m |= (rng_keep_lo(bits, thresh) ? 1u : 0u) << (c * 8 + 2 * i);
+                m |= (rng_keep_hi(bits, thresh) ? 1u : 0u) << (c * 8 + 2 * i + 1);
+            }
+        }
+    }
+    return m;
+}
+template <int NCH>
+__device__ __forceinline__ void row_apply_mask(RowF<NCH>& r, uint32_t mask, float inv_keep) {
+    if (mask == 0xFFFFFFFFu && inv_keep == 1.0f) return;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[c][i] = ((mask >> (c * 8 + i)) & 1u) ? r.v[c][i] * inv_keep : 0.f;
 }
 
 // mean / rstd of a row (two-pass in registers: exact mean first, then centred second moment)
