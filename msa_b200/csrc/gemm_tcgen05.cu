@@ -209,18 +209,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[3
             flush_stage(st, Cb, p.ldc, row_base, p.M, col0, p.N, lane);
         } break;
         case MMB_EPI_GELU_GRAD_BF16: {
-            float d[32];
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-                float2 g, dg;
-                gelu_fast2(make_float2(v[i], v[i + 1]), g, dg);
-                v[i] = g.x;
-                v[i + 1] = g.y;
-                d[i] = dg.x;
-                d[i + 1] = dg.y;
+            for (int j = 0; j < 4; ++j) {     // 8 columns -> one 16-byte chunk of each staging row (keeps few values live)
+                uint32_t pg[4], pd[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float2 g, dg;
+                    gelu_fast2(make_float2(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]), g, dg);
+                    pg[i] = pack_bf16x2(g.x, g.y);
+                    pd[i] = pack_bf16x2(dg.x, dg.y);
+                }
+                sts128(st + stage_off(lane, j), pg[0], pg[1], pg[2], pg[3]);
+                sts128(st + 2048 + stage_off(lane, j), pd[0], pd[1], pd[2], pd[3]);
             }
-            stage_row(st + 2048, d, lane);
-            stage_row(st, v, lane);
             flush_stage(st + 2048, reinterpret_cast<__nv_bfloat16*>(p.aux), p.ldaux, row_base, p.M, col0, p.N, lane);
             flush_stage(st, Cb, p.ldc, row_base, p.M, col0, p.N, lane);
         } break;
@@ -482,16 +483,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // its own 128 accumulator rows from its own TMEM.  Per SM the shared-memory traffic drops from 192 B/cycle
 // (96 B/cycle TMA fill + 96 B/cycle operand reads at full MMA rate; the 1-CTA kernel measured 66-69 % tensor-pipe
 // activity, i.e. the 128 B/cycle shared-memory limit) to 128 B/cycle.
-constexpr int k2Stages = 6;
+// Two instantiations: 8 epilogue warps (12 warps, 6 smem stages) for the plain / atomic / multiply epilogues, and
+// SIXTEEN epilogue warps (20 warps, 4 per TMEM lane quarter, 64 columns each, 5 stages) for the GELU epilogues, which
+// are long latency chains (tcgen05.ld -> bias -> erf math -> two staged output streams): with 8 warps the issue slots
+// were ~30 % busy and the epilogue, not the MMA, bounded FFN1 (39 % tensor-pipe active).
+template <int kEpiWarps> struct Cfg2 {
+    static constexpr int kStages = kEpiWarps == 16 ? 5 : 6;
+    static constexpr int kThreads = (4 + kEpiWarps) * 32;
+    static constexpr int kSmemBytes = kStages * (2 * 128 * BK * 2) + 256 + kEpiWarps * 4096 + 1024;
+};
 constexpr int k2ABytes = 128 * BK * 2;           // this CTA's half of the 256-row A tile
 constexpr int k2BBytes = 128 * BK * 2;           // this CTA's half of the 256-column B tile
 constexpr int k2StageBytes = k2ABytes + k2BBytes;
-constexpr int k2SmemBytes = k2Stages * k2StageBytes + 256 + 8 * 4096 + 1024;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+template <int k2EpiWarps>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg2<k2EpiWarps>::kThreads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmParams p) {
+    constexpr int k2Stages = Cfg2<k2EpiWarps>::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t smem_base = ptx::smem_u32(smem);
@@ -521,7 +531,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(tfull_bar(a), 1);                    // per CTA: multicast tcgen05.commit
-            ptx::mbar_init(tempty_bar(a), 2 * kNumEpiWarps);    // leader's: epilogue warps of both CTAs
+            ptx::mbar_init(tempty_bar(a), 2 * k2EpiWarps);      // leader's: epilogue warps of both CTAs
         }
         ptx::fence_barrier_init();
     }
@@ -611,9 +621,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // ================================ epilogue (both CTAs, own 128 rows) ================================
         const int ew = warp - kEpiWarp0;
         const int quarter = warp & 3;
-        const int half = ew >> 2;
+        const int half = ew >> 2;          // column group 0..3 of the tile
         const uint32_t stage_buf = ptx::smem_u32(epi_stage) + ew * kStageBytesPerWarp;
-        constexpr int kColsPerWarp = TN / 2;
+        constexpr int kColsPerWarp = TN / (k2EpiWarps / 4);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = cluster_id; t < p.total_tiles; t += num_clusters) {
@@ -881,12 +891,21 @@ static int launch_gemm_2cta(const mmb_gemm_args* a, cudaStream_t stream) {
     fill_common(p, a, 256, 256);
     static bool attr_set = false;
     if (!attr_set) {
-        MMB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes));
+        MMB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg2<8>::kSmemBytes));
+        MMB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg2<16>::kSmemBytes));
         attr_set = true;
     }
     const int pairs = num_sms() / 2;
     const int clusters = p.total_tiles < pairs ? p.total_tiles : pairs;
-    gemm_tcgen05_2cta_kernel<<<2 * clusters, kGemmThreads, k2SmemBytes, stream>>>(tmA, tmB, p);
+    // GELU epilogues are long latency chains: 16 epilogue warps; everything else: 8 (dbg bit 6 flips the choice, for A/B runs)
+    bool wide = a->epilogue == MMB_EPI_GELU_BF16 || a->epilogue == MMB_EPI_GELU_GRAD_BF16;
+    if (a->dbg_flags & 64) wide = !wide;
+    if (wide)
+        gemm_tcgen05_2cta_kernel<16><<<2 * clusters, Cfg2<16>::kThreads, Cfg2<16>::kSmemBytes, stream>>>(tmA, tmB, p);
+    else
+        gemm_tcgen05_2cta_kernel<8><<<2 * clusters, Cfg2<8>::kThreads, Cfg2<8>::kSmemBytes, stream>>>(tmA, tmB, p);
     return check_launch("gemm_tcgen05_2cta_kernel");
 }
 

@@ -35,6 +35,13 @@ CASES = {
     "kk_dec_dgrad": (16000, 768, 30522, 0, 1, "store", 1, 0),
     "mnmn_dec_wgrad": (30522, 768, 16000, 1, 1, "atomic", 1, 0),
     "kk_c3_ffn1": (73600, 3072, 768, 0, 0, "gelu", 1, 0),
+    # dbg bit 6 (64) flips the 8 / 16 epilogue-warp choice: same-box A/B
+    "ab_qkv_8": (16000, 2304, 768, 0, 0, "bias", 1, 0), "ab_qkv_16": (16000, 2304, 768, 0, 0, "bias", 1, 64),
+    "ab_gelu_16": (16000, 3072, 768, 0, 0, "gelu", 1, 0), "ab_gelu_8": (16000, 3072, 768, 0, 0, "gelu", 1, 64),
+    "ab_ffn2_8": (16000, 768, 3072, 0, 0, "bias", 1, 0), "ab_ffn2_16": (16000, 768, 3072, 0, 0, "bias", 1, 64),
+    "ab_wgrad_8": (768, 3072, 16000, 1, 1, "atomic", 5, 0), "ab_wgrad_16": (768, 3072, 16000, 1, 1, "atomic", 5, 64),
+    "ab_c3qkv_8": (73600, 2304, 768, 0, 0, "bias", 1, 0), "ab_c3qkv_16": (73600, 2304, 768, 0, 0, "bias", 1, 64),
+    "ab_c3gelu_16": (73600, 3072, 768, 0, 0, "gelu", 1, 0), "ab_c3gelu_8": (73600, 3072, 768, 0, 0, "gelu", 1, 64),
     "y_ffn1_plain": (16000, 3072, 768, 0, 0, "bias", 1, 0),
     "y_ffn1_gelu_noaux": (16000, 3072, 768, 0, 0, "gelu_noaux", 1, 0),
     "y_ffn1_gelu_half": (8000, 3072, 768, 0, 0, "gelu", 1, 0),
@@ -112,7 +119,7 @@ def run_case(name):
     res = {"case": name, "max_abs_err": err, "ref_max": scale, "rel": err / max(scale, 1e-9)}
     if epi == "gelu":
         res["aux_err"] = (aux.float() - pre).abs().max().item()
-    if epi != "atomic":
+    if True:
         for _ in range(3):
             launch()
         s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
