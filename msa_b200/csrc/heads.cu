@@ -29,10 +29,11 @@ sgemm64_kernel(const float* __restrict__ A, int sam, int sak, const float* __res
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * kSgT, n0 = blockIdx.x * kSgT;
     float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-    for (int k0 = 0; k0 < K; k0 += kSgBK) {
-        float ra[8], rb[8];
+    float ra[8], rb[8];
+    // all 16 loads of a k-tile are issued together, and the NEXT tile's loads fly under the current tile's math
+    auto fetch = [&](int k0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {       // all 16 loads of this thread are issued before any is consumed
+        for (int i = 0; i < 8; ++i) {
             const int idx = tid + i * 256;  // 2048 = 32 x 64 elements per operand tile
             int m, k;
             if (sak == 1) { m = idx >> 6; k = idx & 63; } else { m = idx & 31; k = idx >> 5; }
@@ -41,6 +42,9 @@ sgemm64_kernel(const float* __restrict__ A, int sam, int sak, const float* __res
             if (sbn == 1) { kb = idx >> 5; n = idx & 31; } else { kb = idx & 63; n = idx >> 6; }
             rb[i] = (n0 + n < N && k0 + kb < K) ? __ldg(B + (size_t)(k0 + kb) * sbk + (size_t)(n0 + n) * sbn) : 0.f;
         }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < K; k0 += kSgBK) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int idx = tid + i * 256;
@@ -52,6 +56,7 @@ sgemm64_kernel(const float* __restrict__ A, int sam, int sak, const float* __res
             Bs[kb][n] = rb[i];
         }
         __syncthreads();
+        if (k0 + kSgBK < K) fetch(k0 + kSgBK);
 #pragma unroll 16
         for (int k = 0; k < kSgBK; ++k) {
             const float2 a = *reinterpret_cast<const float2*>(&As[k][ty * 2]);
@@ -198,11 +203,31 @@ cpc_rows_kernel(const float* __restrict__ xn, const float* __restrict__ an, floa
     extern __shared__ float g[];
     __shared__ float red[8];
     const int i = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int j = warp; j < B; j += 8) {
-        float acc = 0.f;
-        for (int k = lane; k < H; k += 32) acc = fmaf(xn[(size_t)i * H + k], an[(size_t)j * H + k], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) g[j] = acc;
+    // g[j] = <xn_i, an_j>: row i is read once into registers (H <= 1024: 8 float4 per lane), two rows j per pass with
+    // 16-byte loads so that many loads are in flight (the scalar one-row-at-a-time loop was latency-bound: 58 us)
+    const float4* xi = reinterpret_cast<const float4*>(xn + (size_t)i * H);
+    const int nv = H >> 2;                       // H % 4 == 0 (H = heads * 64)
+    float4 xr[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) xr[t] = (lane + 32 * t) < nv ? __ldg(xi + lane + 32 * t) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 2 * warp; j < B; j += 16) {
+        const float4* a0 = reinterpret_cast<const float4*>(an + (size_t)j * H);
+        const float4* a1 = reinterpret_cast<const float4*>(an + (size_t)min(j + 1, B - 1) * H);
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            if ((lane + 32 * t) < nv) {
+                const float4 u = __ldg(a0 + lane + 32 * t), v = __ldg(a1 + lane + 32 * t);
+                acc0 += xr[t].x * u.x + xr[t].y * u.y + xr[t].z * u.z + xr[t].w * u.w;
+                acc1 += xr[t].x * v.x + xr[t].y * v.y + xr[t].z * v.z + xr[t].w * v.w;
+            }
+        }
+        acc0 = warp_sum(acc0);
+        acc1 = warp_sum(acc1);
+        if (lane == 0) {
+            g[j] = acc0;
+            if (j + 1 < B) g[j + 1] = acc1;
+        }
     }
     __syncthreads();
     float mx = -INFINITY;
@@ -259,10 +284,33 @@ normalize_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, 
 __global__ void __launch_bounds__(256)
 bb_matmul_kernel(const float* __restrict__ Mx, const float* __restrict__ Y, float* __restrict__ out, int B, int H, int transpose) {
     const int i = blockIdx.x;
-    for (int k = threadIdx.x; k < H; k += 256) {
-        float acc = 0.f;
-        for (int j = 0; j < B; ++j) acc = fmaf(transpose ? Mx[(size_t)j * B + i] : Mx[(size_t)i * B + j], Y[(size_t)j * H + k], acc);
-        out[(size_t)i * H + k] = acc;
+    extern __shared__ float mrow[];              // row (or column) i of Mx: B floats
+    for (int j = threadIdx.x; j < B; j += 256) mrow[j] = transpose ? Mx[(size_t)j * B + i] : Mx[(size_t)i * B + j];
+    __syncthreads();
+    // up to 4 output columns per thread, 4 rows of Y per pass: 16 independent loads in flight
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int j = 0;
+    for (; j + 4 <= B; j += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float m = mrow[j + u];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int k = threadIdx.x + 256 * c;
+                if (k < H) acc[c] = fmaf(m, __ldg(Y + (size_t)(j + u) * H + k), acc[c]);
+            }
+        }
+    }
+    for (; j < B; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int k = threadIdx.x + 256 * c;
+            if (k < H) acc[c] = fmaf(mrow[j], __ldg(Y + (size_t)j * H + k), acc[c]);
+        }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int k = threadIdx.x + 256 * c;
+        if (k < H) out[(size_t)i * H + k] = acc[c];
     }
 }
 
@@ -413,7 +461,7 @@ extern "C" size_t mmb_heads_workspace_bytes(int B, int H) { return heads_ws(B, H
 
 static int heads_check(const mmb_heads_args* a) {
     MMB_REQUIRE(a && a->seq_out && a->cu_seqlens && a->workspace && a->losses && a->logits_out, "heads: null pointer");
-    MMB_REQUIRE(a->B > 0 && a->H > 0, "heads: bad dims");
+    MMB_REQUIRE(a->B > 0 && a->H > 0 && a->H % 4 == 0 && a->H <= 1024, "heads: bad dims (H must be a multiple of 4, <= 1024)");
     MMB_REQUIRE(a->w_pooler && a->b_pooler && a->w_align && a->b_align && a->w_attn && a->b_attn && a->w_c11 && a->b_c11 &&
                     a->w_c12 && a->b_c12 && a->ap_label[0] && a->ap_label[1] && a->sentiment && a->ce_loss_sum &&
                     a->label_count,
@@ -518,8 +566,8 @@ extern "C" int mmb_heads_bwd(const mmb_heads_args* a, void* stream) {
         const float* xn = ws + w.xn + (size_t)m * B * H;
         const float* an = ws + w.an + (size_t)m * B * H;
         cpc_dg_kernel<<<(B * B + 255) / 256, 256, 0, st>>>(Sm, a->gscale, a->beta, B);          // Sm <- dG
-        bb_matmul_kernel<<<B, 256, 0, st>>>(Sm, an, ws + w.dxn, B, H, 0);                          // dXn = dG An
-        bb_matmul_kernel<<<B, 256, 0, st>>>(Sm, xn, ws + w.dan, B, H, 1);                          // dAn = dG^T Xn
+        bb_matmul_kernel<<<B, 256, B * sizeof(float), st>>>(Sm, an, ws + w.dxn, B, H, 0);                          // dXn = dG An
+        bb_matmul_kernel<<<B, 256, B * sizeof(float), st>>>(Sm, xn, ws + w.dan, B, H, 1);                          // dAn = dG^T Xn
         normalize_bwd_kernel<<<B, 256, 0, st>>>(xn, ws + w.dxn, ws + w.nx + (size_t)m * B, ws + w.dP + (size_t)m * B * H, H, 1);
         normalize_bwd_kernel<<<B, 256, 0, st>>>(an, ws + w.dan, ws + w.na + (size_t)m * B, ws + w.dXH, H, 0);
         dx(st, ws + w.dXH, H, a->w_cpc[m], H, ws + w.dtemp, H, B, H, H, 1);
