@@ -327,6 +327,30 @@ int mmb_heads_fwd(const mmb_heads_args* a, void* stream);
 int mmb_heads_bwd(const mmb_heads_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * On-device MLM masking.  Replaces model_utils.mask_tokens (model_utils.py:6-39), which the
+ * reference runs three times per step (trainer.py:45-47) with host round trips: 15 % (prob) of the non-special tokens are
+ * selected; labels = original id where selected, -100 elsewhere; 80 % (replace_prob) of the selected positions get
+ * mask_id, the rest keep their token (the reference's random-word branch is commented out, :34-37).  ids are updated IN
+ * PLACE like the reference's `inputs`.  Special tokens = the ids listed in special[] (BERT: [PAD] 0, [UNK] 100, [CLS] 101,
+ * [SEP] 102, [MASK] 103 — tokenizer.all_special_ids).  Decisions come from the counter-based generator of common.cuh
+ * keyed by (seed, rng_stream, element index): same seed -> same mask.  If labels_dup is not NULL it receives the
+ * reference's cat((labels, labels), -1) of trainer.py:50,53 ([B, 2T]) in the same pass.
+ */
+typedef struct mmb_mlm_mask_args {
+    void* ids;        /* int64 [B,T] in/out */
+    void* labels;     /* int64 [B,T] out */
+    void* labels_dup; /* int64 [B,2T] out or NULL */
+    int32_t special[8];
+    int32_t n_special;
+    int32_t B, T;
+    int32_t mask_id;
+    float prob, replace_prob;
+    uint64_t seed;
+    uint32_t rng_stream;
+} mmb_mlm_mask_args;
+int mmb_mlm_mask(const mmb_mlm_mask_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * fp32 validation path (forward only).  BASELINE.json asks for an fp32 path within 1e-4 relative of the reference on
  * logits and loss; the tensor-core path above is bf16 by construction, so the same forward can also be run with fp32
  * storage and plain fp32 CUDA-core arithmetic: mmb_embed_fwd (exact_frames), mmb_linear_f32, mmb_attn_f32_fwd,

@@ -112,6 +112,7 @@ EmbedArgs = _make_struct("mmb_embed_args")
 CeArgs = _make_struct("mmb_ce_args")
 HeadsArgs = _make_struct("mmb_heads_args")
 AdamwArgs = _make_struct("mmb_adamw_args")
+MlmMaskArgs = _make_struct("mmb_mlm_mask_args")
 LinearF32Args = _make_struct("mmb_linear_f32_args")
 AttnF32Args = _make_struct("mmb_attn_f32_args")
 ACT_NONE, ACT_TANH, ACT_RELU, ACT_GELU = range(4)

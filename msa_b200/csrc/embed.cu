@@ -593,3 +593,60 @@ extern "C" int mmb_embed_bwd(const mmb_embed_args* a, void* stream) {
     }
     return MMB_OK;
 }
+
+// ------------------------------------------------------------------ on-device MLM masking (model_utils.py:6-39)
+namespace mmb {
+struct MlmParams {
+    long long* ids;
+    long long* labels;
+    long long* labels_dup;
+    int special[8];
+    int n_special, B, T, mask_id;
+    uint32_t thr_sel, thr_rep;   // 16-bit thresholds: select iff u < thr_sel, replace iff u' < thr_rep
+    uint64_t seed;
+    uint32_t stream;
+};
+__global__ void __launch_bounds__(256)
+mlm_mask_kernel(const MlmParams p) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= p.B * p.T) return;
+    const long long id = p.ids[i];
+    bool special = false;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) special |= (s < p.n_special) && (id == (long long)p.special[s]);
+    // one hash per element: two independent 16-bit uniforms (selection, replacement)
+    const uint32_t bits = rng_pair(rng_row_key(p.seed, p.stream, (uint32_t)(i >> 16)), (uint32_t)(i & 0xFFFF));
+    const bool selected = !special && (bits & 0xFFFFu) < p.thr_sel;
+    const bool replaced = selected && (bits >> 16) < p.thr_rep;
+    const long long lab = selected ? id : -100;
+    p.labels[i] = lab;
+    if (p.labels_dup != nullptr) {
+        const int b = i / p.T, t = i - b * p.T;
+        p.labels_dup[(size_t)b * 2 * p.T + t] = lab;
+        p.labels_dup[(size_t)b * 2 * p.T + p.T + t] = lab;
+    }
+    if (replaced) p.ids[i] = p.mask_id;
+}
+}  // namespace mmb
+
+extern "C" int mmb_mlm_mask(const mmb_mlm_mask_args* a, void* stream) {
+    MMB_REQUIRE(a && a->ids && a->labels, "mlm_mask: null pointer");
+    MMB_REQUIRE(a->B > 0 && a->T > 0 && a->n_special >= 0 && a->n_special <= 8, "mlm_mask: bad shape");
+    MMB_REQUIRE(a->prob >= 0.f && a->prob <= 1.f && a->replace_prob >= 0.f && a->replace_prob <= 1.f, "mlm_mask: bad probability");
+    MlmParams p;
+    p.ids = (long long*)a->ids;
+    p.labels = (long long*)a->labels;
+    p.labels_dup = (long long*)a->labels_dup;
+    for (int i = 0; i < 8; ++i) p.special[i] = a->special[i];
+    p.n_special = a->n_special;
+    p.B = a->B;
+    p.T = a->T;
+    p.mask_id = a->mask_id;
+    p.thr_sel = (uint32_t)((double)a->prob * 65536.0 + 0.5);
+    p.thr_rep = (uint32_t)((double)a->replace_prob * 65536.0 + 0.5);
+    p.seed = a->seed;
+    p.stream = a->rng_stream;
+    const int n = a->B * a->T;
+    mlm_mask_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("mlm_mask_kernel");
+}

@@ -192,3 +192,28 @@ def forward_backward(sd, cfg, batch, alpha=1.0, beta=1.0, dtype=torch.float64):
     out[0].backward()
     grads = {k: (v.grad if v.grad is not None else None) for k, v in leaves.items()}
     return out, logits, grads
+
+
+def mask_tokens_rules(orig_ids, new_ids, labels, special_ids, mask_id):
+    """Checker for an MLM-masking implementation against the rules of model_utils.mask_tokens (model_utils.py:6-39):
+    returns a dict of violation counts (all zero = conforming) and the observed rates.
+      * labels == original id at selected positions, -100 elsewhere (:29)
+      * special tokens are never selected (:16-22)
+      * a position's id changes only if it is selected, and only to mask_id (:31-33); the rest keep their token
+    """
+    orig_ids, new_ids, labels = orig_ids.cpu(), new_ids.cpu(), labels.cpu()
+    special = torch.zeros_like(orig_ids, dtype=torch.bool)
+    for s_ in special_ids:
+        special |= orig_ids == s_
+    selected = labels != -100
+    changed = new_ids != orig_ids
+    n_cand = int((~special).sum())
+    return {
+        "label_mismatch": int((labels[selected] != orig_ids[selected]).sum()),
+        "special_selected": int((selected & special).sum()),
+        "changed_unselected": int((changed & ~selected).sum()),
+        "changed_not_to_mask": int((changed & (new_ids != mask_id)).sum()),
+        "select_rate": float(selected.sum()) / max(n_cand, 1),
+        "replace_rate": float((selected & (new_ids == mask_id) & (orig_ids != mask_id)).sum()) / max(int(selected.sum()), 1),
+    }
+

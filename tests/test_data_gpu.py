@@ -1,0 +1,85 @@
+"""On-device MLM masking (row N3) against the rules of the reference's model_utils.mask_tokens (oracle restatement)."""
+import types
+
+import pytest
+import torch
+
+from msa_b200 import data, synth
+from oracle import mmbert_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+class _Tok:          # the few tokenizer attributes model_utils.mask_tokens touches
+    mask_token = "[MASK]"
+    _pad_token = "[PAD]"
+    pad_token_id = 0
+    all_special_ids = [100, 102, 0, 101, 103]
+
+    def convert_tokens_to_ids(self, tok):
+        return {"[MASK]": 103}[tok]
+
+
+def _ids(B=256, T=50, seed=3):
+    return synth.make_batch(B, T, T, T, 47, 74, seed=seed, mlm=False)["input_ids"][0]
+
+
+def test_mask_tokens_follows_the_reference_rules():
+    ids0 = _ids()
+    ids = ids0.clone().cuda()
+    torch.manual_seed(11)
+    out, labels = data.mask_tokens(ids, _Tok(), types.SimpleNamespace(mlm_probability=0.15))
+    assert out.data_ptr() == ids.data_ptr()            # in place, like the reference
+    r = O.mask_tokens_rules(ids0, out, labels, _Tok.all_special_ids, 103)
+    assert r["label_mismatch"] == r["special_selected"] == r["changed_unselected"] == r["changed_not_to_mask"] == 0, r
+    assert abs(r["select_rate"] - 0.15) < 0.015 and abs(r["replace_rate"] - 0.8) < 0.03, r
+    # deterministic in the torch seed, different otherwise
+    ids2 = ids0.clone().cuda()
+    torch.manual_seed(11)
+    out2, labels2 = data.mask_tokens(ids2, _Tok(), types.SimpleNamespace(mlm_probability=0.15))
+    assert torch.equal(out, out2) and torch.equal(labels, labels2)
+    ids3 = ids0.clone().cuda()
+    torch.manual_seed(12)
+    _, labels3 = data.mask_tokens(ids3, _Tok(), types.SimpleNamespace(mlm_probability=0.15))
+    assert not torch.equal(labels, labels3)
+
+
+def test_mask_step_builds_the_label_tuple_of_the_trainer():
+    ids0 = _ids(B=64, T=50, seed=5)
+    t, v, s = ids0.clone().cuda(), ids0.clone().cuda(), ids0.clone().cuda()
+    lab_t, lab_v, lab_s = data.mask_step(t, v, s, seed=7)
+    assert lab_t.shape == (64, 50) and lab_v.shape == (64, 100) and lab_s.shape == (64, 100)
+    assert torch.equal(lab_v[:, :50], lab_v[:, 50:]) and torch.equal(lab_s[:, :50], lab_s[:, 50:])   # trainer.py:50,53
+    assert not torch.equal(lab_t, lab_v[:, :50])        # three independent draws (trainer.py:45-47)
+    for orig, new, lab in ((ids0, t, lab_t), (ids0, v, lab_v[:, :50]), (ids0, s, lab_s[:, :50])):
+        r = O.mask_tokens_rules(orig, new, lab.contiguous(), data.BERT_SPECIAL_IDS, 103)
+        assert r["label_mismatch"] == r["special_selected"] == r["changed_unselected"] == r["changed_not_to_mask"] == 0, r
+    # unaligned frames: the frame half carries no targets
+    t2, v2, s2 = ids0.clone().cuda(), ids0.clone().cuda(), ids0.clone().cuda()
+    _, lab_v2, _ = data.mask_step(t2, v2, s2, Lv=77, La=50, seed=7)
+    assert lab_v2.shape == (64, 127) and bool((lab_v2[:, 50:] == -100).all())
+
+
+def test_masked_batch_runs_through_the_model():
+    from tests.test_model_gpu import _build
+    from msa_b200.params import seeded_state_dict
+    ocfg = O.Cfg(hidden_size=128, num_hidden_layers=1, num_attention_heads=2, intermediate_size=256, vocab_size=30522,
+                 max_position_embeddings=64)
+    sd = seeded_state_dict(ocfg, "mosi", seed=1, std=0.03)
+    m = _build(ocfg, "mosi", sd).train()
+    batch = synth.tree_to(synth.make_batch(8, 16, 16, 16, 47, 74, seed=2, min_len=6, mlm=False), "cuda")
+    ids = batch["input_ids"]
+    labels = data.mask_step(ids[0], ids[3], ids[4], seed=1)
+    batch["masked_labels"] = labels
+    out, _ = m(**batch)
+    assert torch.isfinite(out[0])
+    out[0].backward()
+
+
+def test_cpu_tensors_and_bad_arguments_fail_loudly():
+    from msa_b200 import capi
+    ids = _ids(B=4, T=8)
+    with pytest.raises(capi.MMBError):
+        data.mask_ids_(ids, torch.empty_like(ids))          # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        data.mask_tokens(ids.cuda(), types.SimpleNamespace(mask_token=None), types.SimpleNamespace(mlm_probability=0.15))
