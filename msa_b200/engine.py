@@ -22,12 +22,23 @@ BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
 ST_ATTN, ST_OUT1, ST_OUT2 = 1, 2, 3
 
 
-def _split_k(M_out, N_out, K, sms=148):
-    """Split-K factor for a wgrad GEMM whose output (M_out x N_out) is small and whose K is the token count."""
-    tiles = ((M_out + 127) // 128) * ((N_out + 255) // 256 if N_out > 128 else 1)
+def _split_k(M_out, N_out, K, clusters=74):
+    """Split-K factor for a wgrad GEMM (small M_out x N_out output, K = token count) on the CTA-pair kernel: 256 x 256
+    output tiles, one work unit = (tile, K-slice), `clusters` CTA pairs walking the units round-robin.  Picks the factor
+    whose unit count fills whole waves best (e.g. 36 tiles x 2 = 72 units = one wave of 74 pairs at 97 %, where the old
+    "2 x SMs / tiles" rule gave 36 x 5 = 180 units = 2.43 waves at 81 %); ties go to the smaller factor (fewer fp32
+    reductions).  Every slice keeps at least 8 k-blocks of 64."""
+    tiles = ((M_out + 255) // 256) * ((N_out + 255) // 256)
     kb = (K + 63) // 64
-    want = max(1, (2 * sms + tiles - 1) // tiles)
-    return max(1, min(want, max(1, kb // 4)))
+    best, best_eff = 1, 0.0
+    for sk in range(1, max(1, min(32, kb // 8)) + 1):
+        units = tiles * sk
+        eff = units / (((units + clusters - 1) // clusters) * clusters)
+        if eff >= 0.95:
+            return sk                      # the smallest factor that fills its waves
+        if eff > best_eff:
+            best, best_eff = sk, eff
+    return best
 
 
 class Plan:
