@@ -253,6 +253,12 @@ typedef struct mmb_embed_args {
     int32_t L[2];
     int32_t H, V, max_pos;
     int32_t exact_frames; /* fp32 validation path: keep relu(W f + b) in fp32 (no bf16 rounding) on the way into x0_f32 */
+    /* optional (both or neither per modality): lets mmb_embed_bwd compute the projection weight gradient
+     * g_w = dpre^T · frames on the tensor cores (mmb_gemm, split-K) instead of a CUDA-core kernel.
+     *   frames_bf16[m]: [B*L[m], ldf] bf16 copy of the frames, ldf = frame_dim[m] rounded up to 8, written by mmb_embed_fwd
+     *   gw_pad[m]:      [H, ldf] f32 scratch (zeroed and consumed by mmb_embed_bwd) */
+    void* frames_bf16[2];
+    float* gw_pad[2];
 } mmb_embed_args;
 int mmb_embed_fwd(const mmb_embed_args* a, void* stream);
 int mmb_embed_bwd(const mmb_embed_args* a, void* stream);

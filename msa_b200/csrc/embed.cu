@@ -126,6 +126,8 @@ struct EmbedParams {
     float* g_ln1_g; float* g_ln1_b; float* g_ln2_g; float* g_ln2_b;
     float* g_w[2];                 // [H,D]
     float* g_wb[2];                // [H]
+    __nv_bfloat16* frames_bf16[2]; // optional [B*L, ldf] bf16 copy of the frames (ldf = D rounded up to 8)
+    float* gw_pad[2];              // optional [H, ldf] scratch of the tensor-core projection wgrad
 };
 
 constexpr uint32_t kStreamEmb1 = 0x100, kStreamEmb2 = 0x101;
@@ -218,6 +220,14 @@ embed_frame_fwd_kernel(const EmbedParams p, int mod) {  // mod 0 = visual (pass 
         sF[r * Dp + k] = (r0 + r) < nrows ? load_as_float(p.frames[mod], p.frames_dt[mod], (int64_t)(r0 + r) * D + k) : 0.f;
     }
     __syncthreads();
+    if (p.frames_bf16[mod] != nullptr) {      // bf16 copy (zero padded to ldf) for the tensor-core wgrad of the backward
+        const int ldf = (D + 7) & ~7;
+        for (int i = tid; i < kFrameRows * ldf; i += 256) {
+            const int r = i / ldf, k = i - r * ldf;
+            if (r0 + r < nrows)
+                p.frames_bf16[mod][(int64_t)(r0 + r) * ldf + k] = __float2bfloat16_rn(k < D ? sF[r * Dp + k] : 0.f);
+        }
+    }
     float acc[kFrameRows][NCH];
 #pragma unroll
     for (int r = 0; r < kFrameRows; ++r)
@@ -439,6 +449,14 @@ frame_wgrad_kernel(const EmbedParams p, int mod, int rows_per_cta) {
     }
 }
 
+// g_w[c][k] += pad[c][k]  (k < D; pad has row stride ldf)
+__global__ void add_padded_kernel(float* __restrict__ gw, const float* __restrict__ pad, int H, int D, int ldf) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= H * D) return;
+    const int c = i / D, k = i - c * D;
+    gw[i] += pad[(size_t)c * ldf + k];
+}
+
 static int fill_embed(EmbedParams& p, const mmb_embed_args* a) {
     MMB_REQUIRE(a != nullptr, "embed: null args");
     MMB_REQUIRE(a->B > 0 && a->T > 0 && a->L[0] >= 0 && a->L[1] >= 0, "embed: bad dims");
@@ -470,6 +488,10 @@ static int fill_embed(EmbedParams& p, const mmb_embed_args* a) {
     p.mean1 = a->mean1; p.rstd1 = a->rstd1; p.mean2 = a->mean2; p.rstd2 = a->rstd2;
     p.pframe = (__nv_bfloat16*)a->pframe;
     p.exact_frames = a->exact_frames;
+    for (int i = 0; i < 2; ++i) {
+        p.frames_bf16[i] = (__nv_bfloat16*)a->frames_bf16[i];
+        p.gw_pad[i] = a->gw_pad[i];
+    }
     p.dx0 = (const __nv_bfloat16*)a->dx0;
     p.dx0b = a->dx0b;
     p.dpre = (__nv_bfloat16*)a->dpre;
@@ -570,6 +592,47 @@ extern "C" int mmb_embed_bwd(const mmb_embed_args* a, void* stream) {
             MMB_REQUIRE(p.g_w[mod] && p.g_wb[mod] && p.frames[mod], "embed_bwd: null projection grads %d", mod);
             const int D = p.frame_dim[mod], nrows = p.d.B * L;
             MMB_REQUIRE(D <= 384, "embed_bwd: frame dim %d > 384 unsupported", D);
+            if (p.frames_bf16[mod] != nullptr && p.gw_pad[mod] != nullptr) {
+                // tensor-core path: g_w += dpre^T (H x rows) · frames (rows x D) as a split-K GEMM into the padded scratch,
+                // g_wb += colsum(dpre)
+                const int ldf = (D + 7) & ~7;
+                const int fr_base = mod == 0 ? 0 : p.d.B * p.d.L1;
+                MMB_CUDA(cudaMemsetAsync(p.gw_pad[mod], 0, (size_t)p.H * ldf * sizeof(float), st));
+                mmb_gemm_args ga;
+                memset(&ga, 0, sizeof(ga));
+                ga.A = p.dpre + (int64_t)fr_base * p.H;
+                ga.B = p.frames_bf16[mod];
+                ga.C = p.gw_pad[mod];
+                ga.lda = p.H;
+                ga.ldb = ldf;
+                ga.ldc = ldf;
+                ga.M = p.H;
+                ga.N = D;
+                ga.K = nrows;
+                ga.a_major = MMB_MAJOR_MN;
+                ga.b_major = MMB_MAJOR_MN;
+                ga.epilogue = MMB_EPI_ATOMIC_ADD_F32;
+                ga.alpha = 1.0f;
+                const int tile = D <= 128 ? 128 : 256, slots = D <= 128 ? num_sms() : num_sms() / 2;
+                const int tiles = ((p.H + tile - 1) / tile) * ((D + tile - 1) / tile);
+                int sk = slots / tiles, kb = (nrows + 63) / 64;
+                if (sk > kb / 4) sk = kb / 4;
+                ga.split_k = sk < 1 ? 1 : sk;
+                rc = mmb_gemm(&ga, st);
+                if (rc != MMB_OK) return rc;
+                add_padded_kernel<<<(p.H * D + 255) / 256, 256, 0, st>>>(p.g_w[mod], p.gw_pad[mod], p.H, D, ldf);
+                rc = check_launch("add_padded_kernel");
+                if (rc != MMB_OK) return rc;
+                mmb_colsum_args ca;
+                ca.X = p.dpre + (int64_t)fr_base * p.H;
+                ca.out = p.g_wb[mod];
+                ca.ld = p.H;
+                ca.M = nrows;
+                ca.N = p.H;
+                rc = mmb_colsum_bf16(&ca, st);
+                if (rc != MMB_OK) return rc;
+                continue;
+            }
             const int col_tiles = (p.H + 63) / 64;
             int chunks = (num_sms() * 2 + col_tiles - 1) / col_tiles;
             int rows_per_cta = (nrows + chunks - 1) / chunks;
