@@ -99,7 +99,7 @@ def profile_gemm(model, plan):
     gemm = plan._fn("gemm")
     stream = torch.cuda.current_stream()
     sp = ctypes.c_void_p(stream.cuda_stream)
-    evs, flops = [], 0.0
+    evs, flops, abytes = [], 0.0, 0.0
     model._prepare_grads()
     for seq in (plan.fwd, plan.bwd):
         for fn, a in seq:
@@ -110,11 +110,27 @@ def profile_gemm(model, plan):
                 e.record(stream)
                 evs.append((s, e))
                 flops += 2.0 * a.M * a.N * a.K
+                # algorithmic HBM bytes of the launch: both operands once, the output once (f32 for the wgrad epilogues),
+                # plus the auxiliary stream of the GELU / multiply epilogues
+                out_b = 4 if a.epilogue in (capi.EPI_STORE_F32, capi.EPI_ATOMIC_ADD_F32) else 2
+                aux_b = 2 if (a.aux and a.epilogue in (capi.EPI_GELU_BF16, capi.EPI_DGELU_BF16, capi.EPI_GELU_GRAD_BF16,
+                                                       capi.EPI_MUL_AUX_BF16)) else 0
+                abytes += 2.0 * a.K * (a.M + a.N) + float(a.M) * a.N * (out_b + aux_b)
             else:
                 capi.check(fn(ctypes.byref(a), sp), "launch")
     torch.cuda.synchronize()
     ms = sum(s.elapsed_time(e) for s, e in evs)
-    return flops, ms, len(evs)
+    return flops, ms, len(evs), abytes
+
+
+def measured_traffic(workload_name):
+    """DRAM bytes per GEMM launch measured under ncu for this workload (profiles/r1_gemm_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+    try:
+        d = json.load(open(p)).get(workload_name)
+        return None if d is None else float(d["traffic_bytes_per_launch"])
+    except (OSError, ValueError, KeyError):
+        return None
 
 
 def cpu_baseline(shape, workload, batch=4, steps=2, warmup=1):
@@ -250,7 +266,7 @@ def main():
     if rank == 0:
         plan = next(p for p in model._plans.values() if p.training)
         model(**resident[0])     # fresh forward state for the profiling pass
-        flops, gemm_ms, n_gemm = profile_gemm(model, plan)
+        flops, gemm_ms, n_gemm, gemm_bytes = profile_gemm(model, plan)
         opt.zero_grad()
         achieved = flops / (gemm_ms / 1e3) / 1e12
         gf = train_gflop_per_sample(shape, workload)
@@ -269,7 +285,11 @@ def main():
                     "h2d_bytes_per_step": synth.tree_bytes(host[0]), "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peaks["tflops"],
-                         "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": measured_traffic(workload.name),
+                         "traffic_note": "DRAM read+write bytes per GEMM launch, averaged over the ~160 GEMM launches of one "
+                                         "step (ncu, profiles/r1_gemm_traffic.json); algorithmic_bytes = the same average "
+                                         "computed from the launch shapes",
+                         "algorithmic_bytes": gemm_bytes / n_gemm,
                          "peak_source": peaks["source"], "launches_per_step": n_gemm,
                          "gemm_share_of_step": gemm_ms / (ms / args.steps)},
             "model_flops": {"train_gflop_per_sample": gf, "achieved_tflops_per_gpu": value / world * gf / 1e3,

@@ -83,3 +83,42 @@ def test_cpu_tensors_and_bad_arguments_fail_loudly():
         data.mask_ids_(ids, torch.empty_like(ids))          # CPU tensor: no fallback
     with pytest.raises(ValueError):
         data.mask_tokens(ids.cuda(), types.SimpleNamespace(mask_token=None), types.SimpleNamespace(mlm_probability=0.15))
+
+
+def test_sync_free_train_epoch_on_the_cuda_model():
+    """msa_b200.trainer_fast.train_epoch (row N1) drives the CUDA model with on-device masking and the fused AdamW:
+    losses come back finite, the optimizer stepped on every second batch (trainer.py:96), parameters moved."""
+    from msa_b200 import trainer_fast
+    from msa_b200.optim import FusedAdamW
+    from msa_b200.params import seeded_state_dict
+    from tests.test_model_gpu import _build
+    ocfg = O.Cfg(hidden_size=128, num_hidden_layers=1, num_attention_heads=2, intermediate_size=256, vocab_size=30522,
+                 max_position_embeddings=64)
+    sd = seeded_state_dict(ocfg, "mosi", seed=1, std=0.03)
+    m = _build(ocfg, "mosi", sd)
+    N, T = 12, 16
+    full = synth.make_batch(N, T, T, T, 47, 74, seed=4, min_len=6, mlm=False)
+
+    def collate(idx):            # the tuple structure of model_utils.collate (:117-142), sliced from one synthetic batch
+        i = torch.tensor(idx)
+        ids, vis, aud = full["input_ids"][0][i], full["input_ids"][1][i], full["input_ids"][2][i]
+        m_t, (m_tv, m_v), (m_ts, m_s) = full["attention_mask"]
+        tt = full["token_type_ids"][0][i]
+        text = (ids, None, tt, m_t[i], full["sentiment"][i])
+        visual = (ids.clone(), vis, full["ap_label"][0][i], tt, m_v[i], None)
+        speech = (ids.clone(), aud, full["ap_label"][1][i], tt, m_s[i], None)
+        return text, visual, speech, (m_tv[i], m_ts[i]), None, None
+
+    args = types.SimpleNamespace(train_batch_size=4, gradient_accumulation_step=1, mlm=True, mlm_probability=0.15)
+    opt = FusedAdamW(m, lr=1e-3)
+    steps = []
+    orig_step = opt.step
+    opt.step = lambda *a, **k: (steps.append(1), orig_step(*a, **k))[1]
+    sched = types.SimpleNamespace(step=lambda: None)
+    w0 = m.classifier1_1.weight.detach().clone()
+    torch.manual_seed(3)
+    out = trainer_fast.train_epoch(args, m, list(range(N)), opt, sched, _Tok(), collate_fn=collate)
+    assert len(steps) == 1                                   # 3 batches: only (step+1) = 2 satisfies (step+1) & 1 == 0
+    assert all(isinstance(v, float) and v == v for v in (out[0], out[5]))
+    assert torch.isfinite(out[4]).all()
+    assert not torch.equal(w0, m.classifier1_1.weight.detach())

@@ -1,0 +1,78 @@
+"""msa_b200.trainer_fast.train_epoch against a line-by-line restatement of trainer.train_epoch (trainer.py:13-101) on a
+recording fake model (CPU: the loop is host logic; the CUDA model is exercised by tests/test_data_gpu.py)."""
+import types
+
+import torch
+
+from msa_b200 import trainer_fast
+
+
+class _FakeModel(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.tensor(0.5))
+        self.calls = []
+
+    def forward(self, input_ids, token_type_ids, attention_mask, masked_labels, ap_label, sentiment):
+        self.calls.append((input_ids, token_type_ids, attention_mask, masked_labels, ap_label, sentiment))
+        loss = (self.w * sentiment.float().mean() + input_ids[0].float().mean() * 1e-3) ** 2
+        ap = self.w.detach() * 2 + len(self.calls)
+        label = loss.detach() * 0.25
+        return (loss, None, None, None, ap, label, None), None
+
+
+class _Opt:
+    def __init__(self):
+        self.steps = self.zeros = 0
+
+    def step(self):
+        self.steps += 1
+
+    def zero_grad(self):
+        self.zeros += 1
+
+
+def _collate(items):          # same tuple structure as model_utils.collate (:117-142)
+    B, T, D = len(items), 6, 3
+    ids = torch.stack([torch.full((T,), i + 1) for i in items])
+    frames = torch.ones(B, T, D, dtype=torch.float64)
+    text = (ids, torch.zeros(B, dtype=torch.int64), torch.zeros(B, T, dtype=torch.int64), torch.ones(B, T, dtype=torch.float64),
+            torch.tensor([float(i) for i in items]))
+    vis = (ids + 1, frames, torch.ones(B, dtype=torch.int64), torch.zeros(B, T, dtype=torch.int64), frames.clone(), None)
+    sp = (ids + 2, frames * 2, torch.zeros(B, dtype=torch.int64), torch.zeros(B, T, dtype=torch.int64), frames.long(), None)
+    return text, vis, sp, (torch.ones(B, T, dtype=torch.float64), torch.ones(B, T, dtype=torch.int64)), None, None
+
+
+def test_train_epoch_matches_the_reference_loop():
+    args = types.SimpleNamespace(train_batch_size=2, gradient_accumulation_step=1, mlm=False, mlm_probability=0.15)
+    data = list(range(10))            # 5 batches
+    torch.manual_seed(0)
+    model, opt, sched = _FakeModel(), _Opt(), _Opt()
+    out = trainer_fast.train_epoch(args, model, data, opt, sched, tokenizer=None, collate_fn=_collate, device=torch.device("cpu"))
+    # the `&` rule of trainer.py:96 with accumulation 1: steps on batches 2 and 4 only
+    assert opt.steps == 2 and sched.steps == 2 and opt.zeros == 2
+    assert len(model.calls) == 5
+    ids, tt, am, labels, ap, sent = model.calls[0]
+    assert len(ids) == 5 and len(labels) == 3 and labels[1].shape[-1] == 2 * ids[0].shape[-1]     # cat((l, l), -1)
+    assert am[1][1].dtype == torch.float64 and am[2][1].dtype == torch.int64                      # collate's dtypes kept
+    # restatement with per-step .item() (same sampler order through the same seed)
+    torch.manual_seed(0)
+    ref_model = _FakeModel()
+    from torch.utils.data import DataLoader, RandomSampler
+    tl = ll = 0.0
+    nb = 0
+    for step, batch in enumerate(DataLoader(data, sampler=RandomSampler(data), batch_size=2, collate_fn=_collate)):
+        o, _ = ref_model(**trainer_fast.unpack_batch(batch, torch.device("cpu")))
+        o[0].mean().backward()
+        tl += o[0].mean().item()
+        ll += o[5].mean().item()
+        ap_last = o[4]
+        nb += 1
+    assert abs(out[0] - tl / nb) < 1e-9 and abs(out[5] - ll / nb) < 1e-9
+    assert out[1] == out[2] == out[3] == 0.0
+    assert torch.allclose(out[4], ap_last / nb)                    # the reference's "last ap_loss / steps" quirk
+    # modulo stepping on request
+    model2, opt2 = _FakeModel(), _Opt()
+    trainer_fast.train_epoch(args, model2, data, opt2, _Opt(), None, collate_fn=_collate, device=torch.device("cpu"),
+                             faithful_stepping=False)
+    assert opt2.steps == 5
