@@ -49,7 +49,7 @@ constexpr int kHd = 64;              // head dim
 constexpr int kComputeWarps = 16;
 constexpr int kProducerWarp = 16, kScoreWarp = 17, kAccWarp = 18;
 constexpr int kWsThreads = 19 * 32;
-constexpr int kStages = 8;           // step-operand ring
+constexpr int kStages = 6;           // step-operand ring
 constexpr float kLog2eB = 1.4426950408889634f;
 constexpr int kBig = kRows * kHd * 2;     // 16 KB: 128-row operand tile (128 B rows, SWIZZLE_128B)
 constexpr int kSmall = kStep * kHd * 2;   // 8 KB: 64-row operand tile
@@ -61,7 +61,14 @@ template <bool kIsDq> constexpr int off_cols() { return kOffStep + kStages * 2 *
 constexpr int kColBytes = kStep * 16;                    // per stage: one 16-byte record per column (attn.cu: Rq / Rk)
 constexpr int kRowcBytes = kRows * 16;                   // per row buffer: one record per row
 template <bool kIsDq> constexpr int off_rowc() { return off_cols<kIsDq>() + kStages * kColBytes; }
-template <bool kIsDq> constexpr int off_bars() { return off_rowc<kIsDq>() + 2 * kRowcBytes; }
+// epilogue staging: per TMEM lane quarter a 32-row x 128-byte tile per output matrix (dQ | dV, dK), XOR-swizzled
+template <bool kIsDq> constexpr int stage_bytes() { return (kIsDq ? 1 : 2) * 4 * 4096; }
+template <bool kIsDq> constexpr int off_stage() { return off_rowc<kIsDq>() + 2 * kRowcBytes; }
+// sequence metadata (cu_seqlens, kv_end) of up to kMetaSeqs sequences, copied once per CTA
+constexpr int kMetaSeqs = 2048;
+constexpr int kMetaBytes = (2 * kMetaSeqs + 4) * 4;
+template <bool kIsDq> constexpr int off_meta() { return off_stage<kIsDq>() + stage_bytes<kIsDq>(); }
+template <bool kIsDq> constexpr int off_bars() { return off_meta<kIsDq>() + kMetaBytes; }
 template <bool kIsDq> constexpr int smem_bytes() { return off_bars<kIsDq>() + 256 + 1024; }
 // barrier slots (8 bytes each)
 enum { B_ROW_FULL = 0, B_ROW_EMPTY = 2, B_STEP_FULL = 4, B_STEP_EMPTY = 12, B_SC_FULL = 20, B_SC_EMPTY = 22,
@@ -80,11 +87,6 @@ struct BwdTcParams {
 __device__ __forceinline__ uint32_t lds32_b(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
@@ -137,15 +139,15 @@ struct Item {
 struct ItemRaw {
     int idx, row0, row1, kvend;
 };
-__device__ __forceinline__ ItemRaw fetch_item(const BwdTcParams& p, int idx, int total) {
+__device__ __forceinline__ ItemRaw fetch_item(const BwdTcParams& p, const int* cu, const int* kvend, int idx, int total) {
     ItemRaw r;
     r.idx = idx;
     r.row0 = r.row1 = r.kvend = 0;
     if (idx < total) {
         const int seq = idx / (p.tiles * p.nheads);
-        r.row0 = p.cu_seqlens[seq];
-        r.row1 = p.cu_seqlens[seq + 1];
-        if (p.kv_end != nullptr) r.kvend = p.kv_end[seq];
+        r.row0 = cu[seq];
+        r.row1 = cu[seq + 1];
+        if (kvend != nullptr) r.kvend = kvend[seq];
     }
     return r;
 }
@@ -251,6 +253,18 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
         }
         ptx::fence_barrier_init();
     }
+    // sequence metadata -> shared memory (items are decoded from it by every role; an item whose tile lies beyond its
+    // sequence is skipped for the price of two shared loads instead of a global round trip)
+    extern __shared__ uint8_t smem_generic[];
+    int* meta = reinterpret_cast<int*>(smem_generic + (sbase - ptx::smem_u32(smem_generic)) + off_meta<kIsDq>());
+    const bool meta_in_smem = p.nseq <= kMetaSeqs;
+    if (meta_in_smem) {
+        for (int i = tid; i <= p.nseq; i += kWsThreads) meta[i] = p.cu_seqlens[i];
+        if (p.kv_end != nullptr)
+            for (int i = tid; i < p.nseq; i += kWsThreads) meta[kMetaSeqs + 2 + i] = p.kv_end[i];
+    }
+    const int* m_cu = meta_in_smem ? meta : p.cu_seqlens;
+    const int* m_kv = p.kv_end == nullptr ? nullptr : (meta_in_smem ? meta + kMetaSeqs + 2 : p.kv_end);
     if (warp == kScoreWarp) ptx::tmem_alloc<512>(tmem_slot);
     ptx::tc_fence_before();
     __syncthreads();
@@ -266,10 +280,10 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
         // per-row records (attn.cu): planes [0, nh) = Rq {-LSE, -D, row dropout key}, [nh, 2 nh) = Rk {bias, column key};
         // the dQ pass wants Rq for its rows and Rk for its columns, the dKV pass the other way round
         uint32_t g = 0, n = 0;
-        ItemRaw raw = fetch_item(p, blockIdx.x, total_items);
+        ItemRaw raw = fetch_item(p, m_cu, m_kv, blockIdx.x, total_items);
         for (int idx = blockIdx.x; idx < total_items; idx += stride) {
             const Item cur = make_item<kIsDq>(p, raw, total_items);
-            raw = fetch_item(p, idx + stride, total_items);              // next item's metadata loads fly under this item
+            raw = fetch_item(p, m_cu, m_kv, idx + stride, total_items);
             if (cur.nsteps == 0) continue;
             const int rb = n & 1;
             const int col_q = cur.head * kHd, col_k = p.H + cur.head * kHd, col_v = 2 * p.H + cur.head * kHd;
@@ -310,17 +324,16 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
                     }
                 }
                 __syncwarp();
-                TRACE(0, g, 2);
             }
             ++n;
         }
     } else if (warp == kScoreWarp) {
         // ================================================================ score MMAs: S = A0 B0^T, dP = A1 B1^T
         uint32_t g = 0, n = 0;
-        ItemRaw raw = fetch_item(p, blockIdx.x, total_items);
+        ItemRaw raw = fetch_item(p, m_cu, m_kv, blockIdx.x, total_items);
         for (int idx = blockIdx.x; idx < total_items; idx += stride) {
             const Item cur = make_item<kIsDq>(p, raw, total_items);
-            raw = fetch_item(p, idx + stride, total_items);
+            raw = fetch_item(p, m_cu, m_kv, idx + stride, total_items);
             if (cur.nsteps == 0) continue;
             const int rb = n & 1;
             ptx::mbar_wait(bar(B_ROW_FULL + rb), (n >> 1) & 1);
@@ -346,10 +359,10 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
     } else if (warp == kAccWarp) {
         // ================================================================ accumulating MMAs
         uint32_t g = 0, n = 0;
-        ItemRaw raw = fetch_item(p, blockIdx.x, total_items);
+        ItemRaw raw = fetch_item(p, m_cu, m_kv, blockIdx.x, total_items);
         for (int idx = blockIdx.x; idx < total_items; idx += stride) {
             const Item cur = make_item<kIsDq>(p, raw, total_items);
-            raw = fetch_item(p, idx + stride, total_items);
+            raw = fetch_item(p, m_cu, m_kv, idx + stride, total_items);
             if (cur.nsteps == 0) continue;
             const int a = n & 1;
             ptx::mbar_wait(bar(B_ACC_EMPTY + a), ((n >> 1) & 1) ^ 1);
@@ -388,8 +401,25 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
         // that nobody waits for the item's last accumulating MMA
         bool pend = false;
         uint32_t pend_n = 0;
-        int64_t pend_row = 0;      // packed row of this thread's output, or -1
+        int pend_base = 0;         // packed row of the tile's first row
+        int pend_valid = 0;        // rows of the tile that belong to the sequence
         int pend_head = 0;
+        // The four warps of a TMEM lane quarter own the same 32 rows (16 columns each).  Writing them straight to global
+        // memory costs one 32-byte wavefront per row and instruction (~1000-2000 LSU cycles per work item); instead they
+        // meet in a swizzled shared-memory tile and write whole 128-byte rows, 4 rows per instruction.
+        const int quarter = warp & 3;
+        const uint32_t stg = sbase + off_stage<kIsDq>() + (uint32_t)quarter * 4096;
+        auto quarter_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory"); };
+        auto flush = [&](uint32_t tile, int col_off) {     // this warp: rows cq*8 .. cq*8+7 of the quarter's 32
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int i = cq * 8 + it * 4 + (lane >> 3), c = lane & 7;
+                const uint4 v = lds_u4(tile + i * 128 + ((c ^ (i & 7)) << 4));
+                const int trow = quarter * 32 + i;
+                if (trow < pend_valid)
+                    *reinterpret_cast<uint4*>(p.dqkv + (int64_t)(pend_base + trow) * ld + col_off + c * 8) = v;
+            }
+        };
         auto epilogue = [&]() {
             const int a = pend_n & 1;
             ptx::mbar_wait(bar(B_ACC_FULL + a), (pend_n >> 1) & 1);
@@ -402,43 +432,38 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(bar(B_ACC_EMPTY + a));
-            if (pend_row >= 0) {
-                if (kIsDq) {
-                    __nv_bfloat16* o = p.dqkv + pend_row * ld + pend_head * kHd + cq * 16;
+            quarter_sync();                                 // the previous item's staging tile has been read by all four
+            const float s0 = kIsDq ? p.scale : p.inv_keep;  // dQ * scale | dV * 1/keep
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        uint4 u;
-                        u.x = pack_bf16x2(__uint_as_float(r0[8 * j + 0]) * p.scale, __uint_as_float(r0[8 * j + 1]) * p.scale);
-                        u.y = pack_bf16x2(__uint_as_float(r0[8 * j + 2]) * p.scale, __uint_as_float(r0[8 * j + 3]) * p.scale);
-                        u.z = pack_bf16x2(__uint_as_float(r0[8 * j + 4]) * p.scale, __uint_as_float(r0[8 * j + 5]) * p.scale);
-                        u.w = pack_bf16x2(__uint_as_float(r0[8 * j + 6]) * p.scale, __uint_as_float(r0[8 * j + 7]) * p.scale);
-                        *reinterpret_cast<uint4*>(o + 8 * j) = u;
-                    }
-                } else {
-                    __nv_bfloat16* oK = p.dqkv + pend_row * ld + p.H + pend_head * kHd + cq * 16;
-                    __nv_bfloat16* oV = oK + p.H;
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        uint4 u, v;
-                        v.x = pack_bf16x2(__uint_as_float(r0[8 * j + 0]) * p.inv_keep, __uint_as_float(r0[8 * j + 1]) * p.inv_keep);
-                        v.y = pack_bf16x2(__uint_as_float(r0[8 * j + 2]) * p.inv_keep, __uint_as_float(r0[8 * j + 3]) * p.inv_keep);
-                        v.z = pack_bf16x2(__uint_as_float(r0[8 * j + 4]) * p.inv_keep, __uint_as_float(r0[8 * j + 5]) * p.inv_keep);
-                        v.w = pack_bf16x2(__uint_as_float(r0[8 * j + 6]) * p.inv_keep, __uint_as_float(r0[8 * j + 7]) * p.inv_keep);
-                        u.x = pack_bf16x2(__uint_as_float(r1[8 * j + 0]) * p.scale, __uint_as_float(r1[8 * j + 1]) * p.scale);
-                        u.y = pack_bf16x2(__uint_as_float(r1[8 * j + 2]) * p.scale, __uint_as_float(r1[8 * j + 3]) * p.scale);
-                        u.z = pack_bf16x2(__uint_as_float(r1[8 * j + 4]) * p.scale, __uint_as_float(r1[8 * j + 5]) * p.scale);
-                        u.w = pack_bf16x2(__uint_as_float(r1[8 * j + 6]) * p.scale, __uint_as_float(r1[8 * j + 7]) * p.scale);
-                        *reinterpret_cast<uint4*>(oV + 8 * j) = v;
-                        *reinterpret_cast<uint4*>(oK + 8 * j) = u;
-                    }
-                }
+            for (int j = 0; j < 2; ++j) {
+                const uint32_t off = (uint32_t)(lane * 128 + (((cq * 2 + j) ^ (lane & 7)) << 4));
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off),
+                             "r"(pack_bf16x2(__uint_as_float(r0[8 * j + 0]) * s0, __uint_as_float(r0[8 * j + 1]) * s0)),
+                             "r"(pack_bf16x2(__uint_as_float(r0[8 * j + 2]) * s0, __uint_as_float(r0[8 * j + 3]) * s0)),
+                             "r"(pack_bf16x2(__uint_as_float(r0[8 * j + 4]) * s0, __uint_as_float(r0[8 * j + 5]) * s0)),
+                             "r"(pack_bf16x2(__uint_as_float(r0[8 * j + 6]) * s0, __uint_as_float(r0[8 * j + 7]) * s0))
+                             : "memory");
+                if (!kIsDq)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + 4 * 4096 + off),
+                                 "r"(pack_bf16x2(__uint_as_float(r1[8 * j + 0]) * p.scale, __uint_as_float(r1[8 * j + 1]) * p.scale)),
+                                 "r"(pack_bf16x2(__uint_as_float(r1[8 * j + 2]) * p.scale, __uint_as_float(r1[8 * j + 3]) * p.scale)),
+                                 "r"(pack_bf16x2(__uint_as_float(r1[8 * j + 4]) * p.scale, __uint_as_float(r1[8 * j + 5]) * p.scale)),
+                                 "r"(pack_bf16x2(__uint_as_float(r1[8 * j + 6]) * p.scale, __uint_as_float(r1[8 * j + 7]) * p.scale))
+                                 : "memory");
+            }
+            quarter_sync();
+            if (kIsDq) {
+                flush(stg, pend_head * kHd);                                // dQ
+            } else {
+                flush(stg, 2 * p.H + pend_head * kHd);                      // dV
+                flush(stg + 4 * 4096, p.H + pend_head * kHd);               // dK
             }
             pend = false;
         };
-        ItemRaw raw = fetch_item(p, blockIdx.x, total_items);
+        ItemRaw raw = fetch_item(p, m_cu, m_kv, blockIdx.x, total_items);
         for (int idx = blockIdx.x; idx < total_items; idx += stride) {
             const Item cur = make_item<kIsDq>(p, raw, total_items);
-            raw = fetch_item(p, idx + stride, total_items);
+            raw = fetch_item(p, m_cu, m_kv, idx + stride, total_items);
             if (!cur.valid) continue;
             const int rr = cur.tile * kRows + r;        // this thread's query (dQ pass) / key (dKV pass)
             if (cur.nsteps == 0) {
@@ -500,7 +525,8 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
             }
             pend = true;
             pend_n = n;
-            pend_row = rr < cur.S ? (int64_t)(cur.row0 + rr) : -1;
+            pend_base = cur.row0 + cur.tile * kRows;
+            pend_valid = min(kRows, cur.S - cur.tile * kRows);
             pend_head = cur.head;
             ++n;
         }

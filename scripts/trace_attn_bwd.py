@@ -17,6 +17,10 @@ rel = lambda x: int(x) - t0 if x else -1
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 48
 last = max(g for g in range(1024) if buf[3, g, 3] > 0)
 print("steps traced:", last + 1, "total cycles:", int(buf[3, last, 3]) - t0, "avg per step:", (int(buf[3, last, 3]) - t0) / (last + 1))
+print("items (compute warp 0): item | top  rowfullOK  recordsRead")
+for i in range(12):
+    I = buf[0, i]
+    print(f"  item {i:3d} | {rel(I[0]):7d} {rel(I[1]):7d} {rel(I[3]):7d}")
 print("step | prod: top emptyOK fullArr | score: top stepOK slotOK issued | acc: top stagedOK issued | comp: top scoresOK loaded stagedArr")
 for g in range(n):
     P, S, A, C = buf[0, g], buf[1, g], buf[2, g], buf[3, g]
