@@ -132,11 +132,6 @@ __device__ __forceinline__ uint32_t rng_pair(uint32_t row_key, uint32_t pair) {
 }
 __device__ __forceinline__ bool rng_keep_lo(uint32_t bits, uint32_t thresh16) { return (bits & 0xFFFFu) >= thresh16; }
 __device__ __forceinline__ bool rng_keep_hi(uint32_t bits, uint32_t thresh16) { return (bits >> 16) >= thresh16; }
-// decision for a single column
-__device__ __forceinline__ bool rng_keep_col(uint32_t row_key, uint32_t col, uint32_t thresh16) {
-    const uint32_t bits = rng_pair(row_key, col >> 1);
-    return (col & 1u) ? rng_keep_hi(bits, thresh16) : rng_keep_lo(bits, thresh16);
-}
 
 // Attention-probability dropout (tcgen05 kernels): the decision for (query q, key k) is
 //     keep  <=>  (qkey[q] * kkey[k]) mod 2^32  >=  thresh16 << 16
