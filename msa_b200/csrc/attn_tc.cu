@@ -151,6 +151,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
     const uint32_t qkey = p.thresh ? attn_drop_qkey(p.seed, p.rng_stream, prob_base + (uint32_t)q) : 0u;
     const uint32_t thresh32 = p.thresh << 16;
     const int r7 = r & 7;
+    const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
 
     for (int kt = 0; kt < nkv; ++kt) {
         const int st = kt & 1;
@@ -183,10 +184,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float4 b = bias4[(c >> 2) + i];
-                m_part = fmaxf(m_part, fmaf(__uint_as_float(raw[4 * i + 0]), p.scale_log2, b.x));
-                m_part = fmaxf(m_part, fmaf(__uint_as_float(raw[4 * i + 1]), p.scale_log2, b.y));
-                m_part = fmaxf(m_part, fmaf(__uint_as_float(raw[4 * i + 2]), p.scale_log2, b.z));
-                m_part = fmaxf(m_part, fmaf(__uint_as_float(raw[4 * i + 3]), p.scale_log2, b.w));
+                const float2 x0 = fma2(make_float2(__uint_as_float(raw[4 * i + 0]), __uint_as_float(raw[4 * i + 1])), sc2,
+                                       make_float2(b.x, b.y));
+                const float2 x1 = fma2(make_float2(__uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3])), sc2,
+                                       make_float2(b.z, b.w));
+                m_part = fmaxf(m_part, fmaxf(fmaxf(x0.x, x0.y), fmaxf(x1.x, x1.y)));
             }
         }
         sMax[half * kTK + r] = m_part;
@@ -196,19 +198,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
             ptx::mbar_wait(bar_o, (kt - 1) & 1);
             ptx::tc_fence_after();
         }
-        __syncthreads();
-        const float m_new = fmaxf(m_run, fmaxf(sMax[r], sMax[kTK + r]));
+        // Lazy rescaling: the running reference maximum only moves (and O / l are only rescaled) when some row of the
+        // tile exceeds it by more than 2^8 — otherwise the stale reference is kept: probabilities stay <= 256, which
+        // fp32 sums and bf16 P hold without loss, and the TMEM round trip of O is skipped.  Block-uniform decision.
+        const int moved = __syncthreads_or(m_part > m_run + 8.f);
+        float m_new = m_run, corr = 1.f;
+        if (moved) {
+            m_new = fmaxf(m_run, fmaxf(sMax[r], sMax[kTK + r]));
+        }
         // a fully masked-so-far row (all -inf) keeps m = -inf: use 0 as the reference to avoid inf - inf
         const float m_ref = m_new == -INFINITY ? 0.f : m_new;
-        const float corr = ptx_ex2(m_run - m_ref);
+        if (moved) corr = ptx_ex2(m_run - m_ref);
         if (kt > 0) {
-            uint32_t raw[32];
-            ptx::tmem_ld_32x32(tO, raw);
-            ptx::tmem_ld_wait();
+            if (moved) {
+                uint32_t raw[32];
+                ptx::tmem_ld_32x32(tO, raw);
+                ptx::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * corr);
-            tmem_st_32x32(tO, raw);
-            tmem_st_wait();
+                for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * corr);
+                tmem_st_32x32(tO, raw);
+                tmem_st_wait();
+            }
             if (tid == 0 && kt + 1 < nkv) load_v(kt + 1);      // the V stage consumed by tile kt-1 is free
             if (kt + 1 < nkv && tid < kTK) {
                 const int k0 = (kt + 1) * kTK;
@@ -220,6 +230,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         }
         // ---- pass 2: probabilities -> bf16 P row of slab `half` (K-major SWIZZLE_128B), partial running sum
         float l_tile = 0.f;
+        const float2 nm2 = make_float2(-m_ref, -m_ref);
         const uint32_t prow = sP + half * (kTQ * 128) + r * 128;
 #pragma unroll
         for (int c = 0; c < 64; c += 32) {
@@ -230,13 +241,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float4 b = bias4[(c >> 2) + i];
-                pv[4 * i + 0] = ptx_ex2(fmaf(__uint_as_float(raw[4 * i + 0]), p.scale_log2, b.x - m_ref));
-                pv[4 * i + 1] = ptx_ex2(fmaf(__uint_as_float(raw[4 * i + 1]), p.scale_log2, b.y - m_ref));
-                pv[4 * i + 2] = ptx_ex2(fmaf(__uint_as_float(raw[4 * i + 2]), p.scale_log2, b.z - m_ref));
-                pv[4 * i + 3] = ptx_ex2(fmaf(__uint_as_float(raw[4 * i + 3]), p.scale_log2, b.w - m_ref));
+                const float2 x0 = fma2(make_float2(__uint_as_float(raw[4 * i + 0]), __uint_as_float(raw[4 * i + 1])), sc2,
+                                       add2(make_float2(b.x, b.y), nm2));
+                const float2 x1 = fma2(make_float2(__uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3])), sc2,
+                                       add2(make_float2(b.z, b.w), nm2));
+                pv[4 * i + 0] = ptx_ex2(x0.x);
+                pv[4 * i + 1] = ptx_ex2(x0.y);
+                pv[4 * i + 2] = ptx_ex2(x1.x);
+                pv[4 * i + 3] = ptx_ex2(x1.y);
             }
+            {
+                float2 acc2 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) l_tile += pv[i];
+                for (int i = 0; i < 32; i += 2) acc2 = add2(acc2, make_float2(pv[i], pv[i + 1]));
+                l_tile += acc2.x + acc2.y;
+            }
             if (p.thresh != 0u) {     // dropped entries become 0; the 1/(1-p) rescale is applied once in the epilogue
                 const uint4* kk4 = reinterpret_cast<const uint4*>(sKk + st * kTK + half * 64 + c);
 #pragma unroll
