@@ -197,3 +197,27 @@ def test_gradient_reducer_two_ranks_gloo():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
+
+
+def test_wgrad_split_k_fills_whole_waves():
+    """engine._split_k: the (tiles x splits) work units of a wgrad GEMM should fill whole waves of the 74 CTA pairs."""
+    from msa_b200.engine import _split_k
+    for (m, n, k) in ((768, 3072, 16000), (3072, 768, 73600), (2304, 768, 16000), (768, 768, 73600), (30522, 768, 16000)):
+        sk = _split_k(m, n, k)
+        tiles = -(-m // 256) * -(-n // 256)
+        units = tiles * sk
+        eff = units / (-(-units // 74) * 74)
+        assert eff >= 0.95, (m, n, k, sk, eff)
+        assert (k + 63) // 64 // sk >= 8            # every K-slice keeps at least 8 k-blocks
+    assert _split_k(768, 3072, 600) == 1             # too short to split
+    assert _split_k(30522, 768, 16000) == 1          # already 4.86 waves of tiles
+
+
+def test_attention_workspace_size_is_exported():
+    from msa_b200 import capi
+    L = capi.lib()
+    import ctypes
+    L.mmb_attn_bwd_workspace_bytes.restype = ctypes.c_size_t
+    L.mmb_attn_bwd_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+    assert L.mmb_attn_bwd_workspace_bytes(1000, 12) == 2 * 12 * 1000 * 16     # Rq + Rk planes of 16-byte records
+    assert L.mmb_attn_bwd_workspace_bytes(0, 12) == 0
