@@ -178,6 +178,40 @@ def test_attention_fwd_bwd(lens, nh):
         assert _rel(got, want) < 2e-2, name   # P and dS are rounded to bf16 before the second MMA
 
 
+def test_attention_many_short_sequences():
+    """More sequences than the backward kernel keeps in shared memory (2048): exercises its global-metadata path, and
+    work items of one to two rows."""
+    from msa_b200 import capi
+    torch.manual_seed(12)
+    nh, H = 1, 64
+    lens = [3, 5, 4, 1, 2, 6] * 360            # 2160 sequences
+    rows = sum(lens)
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    qkv = _bf(torch.randn(rows, 3 * H, device="cuda"))
+    keybias = torch.zeros(rows, device="cuda")
+    cu_t = torch.tensor(cu, device="cuda", dtype=torch.int32)
+    ctx = torch.empty(rows, H, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(nh, rows, device="cuda")
+    dctx = _bf(torch.randn(rows, H, device="cuda"))
+    dqkv = torch.zeros(rows, 3 * H, device="cuda", dtype=torch.bfloat16)
+    a = capi.attn_args(qkv, ctx, lse, keybias, cu_t, H, nh, max(lens), dctx=dctx, dqkv=dqkv,
+                       bwd_ws=capi.attn_bwd_workspace(rows, nh, "cuda"))
+    capi.call("attn_fwd", a)
+    capi.call("attn_bwd", a)
+    # block-diagonal reference in one shot: additive -inf mask between different sequences
+    seq_id = torch.repeat_interleave(torch.arange(len(lens), device="cuda"), torch.tensor(lens, device="cuda"))
+    x = qkv.float().requires_grad_(True)
+    q, k, v = x[:, :H], x[:, H:2 * H], x[:, 2 * H:]
+    s_ = q @ k.t() / 8.0
+    s_ = s_.masked_fill(seq_id[:, None] != seq_id[None, :], float("-inf"))
+    ref = torch.softmax(s_, -1) @ v
+    assert _rel(ctx.float(), ref) < 3 * BF16_EPS
+    ref.backward(dctx.float())
+    assert _rel(dqkv.float(), x.grad) < 2e-2
+
+
 def test_attention_all_keys_masked_matches_additive_mask():
     """A sequence whose keys are ALL masked: the reference's additive -10000 (not -inf) makes softmax uniform
     over the real keys; the kernel must reproduce that, not NaN."""
