@@ -182,7 +182,7 @@ typedef struct mmb_attn_args {
     float p_drop;
     uint64_t seed;
     uint32_t rng_stream;
-    uint32_t flags; /* reserved, must be 0 */
+    uint32_t flags; /* 0 = default; bring-up: bit 1 forces the persistent warp-specialised forward kernel, bit 2 the other one */
 } mmb_attn_args;
 size_t mmb_attn_bwd_workspace_bytes(int total_rows, int nheads);
 int mmb_attn_fwd(const mmb_attn_args* a, void* stream);

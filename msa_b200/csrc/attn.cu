@@ -15,15 +15,21 @@
 //     Rk[h][row] = { key bias * log2(e), dropout key of the probability COLUMN (key `row` of head h), 0, 0 }
 // ws = [Rq planes: nheads][Rk planes: nheads], each plane total_rows records.  (16-byte records because TMA needs
 // 16-byte aligned source addresses and the packed row offsets of the sequences are arbitrary.)
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace mmb {
 
+#ifndef MMB_ATTN_FWD_DEFAULT_WS
+#define MMB_ATTN_FWD_DEFAULT_WS 1
+#endif
 constexpr int kD = 64;       // head dim
 constexpr float kLog2e = 1.4426950408889634f;
 
 int launch_attn_fwd_tc(const mmb_attn_args* a, cudaStream_t stream);                        // attn_tc.cu
+int launch_attn_fwd_ws(const mmb_attn_args* a, cudaStream_t stream);                        // attn_fwd_ws.cu
 int launch_attn_bwd_tc(const mmb_attn_args* a, cudaStream_t stream);          // attn_bwd_tc.cu
 
 __global__ void __launch_bounds__(256)
@@ -81,7 +87,14 @@ extern "C" int mmb_attn_fwd(const mmb_attn_args* a, void* stream) {
     int rc = check_args(a);
     if (rc != MMB_OK) return rc;
     MMB_REQUIRE(a->ctx != nullptr, "attn_fwd: null ctx");
-    return launch_attn_fwd_tc(a, (cudaStream_t)stream);
+    // two forward kernels with the same contract: the persistent warp-specialised one (attn_fwd_ws.cu) and the
+    // 2-CTA-per-SM one (attn_tc.cu); flags bit 1 / bit 2 force one of them, MMB_ATTN_FWD=ws|tc sets the default (A/B runs)
+    static const int dflt = [] {
+        const char* e = getenv("MMB_ATTN_FWD");
+        return (e != nullptr && e[0] == 't') ? 0 : ((e != nullptr && e[0] == 'w') ? 1 : MMB_ATTN_FWD_DEFAULT_WS);
+    }();
+    const bool ws = (a->flags & 2) ? true : ((a->flags & 4) ? false : dflt != 0);
+    return ws ? launch_attn_fwd_ws(a, (cudaStream_t)stream) : launch_attn_fwd_tc(a, (cudaStream_t)stream);
 }
 
 extern "C" int mmb_attn_bwd(const mmb_attn_args* a, void* stream) {
