@@ -183,10 +183,30 @@ typedef struct mmb_attn_args {
     uint64_t seed;
     uint32_t rng_stream;
     uint32_t flags; /* 0 = default; bring-up: bit 1 forces the persistent warp-specialised forward kernel, bit 2 the other one */
+    const void* work;       /* NULL, or the work lists written by mmb_attn_schedule for the same cu_seqlens / kv_end /
+                               nheads / max_seqlen: the persistent kernels then take their (sequence, head, tile) items
+                               longest first instead of in index order (same results bit for bit; evens out the CTAs) */
 } mmb_attn_args;
 size_t mmb_attn_bwd_workspace_bytes(int total_rows, int nheads);
 int mmb_attn_fwd(const mmb_attn_args* a, void* stream);
 int mmb_attn_bwd(const mmb_attn_args* a, void* stream);
+
+/* Work lists for the persistent attention kernels, built on the device once per batch (the sequence lengths and
+ * kv_end are device data: no host round trip) and shared by every layer's forward and backward launch.
+ * work = 16-byte records: [0] = {count_q, count_kv, cap, count_kv_unmasked}, cap = nseq * nheads * ceil(max_seqlen / 128);
+ * [1, 1 + cap): one record {first row, length, effective key count, head << 16 | tile} per 128-query tile of every
+ * (sequence, head), sequences ordered by effective key count (length, or kv_end where that is smaller), longest first
+ * — an item of the forward and of the dQ pass costs ceil(effective keys / 64) steps; [1 + cap, 1 + 2 cap): the 128-key
+ * tiles of the dK/dV pass, first those that hold an unmasked key (sequences ordered by length: ceil(length / 64) steps
+ * each), then the fully masked ones (zero fill only).  nseq <= 8192. */
+typedef struct mmb_attn_schedule_args {
+    const int32_t* cu_seqlens; /* [nseq + 1] */
+    const int32_t* kv_end;     /* [nseq] or NULL */
+    void* work;                /* out: mmb_attn_schedule_bytes(...) bytes, 16-byte aligned */
+    int32_t nseq, nheads, max_seqlen;
+} mmb_attn_schedule_args;
+size_t mmb_attn_schedule_bytes(int nseq, int nheads, int max_seqlen);
+int mmb_attn_schedule(const mmb_attn_schedule_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Packed batch: the reference's three encoder passes (MMBertForPretraining.py:402-404) are packed into

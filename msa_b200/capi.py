@@ -107,6 +107,7 @@ DrlnFwdArgs = _make_struct("mmb_drln_fwd_args")
 DrlnBwdArgs = _make_struct("mmb_drln_bwd_args")
 ColsumArgs = _make_struct("mmb_colsum_args")
 AttnArgs = _make_struct("mmb_attn_args")
+AttnScheduleArgs = _make_struct("mmb_attn_schedule_args")
 PackArgs = _make_struct("mmb_pack_args")
 EmbedArgs = _make_struct("mmb_embed_args")
 CeArgs = _make_struct("mmb_ce_args")
@@ -201,10 +202,23 @@ def attn_bwd_workspace(total_rows, nheads, device):
 
 
 def attn_args(qkv, ctx, lse, keybias, cu_seqlens, H, nheads, max_seqlen, dctx=None, dqkv=None, bwd_ws=None,
-              p_drop=0.0, seed=0, rng_stream=0, flags=0, kv_end=None):
+              p_drop=0.0, seed=0, rng_stream=0, flags=0, kv_end=None, work=None):
     return fill(AttnArgs(), qkv=qkv, ctx=ctx, lse=lse, keybias=keybias, cu_seqlens=cu_seqlens, dctx=dctx, dqkv=dqkv,
                 bwd_ws=bwd_ws, kv_end=kv_end, H=H, nheads=nheads, nseq=cu_seqlens.numel() - 1, max_seqlen=max_seqlen,
-                total_rows=qkv.shape[0], p_drop=p_drop, seed=seed, rng_stream=rng_stream, flags=flags)
+                total_rows=qkv.shape[0], p_drop=p_drop, seed=seed, rng_stream=rng_stream, flags=flags, work=work)
+
+
+def attn_schedule_buffer(nseq, nheads, max_seqlen, device):
+    """int32 tensor [records, 4] for mmb_attn_schedule (size from mmb_attn_schedule_bytes)."""
+    L = lib()
+    L.mmb_attn_schedule_bytes.restype = ctypes.c_size_t
+    L.mmb_attn_schedule_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    return torch.empty(L.mmb_attn_schedule_bytes(nseq, nheads, max_seqlen) // 16, 4, device=device, dtype=torch.int32)
+
+
+def attn_schedule_args(cu_seqlens, kv_end, work, nheads, max_seqlen):
+    return fill(AttnScheduleArgs(), cu_seqlens=cu_seqlens, kv_end=kv_end, work=work, nseq=cu_seqlens.numel() - 1,
+                nheads=nheads, max_seqlen=max_seqlen)
 
 
 def cast_bf16(src, dst):

@@ -65,12 +65,81 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dctx, const __nv_bfloat16
     }
 }
 
+// Work lists of the persistent kernels (mmb_attn_schedule; record layout in the header).  One CTA: the sequences are
+// rank-sorted in shared memory (O(nseq^2 / threads) comparisons: ~40 at 3 x 64 sequences), one thread runs the prefix
+// sum over the sorted order, then every sequence writes its own records.
+constexpr int kSchedThreads = 1024;
+constexpr int kSchedMaxSeqs = 8192;
+__global__ void __launch_bounds__(kSchedThreads)
+attn_schedule_kernel(const int* __restrict__ cu, const int* __restrict__ kv_end, int4* __restrict__ work, int nseq,
+                     int nheads, int cap) {
+    extern __shared__ int sm[];
+    int* len = sm;                 // sequence length
+    int* eff = sm + nseq;          // keys before the all-masked tail
+    int* ord_q = sm + 2 * nseq;    // rank -> sequence, by eff (forward / dQ items)
+    int* ord_kv = sm + 3 * nseq;   // rank -> sequence, by len (dK/dV items)
+    int* off_q = sm + 4 * nseq;    // sequence -> first record
+    int* off_kv = sm + 5 * nseq;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < nseq; i += kSchedThreads) {
+        const int S = cu[i + 1] - cu[i];
+        const int e = kv_end != nullptr ? kv_end[i] : 0;
+        len[i] = S;
+        eff[i] = (e > 0 && e < S) ? e : S;
+    }
+    __syncthreads();
+    for (int i = tid; i < nseq; i += kSchedThreads) {
+        const int ei = eff[i], li = len[i];
+        int rq = 0, rkv = 0;
+        for (int j = 0; j < nseq; ++j) {
+            const int ej = eff[j], lj = len[j];
+            rq += (ej > ei || (ej == ei && j < i)) ? 1 : 0;
+            rkv += (lj > li || (lj == li && j < i)) ? 1 : 0;
+        }
+        ord_q[rq] = i;
+        ord_kv[rkv] = i;
+    }
+    __syncthreads();
+    int* off_z = ord_q;            // sequence -> first record of its fully masked key tiles (reuses ord_q once consumed)
+    if (tid == 0) {
+        int nq = 0, nkv = 0;
+        for (int r = 0; r < nseq; ++r) {
+            const int iq = ord_q[r], ikv = ord_kv[r];
+            off_q[iq] = nq;
+            nq += nheads * ((len[iq] + 127) / 128);
+            off_kv[ikv] = nkv;
+            nkv += nheads * ((eff[ikv] + 127) / 128);
+        }
+        int nz = nkv;              // key tiles behind kv_end: dK = dV = 0, the kernel only stores zeros — they go last
+        for (int i = 0; i < nseq; ++i) {
+            off_z[i] = nz;
+            nz += nheads * ((len[i] + 127) / 128 - (eff[i] + 127) / 128);
+        }
+        work[0] = make_int4(nq, nz, cap, nkv);
+    }
+    __syncthreads();
+    // records: (head, tile) in index order within a sequence, so that the CTAs working side by side share K / V in L2
+    for (int i = tid; i < nseq; i += kSchedThreads) {
+        const int row0 = cu[i], S = len[i], e = eff[i];
+        const int tq = (S + 127) / 128, tkv = (e + 127) / 128;
+        int4* wq = work + 1 + off_q[i];
+        int4* wkv = work + 1 + cap + off_kv[i];
+        int4* wz = work + 1 + cap + off_z[i];
+        for (int h = 0; h < nheads; ++h) {
+            for (int t = 0; t < tq; ++t) wq[h * tq + t] = make_int4(row0, S, e, (h << 16) | t);
+            for (int t = 0; t < tkv; ++t) wkv[h * tkv + t] = make_int4(row0, S, e, (h << 16) | t);
+            for (int t = tkv; t < tq; ++t) wz[h * (tq - tkv) + t - tkv] = make_int4(row0, S, e, (h << 16) | t);
+        }
+    }
+}
+
 static int check_args(const mmb_attn_args* a) {
     MMB_REQUIRE(a && a->qkv && a->keybias && a->cu_seqlens, "attn: null pointer");
     MMB_REQUIRE(a->H > 0 && a->nheads > 0 && a->H == a->nheads * kD, "attn: head dim must be 64 (H=%d heads=%d)", a->H,
                 a->nheads);
     MMB_REQUIRE(a->nseq > 0 && a->max_seqlen > 0 && a->total_rows > 0, "attn: empty batch");
     MMB_REQUIRE(a->p_drop >= 0.f && a->p_drop < 1.f, "attn: p_drop=%f out of range", (double)a->p_drop);
+    MMB_REQUIRE(((uintptr_t)a->work % 16) == 0, "attn: work lists must be 16-byte aligned");
     return MMB_OK;
 }
 
@@ -81,6 +150,27 @@ using namespace mmb;
 extern "C" size_t mmb_attn_bwd_workspace_bytes(int total_rows, int nheads) {
     if (total_rows <= 0 || nheads <= 0) return 0;
     return 2 * (size_t)nheads * (size_t)total_rows * 16;
+}
+
+extern "C" size_t mmb_attn_schedule_bytes(int nseq, int nheads, int max_seqlen) {
+    if (nseq <= 0 || nheads <= 0 || max_seqlen <= 0) return 0;
+    const size_t cap = (size_t)nseq * (size_t)nheads * (size_t)((max_seqlen + 127) / 128);
+    return (1 + 2 * cap) * 16;
+}
+
+extern "C" int mmb_attn_schedule(const mmb_attn_schedule_args* a, void* stream) {
+    MMB_REQUIRE(a && a->cu_seqlens && a->work, "attn_schedule: null pointer");
+    MMB_REQUIRE(a->nseq > 0 && a->nseq <= kSchedMaxSeqs, "attn_schedule: nseq=%d not in [1, %d]", a->nseq, kSchedMaxSeqs);
+    MMB_REQUIRE(a->nheads > 0 && a->nheads < 32768 && a->max_seqlen > 0, "attn_schedule: bad nheads / max_seqlen");
+    MMB_REQUIRE(((uintptr_t)a->work % 16) == 0, "attn_schedule: work must be 16-byte aligned");
+    const size_t cap = (size_t)a->nseq * (size_t)a->nheads * (size_t)((a->max_seqlen + 127) / 128);
+    MMB_REQUIRE(cap < (1u << 30), "attn_schedule: too many work items");
+    const int smem = 6 * a->nseq * (int)sizeof(int);
+    if (smem > 48 * 1024)
+        MMB_CUDA(cudaFuncSetAttribute(attn_schedule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attn_schedule_kernel<<<1, kSchedThreads, smem, (cudaStream_t)stream>>>(a->cu_seqlens, a->kv_end, (int4*)a->work,
+                                                                           a->nseq, a->nheads, (int)cap);
+    return check_launch("attn_schedule_kernel");
 }
 
 extern "C" int mmb_attn_fwd(const mmb_attn_args* a, void* stream) {

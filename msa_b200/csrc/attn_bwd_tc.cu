@@ -78,6 +78,7 @@ struct BwdTcParams {
     __nv_bfloat16* dqkv;
     const int* cu_seqlens;
     const int* kv_end;
+    const int4* work;          // mmb_attn_schedule's lists or null (items in index order)
     int H, nheads, nseq, tiles, total_rows;
     float scale_log2, scale;
     uint32_t thresh32;
@@ -131,35 +132,50 @@ __device__ __forceinline__ void mma_tmn(uint32_t tmem_d, uint32_t tA, uint32_t s
 #endif
 
 struct Item {
-    int seq, head, tile, row0, S, nsteps;   // nsteps == 0: nothing to run (invalid tile, or a fully masked key tile)
+    int head, tile, row0, S, nsteps;        // nsteps == 0: nothing to run (invalid tile, or a fully masked key tile)
     bool valid;
 };
-// Work-item metadata is fetched one item ahead: fetch_item only ISSUES the global loads (nothing depends on them until
+// Work-item metadata is fetched one item ahead: fetch_item only ISSUES the loads (nothing depends on them until
 // make_item runs at the top of the next iteration), so their latency hides under the current item's steps.
+// Items come either from mmb_attn_schedule's list (wl != null: one 16-byte record {first row, length, effective keys,
+// head << 16 | tile} per item, longest first) or, in index order, from (sequence, head, tile) = decode(idx).
 struct ItemRaw {
-    int idx, row0, row1, kvend;
+    int idx, row0, row1, kvend, ht;
 };
-__device__ __forceinline__ ItemRaw fetch_item(const BwdTcParams& p, const int* cu, const int* kvend, int idx, int total) {
+__device__ __forceinline__ ItemRaw fetch_item(const BwdTcParams& p, const int4* wl, const int* cu, const int* kvend,
+                                              int idx, int total) {
     ItemRaw r;
     r.idx = idx;
-    r.row0 = r.row1 = r.kvend = 0;
+    r.row0 = r.row1 = r.kvend = r.ht = 0;
     if (idx < total) {
-        const int seq = idx / (p.tiles * p.nheads);
-        r.row0 = cu[seq];
-        r.row1 = cu[seq + 1];
-        if (kvend != nullptr) r.kvend = kvend[seq];
+        if (wl != nullptr) {
+            const int4 w = __ldg(wl + idx);
+            r.row0 = w.x;
+            r.row1 = w.y;       // the length, not the end row
+            r.kvend = w.z;
+            r.ht = w.w;
+        } else {
+            const int seq = idx / (p.tiles * p.nheads);
+            r.row0 = cu[seq];
+            r.row1 = cu[seq + 1];
+            if (kvend != nullptr) r.kvend = kvend[seq];
+        }
     }
     return r;
 }
 template <bool kIsDq>
-__device__ __forceinline__ Item make_item(const BwdTcParams& p, const ItemRaw& r, int total) {
+__device__ __forceinline__ Item make_item(const BwdTcParams& p, const ItemRaw& r, int total, bool listed) {
     Item it;
-    it.tile = r.idx % p.tiles;
-    const int sh = r.idx / p.tiles;
-    it.head = sh % p.nheads;
-    it.seq = sh / p.nheads;
+    if (listed) {
+        it.tile = r.ht & 0xffff;
+        it.head = r.ht >> 16;
+        it.S = r.row1;
+    } else {
+        it.tile = r.idx % p.tiles;
+        it.head = (r.idx / p.tiles) % p.nheads;
+        it.S = r.row1 - r.row0;
+    }
     it.row0 = r.row0;
-    it.S = r.row1 - r.row0;
     it.valid = r.idx < total && it.tile * kRows < it.S;
     int eff = it.S;                         // keys at index >= eff are all masked: P == 0 exactly (see mmb_attn_args)
     if (r.kvend > 0 && r.kvend < it.S) eff = r.kvend;
@@ -270,7 +286,14 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = lds32_b(tmem_slot);
-    const int total_items = p.tiles * p.nheads * p.nseq;
+    int total_items = p.tiles * p.nheads * p.nseq;
+    const int4* wl = nullptr;
+    if (p.work != nullptr) {
+        const int4 hdr = __ldg(p.work);                      // {items of the forward / dQ list, of the dK/dV list, capacity}
+        total_items = kIsDq ? hdr.x : hdr.y;
+        wl = p.work + 1 + (kIsDq ? 0 : hdr.z);
+    }
+    const bool listed = wl != nullptr;
     const int stride = gridDim.x;
     // TMEM columns: scores slot s at s * 128 (S | dP), accumulators from 256
     constexpr int kAccCols = kIsDq ? 64 : 128;
@@ -280,10 +303,10 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
         // per-row records (attn.cu): planes [0, nh) = Rq {-LSE, -D, row dropout key}, [nh, 2 nh) = Rk {bias, column key};
         // the dQ pass wants Rq for its rows and Rk for its columns, the dKV pass the other way round
         uint32_t g = 0, n = 0;
-        ItemRaw raw = fetch_item(p, m_cu, m_kv, blockIdx.x, total_items);
+        ItemRaw raw = fetch_item(p, wl, m_cu, m_kv, blockIdx.x, total_items);
         for (int idx = blockIdx.x; idx < total_items; idx += stride) {
-            const Item cur = make_item<kIsDq>(p, raw, total_items);
-            raw = fetch_item(p, m_cu, m_kv, idx + stride, total_items);
+            const Item cur = make_item<kIsDq>(p, raw, total_items, listed);
+            raw = fetch_item(p, wl, m_cu, m_kv, idx + stride, total_items);
             if (cur.nsteps == 0) continue;
             const int rb = n & 1;
             const int col_q = cur.head * kHd, col_k = p.H + cur.head * kHd, col_v = 2 * p.H + cur.head * kHd;
@@ -330,10 +353,10 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
     } else if (warp == kScoreWarp) {
         // ================================================================ score MMAs: S = A0 B0^T, dP = A1 B1^T
         uint32_t g = 0, n = 0;
-        ItemRaw raw = fetch_item(p, m_cu, m_kv, blockIdx.x, total_items);
+        ItemRaw raw = fetch_item(p, wl, m_cu, m_kv, blockIdx.x, total_items);
         for (int idx = blockIdx.x; idx < total_items; idx += stride) {
-            const Item cur = make_item<kIsDq>(p, raw, total_items);
-            raw = fetch_item(p, m_cu, m_kv, idx + stride, total_items);
+            const Item cur = make_item<kIsDq>(p, raw, total_items, listed);
+            raw = fetch_item(p, wl, m_cu, m_kv, idx + stride, total_items);
             if (cur.nsteps == 0) continue;
             const int rb = n & 1;
             ptx::mbar_wait(bar(B_ROW_FULL + rb), (n >> 1) & 1);
@@ -359,10 +382,10 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
     } else if (warp == kAccWarp) {
         // ================================================================ accumulating MMAs
         uint32_t g = 0, n = 0;
-        ItemRaw raw = fetch_item(p, m_cu, m_kv, blockIdx.x, total_items);
+        ItemRaw raw = fetch_item(p, wl, m_cu, m_kv, blockIdx.x, total_items);
         for (int idx = blockIdx.x; idx < total_items; idx += stride) {
-            const Item cur = make_item<kIsDq>(p, raw, total_items);
-            raw = fetch_item(p, m_cu, m_kv, idx + stride, total_items);
+            const Item cur = make_item<kIsDq>(p, raw, total_items, listed);
+            raw = fetch_item(p, wl, m_cu, m_kv, idx + stride, total_items);
             if (cur.nsteps == 0) continue;
             const int a = n & 1;
             ptx::mbar_wait(bar(B_ACC_EMPTY + a), ((n >> 1) & 1) ^ 1);
@@ -460,10 +483,10 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
             }
             pend = false;
         };
-        ItemRaw raw = fetch_item(p, m_cu, m_kv, blockIdx.x, total_items);
+        ItemRaw raw = fetch_item(p, wl, m_cu, m_kv, blockIdx.x, total_items);
         for (int idx = blockIdx.x; idx < total_items; idx += stride) {
-            const Item cur = make_item<kIsDq>(p, raw, total_items);
-            raw = fetch_item(p, m_cu, m_kv, idx + stride, total_items);
+            const Item cur = make_item<kIsDq>(p, raw, total_items, listed);
+            raw = fetch_item(p, wl, m_cu, m_kv, idx + stride, total_items);
             if (!cur.valid) continue;
             const int rr = cur.tile * kRows + r;        // this thread's query (dQ pass) / key (dKV pass)
             if (cur.nsteps == 0) {
@@ -572,6 +595,7 @@ int launch_attn_bwd_tc(const mmb_attn_args* a, cudaStream_t stream) {
     p.dqkv = (__nv_bfloat16*)a->dqkv;
     p.cu_seqlens = a->cu_seqlens;
     p.kv_end = a->kv_end;
+    p.work = (const int4*)a->work;
     p.H = a->H;
     p.nheads = a->nheads;
     p.nseq = a->nseq;

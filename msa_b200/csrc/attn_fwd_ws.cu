@@ -55,6 +55,7 @@ struct FwParams {
     const float* keybias;
     const int* cu_seqlens;
     const int* kv_end;
+    const int4* work;          // mmb_attn_schedule's lists or null (items in index order)
     int H, nheads, nseq, tiles, total_rows;
     float scale_log2;
     uint32_t thresh32;
@@ -102,26 +103,42 @@ __device__ __forceinline__ void mma_pv(uint32_t tmem_d, uint32_t tA, uint32_t sB
 }
 
 struct Item {
-    int seq, head, tile, row0, S, nsteps;
+    int head, tile, row0, S, nsteps;
     bool valid;
 };
-__device__ __forceinline__ Item make_item(const FwParams& p, const int* cu, const int* kvend, int idx, int total) {
+// Items come either from mmb_attn_schedule's list (wl != null: one 16-byte record {first row, length, effective keys,
+// head << 16 | tile} per item, longest first; the record of the NEXT item is loaded while the current one runs) or, in
+// index order, from (sequence, head, tile) = decode(idx) and the sequence metadata in shared memory.
+__device__ __forceinline__ int4 fetch_work(const int4* wl, int idx, int total) {
+    return (wl != nullptr && idx < total) ? __ldg(wl + idx) : make_int4(0, 0, 0, 0);
+}
+__device__ __forceinline__ Item make_item(const FwParams& p, const int* cu, const int* kvend, int idx, int total,
+                                          const int4* wl, const int4& w) {
     Item it;
-    it.tile = idx % p.tiles;
-    const int sh = idx / p.tiles;
-    it.head = sh % p.nheads;
-    it.seq = sh / p.nheads;
-    it.row0 = it.S = it.nsteps = 0;
+    it.tile = it.head = it.row0 = it.S = it.nsteps = 0;
     it.valid = false;
     if (idx >= total) return it;
-    it.row0 = cu[it.seq];
-    it.S = cu[it.seq + 1] - it.row0;
-    it.valid = it.tile * kRows < it.S;
-    int eff = it.S;                         // keys at index >= eff are all masked: P == 0 exactly (see mmb_attn_args)
-    if (kvend != nullptr) {
-        const int e = kvend[it.seq];
-        if (e > 0 && e < it.S) eff = e;
+    int eff;                                // keys at index >= eff are all masked: P == 0 exactly (see mmb_attn_args)
+    if (wl != nullptr) {
+        it.tile = w.w & 0xffff;
+        it.head = w.w >> 16;
+        it.row0 = w.x;
+        it.S = w.y;
+        eff = w.z;
+    } else {
+        it.tile = idx % p.tiles;
+        const int sh = idx / p.tiles;
+        it.head = sh % p.nheads;
+        const int seq = sh / p.nheads;
+        it.row0 = cu[seq];
+        it.S = cu[seq + 1] - it.row0;
+        eff = it.S;
+        if (kvend != nullptr) {
+            const int e = kvend[seq];
+            if (e > 0 && e < it.S) eff = e;
+        }
     }
+    it.valid = it.tile * kRows < it.S;
     it.nsteps = it.valid ? (eff + kStep - 1) / kStep : 0;
     return it;
 }
@@ -172,15 +189,22 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = lds32(tmem_slot);
-    const int total_items = p.tiles * p.nheads * p.nseq;
+    int total_items = p.tiles * p.nheads * p.nseq;
+    const int4* wl = nullptr;
+    if (p.work != nullptr) {
+        total_items = __ldg(p.work).x;                       // header {items of this list, of the dK/dV list, capacity}
+        wl = p.work + 1;
+    }
     const int stride = gridDim.x;
     // TMEM columns: score slot s at s * 64, O accumulator a at 128 + a * 64
 
     if (warp == kProducerWarp) {
         // ================================================================ producer
         uint32_t g = 0, n = 0;
+        int4 wnext = fetch_work(wl, blockIdx.x, total_items);
         for (int idx = blockIdx.x; idx < total_items; idx += stride) {
-            const Item cur = make_item(p, m_cu, m_kv, idx, total_items);
+            const Item cur = make_item(p, m_cu, m_kv, idx, total_items, wl, wnext);
+            wnext = fetch_work(wl, idx + stride, total_items);
             if (cur.nsteps == 0) continue;
             const int rb = n & 1;
             const int col_q = cur.head * kHd, col_k = p.H + cur.head * kHd, col_v = 2 * p.H + cur.head * kHd;
@@ -228,8 +252,10 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
     } else if (warp == kScoreWarp) {
         // ================================================================ score MMAs
         uint32_t g = 0, n = 0;
+        int4 wnext = fetch_work(wl, blockIdx.x, total_items);
         for (int idx = blockIdx.x; idx < total_items; idx += stride) {
-            const Item cur = make_item(p, m_cu, m_kv, idx, total_items);
+            const Item cur = make_item(p, m_cu, m_kv, idx, total_items, wl, wnext);
+            wnext = fetch_work(wl, idx + stride, total_items);
             if (cur.nsteps == 0) continue;
             const int rb = n & 1;
             ptx::mbar_wait(bar(B_ROW_FULL + rb), (n >> 1) & 1);
@@ -250,8 +276,10 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
     } else if (warp == kAccWarp) {
         // ================================================================ O += P V
         uint32_t g = 0, n = 0;
+        int4 wnext = fetch_work(wl, blockIdx.x, total_items);
         for (int idx = blockIdx.x; idx < total_items; idx += stride) {
-            const Item cur = make_item(p, m_cu, m_kv, idx, total_items);
+            const Item cur = make_item(p, m_cu, m_kv, idx, total_items, wl, wnext);
+            wnext = fetch_work(wl, idx + stride, total_items);
             if (cur.nsteps == 0) continue;
             const int a = n & 1;
             ptx::mbar_wait(bar(B_ACC_EMPTY + a), ((n >> 1) & 1) ^ 1);
@@ -325,8 +353,10 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
             }
             pend = false;
         };
+        int4 wnext = fetch_work(wl, blockIdx.x, total_items);
         for (int idx = blockIdx.x; idx < total_items; idx += stride) {
-            const Item cur = make_item(p, m_cu, m_kv, idx, total_items);
+            const Item cur = make_item(p, m_cu, m_kv, idx, total_items, wl, wnext);
+            wnext = fetch_work(wl, idx + stride, total_items);
             if (cur.nsteps == 0) continue;
             const int a = n & 1;
             const uint32_t prob_base = (uint32_t)cur.head * (uint32_t)p.total_rows + (uint32_t)cur.row0;
@@ -456,6 +486,7 @@ int launch_attn_fwd_ws(const mmb_attn_args* a, cudaStream_t stream) {
     p.keybias = a->keybias;
     p.cu_seqlens = a->cu_seqlens;
     p.kv_end = a->kv_end;
+    p.work = (const int4*)a->work;
     p.H = a->H;
     p.nheads = a->nheads;
     p.nseq = a->nseq;

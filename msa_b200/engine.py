@@ -10,6 +10,7 @@ torch is used for device memory (``torch.empty``) and the stream handle only.
 """
 import ctypes
 import math
+import os
 
 import torch
 
@@ -69,6 +70,11 @@ class Plan:
         self.keybias, self.cu = buf(M, dtype=F32), buf(3 * B + 1, dtype=I32)
         self.label_count = buf(4, dtype=I32)
         self.kv_end = buf(3 * B, dtype=I32)     # per sequence: 1 + last unmasked key (attention skips the masked tail)
+        # work lists of the persistent attention kernels (longest items first), rebuilt on the device for every batch
+        # and shared by all layers; MMB_ATTN_SCHED=0 leaves the items in index order (A/B runs)
+        self.attn_work = None
+        if os.environ.get("MMB_ATTN_SCHED", "1") != "0" and 3 * B <= 8192:
+            self.attn_work = capi.attn_schedule_buffer(3 * B, self.nh, self.max_S, dev)
         # ---- activations (kept for backward when training; one reused set in eval)
         nsets = N if training else 1
         self.x = [buf(M, H) for _ in range(N + 1)] if training else [buf(M, H), buf(M, H)]
@@ -135,6 +141,9 @@ class Plan:
                                    label_count=self.label_count, kv_end=self.kv_end, B=self.B, T=self.T, L=[self.Lv, self.La],
                                    frame_dim=[self.Dv, self.Da])
         f.append((self._fn("pack_prepare"), self.pack_args))
+        if self.attn_work is not None:
+            self.sched_args = capi.attn_schedule_args(self.cu, self.kv_end, self.attn_work, self.nh, self.max_S)
+            f.append((self._fn("attn_schedule"), self.sched_args))
         je = "bert.jointEmbeddings."
         self.embed_args = capi.fill(
             capi.EmbedArgs(), frame_dim=[self.Dv, self.Da],
@@ -169,7 +178,7 @@ class Plan:
             bqkv = st.span(pre + "attention.self.query.bias", pre + "attention.self.value.bias")
             self._gemm(f, xin, wqkv, L["qkv"], M, 3 * H, H, bias=bqkv)
             a = capi.attn_args(L["qkv"], L["ctx"], L["lse"], self.keybias, self.cu, H, self.nh, self.max_S,
-                               p_drop=self.p_attn, rng_stream=(l << 8) | ST_ATTN, kv_end=self.kv_end)
+                               p_drop=self.p_attn, rng_stream=(l << 8) | ST_ATTN, kv_end=self.kv_end, work=self.attn_work)
             L["attn_args"] = a
             self._seeded.append(a)
             f.append((self._fn("attn_fwd"), a))

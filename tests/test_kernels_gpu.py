@@ -311,3 +311,81 @@ def test_attention_masked_tail_skipping_is_exact():
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
     assert torch.equal(res[0][2], res[1][2])
     assert float(res[1][2][131:550, H:].abs().max()) == 0.0        # dK, dV of masked keys
+
+
+def _expected_work_lists(lens, kv_end, nh):
+    """Restates the record layout documented at mmb_attn_schedule (include/mmbert_sm100.h)."""
+    n = len(lens)
+    cu = [0]
+    for s in lens:
+        cu.append(cu[-1] + s)
+    eff = [(e if 0 < e < s else s) for s, e in zip(lens, kv_end)]
+    tq = [(s + 127) // 128 for s in lens]
+    tkv = [(e + 127) // 128 for e in eff]
+    rec = lambda i, h, t: [cu[i], lens[i], eff[i], (h << 16) | t]
+    q = [rec(i, h, t) for i in sorted(range(n), key=lambda i: (-eff[i], i)) for h in range(nh) for t in range(tq[i])]
+    kv = [rec(i, h, t) for i in sorted(range(n), key=lambda i: (-lens[i], i)) for h in range(nh) for t in range(tkv[i])]
+    z = [rec(i, h, t) for i in range(n) for h in range(nh) for t in range(tkv[i], tq[i])]
+    return q, kv, z
+
+
+@pytest.mark.parametrize("with_kv_end", [False, True])
+def test_attention_schedule_lists(with_kv_end):
+    from msa_b200 import capi
+    g = torch.Generator().manual_seed(3)
+    lens = torch.randint(1, 551, (70,), generator=g).tolist() + [550, 550, 128, 129, 1]
+    kv = [int(torch.randint(0, s + 40, (1,), generator=g)) for s in lens] if with_kv_end else [0] * len(lens)
+    nh, max_s = 3, max(lens)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), device="cuda", dtype=torch.int32)
+    kv_t = torch.tensor(kv, device="cuda", dtype=torch.int32) if with_kv_end else None
+    work = capi.attn_schedule_buffer(len(lens), nh, max_s, "cuda")
+    work.fill_(-1)
+    capi.call("attn_schedule", capi.attn_schedule_args(cu, kv_t, work, nh, max_s))
+    w = work.cpu().tolist()
+    q, kvl, z = _expected_work_lists(lens, kv, nh)
+    cap = len(lens) * nh * ((max_s + 127) // 128)
+    assert w[0] == [len(q), len(kvl) + len(z), cap, len(kvl)]
+    assert w[1:1 + len(q)] == q
+    assert w[1 + cap:1 + cap + len(kvl)] == kvl
+    assert w[1 + cap + len(kvl):1 + cap + len(kvl) + len(z)] == z
+    steps = [(r[2] + 63) // 64 for r in q]
+    assert steps == sorted(steps, reverse=True)          # longest items first
+
+
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_attention_with_work_lists_is_bit_identical(p_drop):
+    """The work lists only change WHICH CTA runs an item and when: context, LSE and all three gradients must not
+    change by a bit (masked tails, fully masked key tiles and a fully masked sequence included)."""
+    from msa_b200 import capi
+    g = torch.Generator().manual_seed(8)
+    nh = 12
+    lens = torch.randint(1, 551, (37,), generator=g).tolist() + [550, 40, 300]
+    valid = [int(torch.randint(1, s + 1, (1,), generator=g)) for s in lens[:-3]] + [131, 0, 300]
+    H, rows = nh * 64, sum(lens)
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    torch.manual_seed(9)
+    qkv = _bf(torch.randn(rows, 3 * H, device="cuda"))
+    keybias = torch.zeros(rows, device="cuda")
+    for i, (s, v) in enumerate(zip(lens, valid)):
+        keybias[cu[i] + v:cu[i] + s] = -10000.0
+    kv_end = torch.tensor(valid, device="cuda", dtype=torch.int32)
+    cu_t = torch.tensor(cu, device="cuda", dtype=torch.int32)
+    dctx = _bf(torch.randn(rows, H, device="cuda"))
+    work = capi.attn_schedule_buffer(len(lens), nh, max(lens), "cuda")
+    capi.call("attn_schedule", capi.attn_schedule_args(cu_t, kv_end, work, nh, max(lens)))
+    res = []
+    for wl in (None, work):
+        ctx = torch.zeros(rows, H, device="cuda", dtype=torch.bfloat16)
+        lse = torch.zeros(nh, rows, device="cuda")
+        dqkv = torch.full((rows, 3 * H), 7.0, device="cuda", dtype=torch.bfloat16)
+        bwd_ws = capi.attn_bwd_workspace(rows, nh, "cuda")
+        a = capi.attn_args(qkv, ctx, lse, keybias, cu_t, H, nh, max(lens), dctx=dctx, dqkv=dqkv, bwd_ws=bwd_ws,
+                           kv_end=kv_end, p_drop=p_drop, seed=4, rng_stream=1, work=wl)
+        capi.call("attn_fwd", a)
+        capi.call("attn_bwd", a)
+        res.append((ctx.float(), lse.clone(), dqkv.float()))
+    assert torch.isfinite(res[1][2]).all()
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert torch.equal(res[0][2], res[1][2])
