@@ -119,17 +119,16 @@ attn_schedule_kernel(const int* __restrict__ cu, const int* __restrict__ kv_end,
     }
     __syncthreads();
     // records: (head, tile) in index order within a sequence, so that the CTAs working side by side share K / V in L2
-    for (int i = tid; i < nseq; i += kSchedThreads) {
+    for (int ih = tid; ih < nseq * nheads; ih += kSchedThreads) {      // one thread per (sequence, head)
+        const int i = ih / nheads, h = ih - i * nheads;
         const int row0 = cu[i], S = len[i], e = eff[i];
         const int tq = (S + 127) / 128, tkv = (e + 127) / 128;
-        int4* wq = work + 1 + off_q[i];
-        int4* wkv = work + 1 + cap + off_kv[i];
-        int4* wz = work + 1 + cap + off_z[i];
-        for (int h = 0; h < nheads; ++h) {
-            for (int t = 0; t < tq; ++t) wq[h * tq + t] = make_int4(row0, S, e, (h << 16) | t);
-            for (int t = 0; t < tkv; ++t) wkv[h * tkv + t] = make_int4(row0, S, e, (h << 16) | t);
-            for (int t = tkv; t < tq; ++t) wz[h * (tq - tkv) + t - tkv] = make_int4(row0, S, e, (h << 16) | t);
-        }
+        int4* wq = work + 1 + off_q[i] + h * tq;
+        int4* wkv = work + 1 + cap + off_kv[i] + h * tkv;
+        int4* wz = work + 1 + cap + off_z[i] + h * (tq - tkv);
+        for (int t = 0; t < tq; ++t) wq[t] = make_int4(row0, S, e, (h << 16) | t);
+        for (int t = 0; t < tkv; ++t) wkv[t] = make_int4(row0, S, e, (h << 16) | t);
+        for (int t = tkv; t < tq; ++t) wz[t - tkv] = make_int4(row0, S, e, (h << 16) | t);
     }
 }
 

@@ -10,6 +10,10 @@ every step removed:
   launch per id tensor (``msa_b200.data.mask_tokens``);
 * pageable, blocking host->device copies (trainer.py:49-64) — pinned buffers and ``non_blocking`` copies.
 
+``DevicePrefetcher`` (double-buffered host->device copies on a copy stream) and ``DeferredScalars`` (per-step loss
+read-back that arrives a step late instead of stalling the launch queue) are the building blocks for loops that still want
+a loss value on the host every step; ``bench.py`` times its end-to-end number through them.
+
 What is deliberately kept: the optimizer stepping rule ``(step + 1) & args.gradient_accumulation_step == 0``
 (trainer.py:96 — a bitwise AND, so with the default 1 the optimizer steps on every second batch) unless
 ``faithful_stepping=False`` selects the usual modulo rule; and the returned tuple, including the reference's quirk that
@@ -19,6 +23,131 @@ import torch
 from torch.utils.data import DataLoader, RandomSampler
 
 from . import data
+
+
+def _tree_leaves(obj, out):
+    if torch.is_tensor(obj):
+        out.append(obj)
+    elif isinstance(obj, (tuple, list)):
+        for o in obj:
+            _tree_leaves(o, out)
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            _tree_leaves(v, out)
+    return out
+
+
+def _tree_like(obj, fn):
+    if torch.is_tensor(obj):
+        return fn(obj)
+    if isinstance(obj, (tuple, list)):
+        return tuple(_tree_like(o, fn) for o in obj)
+    if isinstance(obj, dict):
+        return {k: _tree_like(v, fn) for k, v in obj.items()}
+    return obj
+
+
+class DevicePrefetcher:
+    """Iterates host batches (nested tuples / dicts of CPU tensors, ideally pinned) as device batches.
+
+    The host->device copy of batch i+1 runs on a copy stream while batch i computes, into one of two fixed sets of
+    device buffers (no allocation per step).  A buffer set is overwritten only after the work that was enqueued on the
+    consumer's stream while it was the current batch has finished (event recorded when the consumer asks for the next
+    batch), so the consumer may use a yielded batch until it calls ``next`` again — not longer.
+    Replaces the blocking per-tensor ``.to(DEVICE)`` calls of trainer.py:49-72.
+    """
+
+    def __init__(self, batches, device):
+        self.batches = batches
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("DevicePrefetcher copies to a CUDA device")
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self._slots = [None, None]      # device trees
+        self._sig = [None, None]        # (shape, dtype) signature of each slot
+        self._free = [None, None]       # event on the consumer stream: the slot may be overwritten after it
+
+    def _slot_for(self, s, host_batch, main):
+        sig = tuple((tuple(t.shape), t.dtype) for t in _tree_leaves(host_batch, []))
+        if self._sig[s] != sig:         # first use, or a batch of another shape (the last, short one)
+            self._slots[s] = _tree_like(host_batch, lambda t: torch.empty(t.shape, dtype=t.dtype, device=self.device))
+            for t in _tree_leaves(self._slots[s], []):
+                t.record_stream(self.copy_stream)
+            self._sig[s] = sig
+            ev = torch.cuda.Event()     # memory handed out by the allocator is only ordered on the consumer's stream
+            ev.record(main)
+            self._free[s] = ev
+        return self._slots[s]
+
+    def _launch(self, i, host_batch, main):
+        s = i % 2
+        dst = self._slot_for(s, host_batch, main)
+        self.copy_stream.wait_event(self._free[s])
+        with torch.cuda.stream(self.copy_stream):
+            for d, h in zip(_tree_leaves(dst, []), _tree_leaves(host_batch, [])):
+                d.copy_(h, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self.copy_stream)
+        return dst, ready
+
+    def __iter__(self):
+        main = torch.cuda.current_stream(self.device)
+        it = iter(self.batches)
+        try:
+            pending = self._launch(0, next(it), main)
+        except StopIteration:
+            return
+        i = 0
+        while pending is not None:
+            cur, ready = pending
+            try:
+                pending = self._launch(i + 1, next(it), main)
+            except StopIteration:
+                pending = None
+            main.wait_event(ready)
+            yield cur
+            done = torch.cuda.Event()   # everything the consumer enqueued for this batch
+            done.record(main)
+            self._free[i % 2] = done
+            i += 1
+
+
+class DeferredScalars:
+    """Per-step read-back of a device scalar (the loss) that does not drain the launch queue: ``push`` starts an
+    asynchronous copy into pinned memory and returns the value pushed ``depth`` calls earlier (None at first), which has
+    long arrived; ``flush`` returns the rest.  Every value still reaches the host — ``depth`` steps late — so the host
+    runs at most ``depth`` steps ahead of the device.  Replaces the ``.item()`` calls of trainer.py:85,93."""
+
+    def __init__(self, device, depth=2):
+        self.device = torch.device(device)
+        self.depth = depth
+        self._host = torch.empty(depth, dtype=torch.float32).pin_memory() if self.device.type == "cuda" else \
+            torch.empty(depth, dtype=torch.float32)
+        self._events = [None] * depth
+        self._n = 0
+
+    def _take(self, slot):
+        if self._events[slot] is not None:
+            self._events[slot].synchronize()
+        return float(self._host[slot])
+
+    def push(self, value):
+        slot = self._n % self.depth
+        out = self._take(slot) if self._n >= self.depth else None
+        self._host[slot:slot + 1].copy_(value.detach().reshape(1).float(), non_blocking=True)
+        if self.device.type == "cuda":
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._events[slot] = ev
+        self._n += 1
+        return out
+
+    def flush(self):
+        first = max(0, self._n - self.depth)
+        out = [self._take(k % self.depth) for k in range(first, self._n)]
+        self._events = [None] * self.depth
+        self._n = 0
+        return out
 
 
 def _to_dev(t, device):

@@ -122,3 +122,26 @@ def test_sync_free_train_epoch_on_the_cuda_model():
     assert all(isinstance(v, float) and v == v for v in (out[0], out[5]))
     assert torch.isfinite(out[4]).all()
     assert not torch.equal(w0, m.classifier1_1.weight.detach())
+
+
+def test_prefetcher_and_deferred_reads_deliver_every_batch_in_order():
+    """DevicePrefetcher reuses two device buffer sets while copies run ahead on a copy stream: with a slow consumer
+    every batch must still arrive intact and in order (a buffer overwritten early would show the next batch's values),
+    including a last batch of another shape; DeferredScalars must hand back one value per push, in order."""
+    from msa_b200.trainer_fast import DeferredScalars, DevicePrefetcher
+    batches = [{"a": (torch.full((1000, 257), float(i)).pin_memory(), (torch.arange(64) + i).pin_memory()),
+                "b": torch.tensor([i]).pin_memory()} for i in range(7)]
+    batches.append({"a": (torch.full((10, 257), 7.0), torch.arange(3) + 7), "b": torch.tensor([7])})   # short, pageable
+    want = [float(b["a"][0].sum() + b["a"][1].sum() + b["b"].sum()) for b in batches]
+    big = torch.randn(4096, 4096, device="cuda")
+    reader, got = DeferredScalars("cuda"), []
+    for dev in DevicePrefetcher(iter(batches), "cuda"):
+        assert dev["a"][0].is_cuda
+        for _ in range(6):
+            big @ big                     # keeps the consumer stream busy: the copies run ahead of it
+        v = reader.push(dev["a"][0].sum() + dev["a"][1].sum() + dev["b"].sum())
+        if v is not None:
+            got.append(v)
+    got += reader.flush()
+    assert got == want
+    assert list(DevicePrefetcher(iter([]), "cuda")) == []

@@ -76,3 +76,11 @@ def test_train_epoch_matches_the_reference_loop():
     trainer_fast.train_epoch(args, model2, data, opt2, _Opt(), None, collate_fn=_collate, device=torch.device("cpu"),
                              faithful_stepping=False)
     assert opt2.steps == 5
+
+
+def test_deferred_scalars_return_every_value_in_order():
+    from msa_b200.trainer_fast import DeferredScalars
+    r = DeferredScalars("cpu", depth=2)
+    got = [r.push(torch.tensor(float(i))) for i in range(5)]
+    assert got == [None, None, 0.0, 1.0, 2.0] and r.flush() == [3.0, 4.0]
+    assert r.push(torch.tensor(9.0)) is None and r.flush() == [9.0] and r.flush() == []
