@@ -13,7 +13,7 @@
 // (no swizzled stores, no generic->async proxy fence) — against B0 / B1 read in place as MN-major operands.
 //
 // One CTA per SM (all 512 TMEM columns, ~200 KB shared memory), 19 warps:
-//   warp 16   TMA producer: row operands (double-buffered across work items), step operands (8-stage ring), and the
+//   warp 16   TMA producer: row operands (double-buffered across work items), step operands (6-stage ring), and the
 //             per-row / per-column vectors (key bias, -LSE, -D, dropout keys: prepared by attn.cu's prep kernel) next
 //             to them — copies only, the producer computes nothing
 //   warp 17   score MMAs (one elected thread; warp-uniform control flow so descriptors live in uniform registers)
@@ -24,8 +24,9 @@
 //             decision — common.cuh: attn_keep)
 // Rings: scores 2 slots x (64 + 64) TMEM columns (a slot is free again when the accumulating MMAs that read it have
 // retired), accumulators 2 buffers (the epilogue of one work item runs one step into the next item).  The CTA walks
-// work items (sequence, head, 128-row tile) with a grid stride; every role evaluates the same item list, and all
-// ring positions are carried across items.
+// work items (sequence, head, 128-row tile) with a grid stride — in index order, or longest first through the work
+// lists of mmb_attn_schedule (attn.cu) when the caller passes them; every role evaluates the same item list, and
+// all ring positions are carried across items.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -71,6 +72,7 @@ template <bool kIsDq> constexpr int off_meta() { return off_stage<kIsDq>() + sta
 template <bool kIsDq> constexpr int off_bars() { return off_meta<kIsDq>() + kMetaBytes; }
 template <bool kIsDq> constexpr int smem_bytes() { return off_bars<kIsDq>() + 256 + 1024; }
 // barrier slots (8 bytes each)
+// (the step ring may grow to 8 stages without renumbering)
 enum { B_ROW_FULL = 0, B_ROW_EMPTY = 2, B_STEP_FULL = 4, B_STEP_EMPTY = 12, B_SC_FULL = 20, B_SC_EMPTY = 22,
        B_ST_FULL = 24, B_ACC_FULL = 26, B_ACC_EMPTY = 28, B_COUNT = 30 };
 
@@ -566,12 +568,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
 template <bool kIsDq, bool kDrop>
 int launch_pass(const CUtensorMap& q128, const CUtensorMap& q64, const CUtensorMap& dmap, const CUtensorMap& aux128,
                 const CUtensorMap& aux64, const BwdTcParams& p, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        MMB_CUDA(cudaFuncSetAttribute(attn_bwd_ws_kernel<kIsDq, kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      smem_bytes<kIsDq>()));
-        attr_set = true;
-    }
+    MMB_ENSURE_SMEM(smem_bytes<kIsDq>(), attn_bwd_ws_kernel<kIsDq, kDrop>);
     const int items = p.tiles * p.nheads * p.nseq;
     const int grid = items < num_sms() ? items : num_sms();
     attn_bwd_ws_kernel<kIsDq, kDrop><<<grid, kWsThreads, smem_bytes<kIsDq>(), stream>>>(q128, q64, dmap, aux128, aux64, p);

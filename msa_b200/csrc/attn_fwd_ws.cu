@@ -461,11 +461,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
 
 template <bool kDrop>
 int launch(const CUtensorMap& q128, const CUtensorMap& q64, const FwParams& p, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        MMB_CUDA(cudaFuncSetAttribute(attn_fwd_ws_kernel<kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwSmem));
-        attr_set = true;
-    }
+    MMB_ENSURE_SMEM(kFwSmem, attn_fwd_ws_kernel<kDrop>);
     const int items = p.tiles * p.nheads * p.nseq;
     const int grid = items < num_sms() ? items : num_sms();
     attn_fwd_ws_kernel<kDrop><<<grid, kFwThreads, kFwSmem, stream>>>(q128, q64, p);

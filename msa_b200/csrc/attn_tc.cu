@@ -346,11 +346,7 @@ int launch_attn_fwd_tc(const mmb_attn_args* a, cudaStream_t stream) {
     p.inv_keep = dropout_inv_keep(a->p_drop);
     p.seed = a->seed;
     p.rng_stream = a->rng_stream;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MMB_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
-        attr_set = true;
-    }
+    MMB_ENSURE_SMEM(kTcSmem, attn_fwd_tc_kernel);
     dim3 grid((a->max_seqlen + kTQ - 1) / kTQ, a->nheads, a->nseq);
     attn_fwd_tc_kernel<<<grid, kTcThreads, kTcSmem, stream>>>(tm, p);
     return check_launch("attn_fwd_tc_kernel");

@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "../../include/mmbert_sm100.h"
 
 namespace mmb {
@@ -33,6 +35,20 @@ int check_launch(const char* what, int kernels = 1);  // MMB_OK / MMB_ECUDA afte
     } while (0)
 
 int num_sms();
+
+// Opt-in to more than 48 KB of dynamic shared memory.  The attribute is per device and must be set before the first
+// launch there: one flag word per call site, bit = device ordinal (mod 64).  Two threads racing only repeat the call.
+#define MMB_ENSURE_SMEM(bytes, ...)                                                                                  \
+    do {                                                                                                             \
+        static std::atomic<unsigned long long> done__{0};                                                            \
+        int dev__ = 0;                                                                                               \
+        MMB_CUDA(cudaGetDevice(&dev__));                                                                             \
+        const unsigned long long bit__ = 1ull << (dev__ & 63);                                                       \
+        if (!(done__.load(std::memory_order_acquire) & bit__)) {                                                     \
+            MMB_CUDA(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));  \
+            done__.fetch_or(bit__, std::memory_order_release);                                                       \
+        }                                                                                                            \
+    } while (0)
 
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__

@@ -553,11 +553,7 @@ extern "C" int mmb_embed_fwd(const mmb_embed_args* a, void* stream) {
         const int nrows = p.d.B * L;
         const size_t smem = (size_t)kFrameRows * (p.frame_dim[mod] + 1 + p.H) * sizeof(float);
         MMB_DISPATCH_NCH(p.H, {
-            static bool attr_set = false;
-            if (!attr_set) {
-                MMB_CUDA(cudaFuncSetAttribute(embed_frame_fwd_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-                attr_set = true;
-            }
+            MMB_ENSURE_SMEM(160 * 1024, embed_frame_fwd_kernel<NCH>);
             embed_frame_fwd_kernel<NCH><<<(nrows + kFrameRows - 1) / kFrameRows, 256, smem, st>>>(p, mod);
         });
         rc = check_launch("embed_frame_fwd_kernel");
@@ -643,11 +639,7 @@ extern "C" int mmb_embed_bwd(const mmb_embed_args* a, void* stream) {
             if (D <= 96) {
                 frame_wgrad_kernel<24><<<g, 256, wsmem, st>>>(p, mod, rows_per_cta);
             } else {
-                static bool attr_set = false;
-                if (!attr_set) {
-                    MMB_CUDA(cudaFuncSetAttribute(frame_wgrad_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-                    attr_set = true;
-                }
+                MMB_ENSURE_SMEM(96 * 1024, frame_wgrad_kernel<96>);
                 frame_wgrad_kernel<96><<<g, 256, wsmem, st>>>(p, mod, rows_per_cta);
             }
             rc = check_launch("frame_wgrad_kernel");

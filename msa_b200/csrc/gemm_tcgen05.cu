@@ -836,12 +836,7 @@ static int launch_gemm(const mmb_gemm_args* a, cudaStream_t stream) {
     if (rc != MMB_OK) return rc;
     GemmParams p;
     fill_common(p, a, BM, BN);
-    static bool attr_set = false;
-    if (!attr_set) {
-        MMB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      Cfg::kSmemBytes));
-        attr_set = true;
-    }
+    MMB_ENSURE_SMEM(Cfg::kSmemBytes, gemm_tcgen05_kernel<BN>);
     const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
     gemm_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
     return check_launch("gemm_tcgen05_kernel");
@@ -889,14 +884,8 @@ static int launch_gemm_2cta(const mmb_gemm_args* a, cudaStream_t stream) {
     if (rc != MMB_OK) return rc;
     GemmParams p;
     fill_common(p, a, 256, 256);
-    static bool attr_set = false;
-    if (!attr_set) {
-        MMB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      Cfg2<8>::kSmemBytes));
-        MMB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      Cfg2<16>::kSmemBytes));
-        attr_set = true;
-    }
+    MMB_ENSURE_SMEM(Cfg2<8>::kSmemBytes, gemm_tcgen05_2cta_kernel<8>);
+    MMB_ENSURE_SMEM(Cfg2<16>::kSmemBytes, gemm_tcgen05_2cta_kernel<16>);
     const int pairs = num_sms() / 2;
     const int clusters = p.total_tiles < pairs ? p.total_tiles : pairs;
     // GELU epilogues are long latency chains: 16 epilogue warps; everything else: 8 (dbg bit 6 flips the choice, for A/B runs)

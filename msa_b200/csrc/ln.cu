@@ -255,11 +255,7 @@ extern "C" int mmb_dropout_residual_ln_bwd(const mmb_drln_bwd_args* a, void* str
     const int grid = min((a->M + kLnWarps - 1) / kLnWarps, num_sms() * 2);
     const size_t smem = (size_t)kLnWarps * 3 * a->H * sizeof(float);
     MMB_DISPATCH_NCH(a->H, {
-        static bool attr_set = false;
-        if (!attr_set) {
-            MMB_CUDA(cudaFuncSetAttribute(drln_bwd_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            attr_set = true;
-        }
+        MMB_ENSURE_SMEM(100 * 1024, drln_bwd_kernel<NCH>);
     });
     MMB_DISPATCH_NCH(a->H, (drln_bwd_kernel<NCH><<<grid, kLnWarps * 32, smem, (cudaStream_t)stream>>>(
                                (const __nv_bfloat16*)a->g1, a->g2, (const __nv_bfloat16*)a->y,
