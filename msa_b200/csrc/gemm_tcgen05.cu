@@ -11,6 +11,7 @@
 // backward (see include/mmbert_sm100.h: mmb_gemm).  Both operands may be K-major (activations, weights)
 // or MN-major (dY^T / X^T read in place for wgrad), selected in the UMMA instruction descriptor.
 #include <cuda.h>
+#include <stdlib.h>
 #include <mutex>
 #include <unordered_map>
 
@@ -580,8 +581,57 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 }
             }
         }
-    } else if (warp == 1 && lane == 0 && rank == 0) {
+    } else if (warp == 1 && rank == 0 && !(p.dbg & 128)) {
         // ================================ MMA issuer (leader CTA only) ================================
+        // The whole warp runs the loop with warp-uniform control flow and one elected lane issues: the descriptors then
+        // live in uniform registers (32-bit adds on the low half, the high half is loop-invariant) and the four MMAs of
+        // a k-block go out back to back.  Issued from a lone lane of a diverged warp the same code costs ~35
+        // instructions per tcgen05.mma (an ELECT / R2UR sequence and 64-bit descriptor arithmetic each time).
+        const uint32_t idesc = make_idesc(TM, TN, p.a_mn, p.b_mn);
+        const uint32_t hi_a = ((p.a_sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
+        const uint32_t hi_b = ((p.b_sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+        const uint32_t lbo_a = ((p.a_lbo >> 4) & 0x3FFFu) << 16, lbo_b = ((p.b_lbo >> 4) & 0x3FFFu) << 16;
+        const uint32_t step_a = p.a_step >> 4, step_b = p.b_step >> 4;   // tile addresses stay below 2^18: no carry
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = cluster_id; t < p.total_tiles; t += num_clusters) {
+            const int ks = t / mn_tiles;
+            const int kb0 = ks * p.kb_per_split;
+            const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+            ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * TN;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                ptx::mbar_wait(full_bar(stage), phase);
+                ptx::tc_fence_after();
+                const uint32_t sa = smem_base + stage * k2StageBytes;
+                const uint32_t a16 = ((sa & 0x3FFFFu) >> 4) | lbo_a;
+                const uint32_t b16 = (((sa + k2ABytes) & 0x3FFFFu) >> 4) | lbo_b;
+                if (ptx::elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        ptx::umma_bf16_2cta(tmem_d, ptx::umma_desc_from_halves(a16 + k * step_a, hi_a),
+                                            ptx::umma_desc_from_halves(b16 + k * step_b, hi_b), idesc,
+                                            (kb > kb0 || k > 0) ? 1u : 0u);
+                    ptx::umma_commit_2cta(empty_bar(stage));   // both CTAs' slots are free once these MMAs retire
+                }
+                __syncwarp();
+                if (++stage == k2Stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            if (ptx::elect_one()) ptx::umma_commit_2cta(tfull_bar(acc));   // both CTAs' epilogues may drain their half
+            __syncwarp();
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // bring-up (dbg bit 7 / MMB_GEMM_ISSUE=lane): the same issued by lane 0 alone, for A/B runs
         const uint32_t idesc = make_idesc(TM, TN, p.a_mn, p.b_mn);
         int stage = 0;
         uint32_t phase = 0;
@@ -605,13 +655,13 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     const uint64_t db = ptx::umma_desc_sw128(sb + k * p.b_step, p.b_lbo, p.b_sbo);
                     ptx::umma_bf16_2cta(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                 }
-                ptx::umma_commit_2cta(empty_bar(stage));   // both CTAs' slots are free once these MMAs retire
+                ptx::umma_commit_2cta(empty_bar(stage));
                 if (++stage == k2Stages) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
-            ptx::umma_commit_2cta(tfull_bar(acc));          // both CTAs' epilogues may drain their half
+            ptx::umma_commit_2cta(tfull_bar(acc));
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;
@@ -806,6 +856,11 @@ static void fill_common(GemmParams& p, const mmb_gemm_args* a, int tile_m, int t
     p.total_tiles = p.m_tiles * p.n_tiles * p.split_k;
     p.alpha = a->alpha;
     p.dbg = a->dbg_flags;
+    static const int lane_issue = [] {                       // MMB_GEMM_ISSUE=lane: single-lane MMA issue (A/B runs)
+        const char* e = getenv("MMB_GEMM_ISSUE");
+        return (e != nullptr && e[0] == 'l') ? 128 : 0;
+    }();
+    p.dbg |= lane_issue;
     // K-major SW128: 8-row groups 1024 B apart (SBO), LBO unused; 32 B per UMMA_K inside the swizzled row.
     // MN-major SW128: 64-element MN blocks 8192 B apart (LBO), 8-k groups 1024 B apart (SBO); two k-groups
     // (2048 B) per UMMA_K.  dbg_flags bit 1 swaps LBO/SBO of MN-major operands, bit 2 sets K-major LBO = 16 B.
