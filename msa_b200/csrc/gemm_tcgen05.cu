@@ -545,8 +545,28 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int total_kb = (p.K + BK - 1) / BK;
     const int mn_tiles = p.m_tiles * p.n_tiles;
 
-    if (warp == 0 && lane == 0) {
+    // one k-block of this CTA's operand halves -> stage ``stage``; bytes are credited to the leader's full barrier
+    auto load_kblock = [&](int stage, int kb, int m0, int n0) {
+        const uint32_t sa = smem_base + stage * k2StageBytes;
+        const uint32_t sb = sa + k2ABytes;
+        const uint32_t lead_full = full_bar(stage) & kPeerMask;
+        if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * k2StageBytes);
+        if (!p.a_mn) {
+            ptx::tma_load_2d_2cta(sa, &tmA, lead_full, kb * BK, m0);
+        } else {
+            ptx::tma_load_2d_2cta(sa, &tmA, lead_full, m0, kb * BK);
+            ptx::tma_load_2d_2cta(sa + 8192, &tmA, lead_full, m0 + 64, kb * BK);
+        }
+        if (!p.b_mn) {
+            ptx::tma_load_2d_2cta(sb, &tmB, lead_full, kb * BK, n0);
+        } else {
+            ptx::tma_load_2d_2cta(sb, &tmB, lead_full, n0, kb * BK);
+            ptx::tma_load_2d_2cta(sb + 8192, &tmB, lead_full, n0 + 64, kb * BK);
+        }
+    };
+    if (warp == 0 && !(p.dbg & 128)) {
         // ================================ TMA producer (both CTAs) ================================
+        // whole warp, warp-uniform control flow, one elected lane issues (see the MMA issuer below)
         int stage = 0;
         uint32_t phase = 0;
         for (int t = cluster_id; t < p.total_tiles; t += num_clusters) {
@@ -559,22 +579,29 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const int m0 = m_blk * TM + (int)rank * 128, n0 = n_blk * TN + (int)rank * 128;
             for (int kb = kb0; kb < kb1; ++kb) {
                 ptx::mbar_wait(empty_bar(stage), phase ^ 1);
-                const uint32_t sa = smem_base + stage * k2StageBytes;
-                const uint32_t sb = sa + k2ABytes;
-                const uint32_t lead_full = full_bar(stage) & kPeerMask;
-                if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * k2StageBytes);
-                if (!p.a_mn) {
-                    ptx::tma_load_2d_2cta(sa, &tmA, lead_full, kb * BK, m0);
-                } else {
-                    ptx::tma_load_2d_2cta(sa, &tmA, lead_full, m0, kb * BK);
-                    ptx::tma_load_2d_2cta(sa + 8192, &tmA, lead_full, m0 + 64, kb * BK);
+                if (ptx::elect_one()) load_kblock(stage, kb, m0, n0);
+                __syncwarp();
+                if (++stage == k2Stages) {
+                    stage = 0;
+                    phase ^= 1;
                 }
-                if (!p.b_mn) {
-                    ptx::tma_load_2d_2cta(sb, &tmB, lead_full, kb * BK, n0);
-                } else {
-                    ptx::tma_load_2d_2cta(sb, &tmB, lead_full, n0, kb * BK);
-                    ptx::tma_load_2d_2cta(sb + 8192, &tmB, lead_full, n0 + 64, kb * BK);
-                }
+            }
+        }
+    } else if (warp == 0 && lane == 0) {
+        // bring-up (dbg bit 7): the same by lane 0 alone
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = cluster_id; t < p.total_tiles; t += num_clusters) {
+            const int ks = t / mn_tiles;
+            const int r = t - ks * mn_tiles;
+            const int m_blk = r / p.n_tiles;
+            const int n_blk = r - m_blk * p.n_tiles;
+            const int kb0 = ks * p.kb_per_split;
+            const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+            const int m0 = m_blk * TM + (int)rank * 128, n0 = n_blk * TN + (int)rank * 128;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+                load_kblock(stage, kb, m0, n0);
                 if (++stage == k2Stages) {
                     stage = 0;
                     phase ^= 1;
