@@ -117,7 +117,15 @@ def test_state_dict_keys_equal_the_live_reference():
     for k in ref_sd:
         assert tuple(ref_sd[k].shape) == tuple(sd[k].shape), k
     assert [n for n, _ in ref.named_parameters()] == [n for n, _ in m.named_parameters()]
-    m.load_state_dict(ref_sd)     # checkpoints interchange (trainer.py:269 / sampling.py:344)
+    m.load_state_dict(ref_sd)     # checkpoints interchange (trainer.py:269 / sampling.py:344) ...
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, ref_sd[k]), k
+    torch.manual_seed(5)
+    m2 = MMBertForPretraining(BertShape(**kw))
+    m2.bert.set_joint_embeddings("ur_funny")
+    res = ref.load_state_dict(m2.state_dict(), strict=True)   # ... in both directions
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(ref.state_dict()["cls.predictions.decoder.weight"], m2.state_dict()["bert.embeddings.word_embeddings.weight"])
 
 
 def test_synthetic_batch_has_reference_dtypes_and_layout():
