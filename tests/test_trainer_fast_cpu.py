@@ -84,3 +84,54 @@ def test_deferred_scalars_return_every_value_in_order():
     got = [r.push(torch.tensor(float(i))) for i in range(5)]
     assert got == [None, None, 0.0, 1.0, 2.0] and r.flush() == [3.0, 4.0]
     assert r.push(torch.tensor(9.0)) is None and r.flush() == [9.0] and r.flush() == []
+
+
+class _EvalModel(_FakeModel):
+    def forward(self, **kw):
+        out, _ = super().forward(**kw)
+        return out, kw["sentiment"].float().reshape(-1, 1) * 0.5 - 1.0
+
+
+def test_eval_epoch_matches_the_reference_loop():
+    import numpy as np
+    args = types.SimpleNamespace(val_batch_size=4, mlm=False, mlm_probability=0.15)
+    data = list(range(10))            # batches of 4, 4, 2
+    torch.manual_seed(1)
+    model = _EvalModel()
+    out = trainer_fast.eval_epoch(args, model, data, tokenizer=None, collate_fn=_collate, device=torch.device("cpu"))
+    assert not model.training and len(out) == 8 and len(model.calls) == 3
+    # restatement of trainer.py:127-194 with its per-batch host reads
+    torch.manual_seed(1)
+    ref = _EvalModel().eval()
+    from torch.utils.data import DataLoader, RandomSampler
+    dl = ll = 0.0
+    preds, labels, nb = [], [], 0
+    with torch.no_grad():
+        for batch in DataLoader(data, sampler=RandomSampler(data), batch_size=4, collate_fn=_collate):
+            o, logits = ref(**trainer_fast.unpack_batch(batch, torch.device("cpu")))
+            dl += o[0].mean().item()
+            ll += o[5].mean().item()
+            ap_last = o[4]
+            preds.extend(logits.numpy())
+            labels.extend(batch[0][-1].numpy())
+            nb += 1
+    assert abs(out[0] - dl / nb) < 1e-9 and abs(out[5] - ll / nb) < 1e-9 and out[1] == out[2] == out[3] == 0.0
+    assert torch.allclose(out[4], ap_last / nb)
+    assert out[6].shape == (10, 1) and out[7].shape == (10,)
+    assert np.array_equal(out[6], np.array(preds)) and np.array_equal(out[7], np.array(labels))
+
+
+def test_score_functions_match_sklearn():
+    import numpy as np
+    from sklearn.metrics import accuracy_score, f1_score
+    rng = np.random.default_rng(0)
+    y = rng.uniform(-3, 3, 200).astype(np.float32)
+    p = (y + rng.normal(0, 1.5, 200)).astype(np.float32).reshape(-1, 1)
+    acc, mae, f = trainer_fast.test_MSE_score_model(p, y)
+    assert abs(mae - np.mean(np.absolute(p - y))) < 1e-7             # the reference's expression, broadcasting included
+    assert abs(f - f1_score(y >= 0, p >= 0, average="weighted")) < 1e-12
+    assert abs(acc - accuracy_score(y >= 0, p >= 0)) < 1e-12
+    yc, pc = rng.integers(0, 7, 300), rng.integers(0, 6, 300)
+    acc, mae, f = trainer_fast.test_CE_score_model(pc, yc)
+    assert abs(f - f1_score(yc, pc, average="weighted")) < 1e-12 and abs(acc - accuracy_score(yc, pc)) < 1e-12
+    assert abs(mae - np.mean(np.abs(pc - yc))) < 1e-12
