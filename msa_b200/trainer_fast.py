@@ -185,14 +185,30 @@ def unpack_batch(batch, device, tokenizer=None, args=None):
     )
 
 
+def _world():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
 def train_epoch(args, model, traindata, optimizer, scheduler, tokenizer, *, collate_fn=None, device=None,
-                faithful_stepping=True):
+                faithful_stepping=True, epoch=0):
+    """One process per GPU (``torch.distributed`` initialised, world size > 1): every rank draws its own shard of a
+    common shuffle (``DistributedSampler`` seeded by ``epoch``; ``args.train_batch_size`` is per rank), gradients are
+    reduced by the model's ``GradReducer`` as usual, and the returned loss averages are over all ranks' batches (one
+    all-reduce of five scalars per epoch).  Single process: the reference's ``RandomSampler``."""
     if collate_fn is None:
         import model_utils                      # the reference's module (on PYTHONPATH in the drop-in setting)
         collate_fn = model_utils.collate
     if device is None:
         device = next(model.parameters()).device
-    loader = DataLoader(traindata, sampler=RandomSampler(traindata), batch_size=args.train_batch_size, collate_fn=collate_fn)
+    world = _world()
+    if world > 1:
+        from torch.utils.data.distributed import DistributedSampler
+        sampler = DistributedSampler(traindata, shuffle=True, drop_last=False)
+        sampler.set_epoch(epoch)
+    else:
+        sampler = RandomSampler(traindata)
+    loader = DataLoader(traindata, sampler=sampler, batch_size=args.train_batch_size, collate_fn=collate_fn)
     sums = torch.zeros(5, device=device, dtype=torch.float64)      # train, text, visual, speech, label
     n, ap_last = 0, None
     model.train()
@@ -216,7 +232,13 @@ def train_epoch(args, model, traindata, optimizer, scheduler, tokenizer, *, coll
             optimizer.zero_grad()
     if n == 0:
         raise ValueError("empty training set")
-    s = (sums / n).tolist()                                        # the epoch's only device->host read
+    if world > 1:
+        import torch.distributed as dist
+        tot = torch.cat((sums, torch.tensor([float(n)], device=device, dtype=torch.float64)))
+        dist.all_reduce(tot)
+        s = (tot[:5] / tot[5]).tolist()
+    else:
+        s = (sums / n).tolist()                                    # the epoch's only device->host read
     return s[0], s[1], s[2], s[3], (ap_last / n if ap_last is not None else None), s[4]
 
 

@@ -135,3 +135,36 @@ def test_score_functions_match_sklearn():
     acc, mae, f = trainer_fast.test_CE_score_model(pc, yc)
     assert abs(f - f1_score(yc, pc, average="weighted")) < 1e-12 and abs(acc - accuracy_score(yc, pc)) < 1e-12
     assert abs(mae - np.mean(np.abs(pc - yc))) < 1e-12
+
+
+def _dist_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    args = types.SimpleNamespace(train_batch_size=2, gradient_accumulation_step=1, mlm=False, mlm_probability=0.15)
+    model, opt = _FakeModel(), _Opt()
+    out = trainer_fast.train_epoch(args, model, list(range(12)), opt, _Opt(), None, collate_fn=_collate,
+                                   device=torch.device("cpu"), epoch=3)
+    seen = sorted(int(v) for c in model.calls for v in c[5].tolist())          # sentiment == sample index
+    local = sum(float(((0.5 * c[5].float().mean() + c[0][0].float().mean() * 1e-3) ** 2)) for c in model.calls)
+    q.put((rank, out[0], seen, local, len(model.calls)))
+    dist.destroy_process_group()
+
+
+def test_train_epoch_shards_the_data_and_averages_losses_over_ranks_gloo():
+    import os
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dist_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    (_, loss0, seen0, local0, n0), (_, loss1, seen1, local1, n1) = res
+    assert sorted(seen0 + seen1) == list(range(12)) and not set(seen0) & set(seen1)     # disjoint shards of one shuffle
+    assert n0 == n1 == 3
+    assert abs(loss0 - loss1) < 1e-12 and abs(loss0 - (local0 + local1) / (n0 + n1)) < 1e-9
