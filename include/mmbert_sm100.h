@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MMB_VERSION 100 /* round 1 */
+#define MMB_VERSION 101 /* round 1; 101: mmb_attn_args.work, mmb_attn_schedule */
 
 enum mmb_status {
     MMB_OK = 0,
