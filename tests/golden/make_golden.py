@@ -27,6 +27,14 @@ FIXTURES = {
     "tiny_mosei_unaligned": ("mosei", dict(hidden_size=128, num_hidden_layers=2, num_attention_heads=2,
                                            intermediate_size=256, vocab_size=256, max_position_embeddings=32),
                              4, 10, 70, 23, 12, 22, 0.7, 0.3),
+    # oracle-only fixtures (tests/helpers.py: GOLDEN_ORACLE_ONLY): the wide UR-FUNNY frame dims (371 / 81), and a
+    # single-sample batch (CPC's in-batch negatives degenerate to one row; every sequence length at its minimum)
+    "tiny_ur_funny": ("ur_funny", dict(hidden_size=128, num_hidden_layers=1, num_attention_heads=2,
+                                       intermediate_size=256, vocab_size=256, max_position_embeddings=32),
+                      3, 9, 9, 9, 13, 23, 1.0, 0.5),
+    "tiny_mosi_single": ("mosi", dict(hidden_size=64, num_hidden_layers=1, num_attention_heads=1,
+                                      intermediate_size=128, vocab_size=256, max_position_embeddings=32),
+                         1, 6, 6, 6, 14, 24, 1.0, 1.0),
 }
 OUT_NAMES = ("joint_loss", None, None, None, "ap_loss", "label_loss", "nce", "pred_t", "rel_t", "pred_v",
              "align_v", "pred_s", "align_s")

@@ -11,6 +11,8 @@ from oracle import mmbert_oracle as O
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN = ("tiny_mosi_aligned", "tiny_mosei_unaligned")
+# further fixtures that (so far) pin the CPU oracle only: UR-FUNNY's wide frame dims, a one-sample batch
+GOLDEN_ORACLE_ONLY = ("tiny_ur_funny", "tiny_mosi_single")
 OUT_NAMES = ("joint_loss", None, None, None, "ap_loss", "label_loss", "nce", "pred_t", "rel_t", "pred_v",
              "align_v", "pred_s", "align_s")
 
