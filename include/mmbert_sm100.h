@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MMB_VERSION 101 /* round 1; 101: mmb_attn_args.work, mmb_attn_schedule */
+#define MMB_VERSION 200 /* round 2; 200: mmb_pack_args.mask_frame_stride */
 
 enum mmb_status {
     MMB_OK = 0,
@@ -223,9 +223,11 @@ enum { MMB_DT_F32 = 0, MMB_DT_F64 = 1, MMB_DT_I64 = 2, MMB_DT_I32 = 3, MMB_DT_U8
 typedef struct mmb_pack_args {
     const void* mask_text[3]; /* [B,T] text-half mask of each pass */
     int32_t mask_text_dtype[3];
-    const void* mask_frame[2]; /* [B,L,D] visual / speech masks */
+    const void* mask_frame[2]; /* [B,L,D] visual / speech masks (only feature 0 is read, MMBertForPretraining.py:74-77) */
     int32_t mask_frame_dtype[2];
     int32_t frame_dim[2];
+    int32_t mask_frame_stride[2]; /* elements between consecutive frames of mask_frame: 0 = frame_dim (a [B,L,D] mask),
+                                     1 = a [B,L] mask (the reference takes those too, :74) */
     const void* labels[3]; /* int64 [B,T], [B,T+Lv], [B,T+La]; may be NULL */
     float* keybias;        /* [rows] */
     int32_t* cu_seqlens;   /* [3B+1] */
@@ -336,11 +338,13 @@ typedef struct mmb_heads_args {
     float* g_w_cpc[3];
     float* g_b_cpc[3];
     const void* ap_label[2]; /* int64 [B] visual, speech */
-    const float* sentiment;  /* [B] f32 */
+    const float* sentiment;  /* [B] f32 (regression target; class index as a float in the classification branch) */
     const float* ce_loss_sum;   /* [3] from mmb_ce_fwd */
     const int32_t* label_count; /* [3] */
     float* losses;     /* [8] */
-    float* logits_out; /* [B]  (tanh applied iff num_labels == 1) */
+    float* logits_out; /* [B]  tanh applied iff num_labels == 1; num_labels not in {1,7} = the reference's CrossEntropyLoss
+                          branch (MMBertForPretraining.py:437-442) on the [B,1] classifier output: label loss 0 (NaN if a
+                          target is not class 0, where torch raises), logits_out = argmax = 0, no label gradient */
     float* rel_out;    /* [B,2] seq_relationship(pooled_text) or NULL */
     float* align_out;  /* [2B,2] align scores (visual rows, then speech rows) or NULL */
     const float* gscale; /* device scalar upstream gradient, NULL = 1 */

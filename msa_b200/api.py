@@ -147,6 +147,7 @@ class MMBertForPretraining(_Node):
         self._keep = None
         self._post_backward = None
         self._bwd_hooks = None
+        self._reducer = None       # msa_b200.ddp.GradReducer once attached (train_epoch toggles its ``sync`` flag)
         self.launches = 0          # kernel-launching C calls issued so far (bench.py reports the per-step count)
         self.dense_mlm = True
         # "bf16": tcgen05 tensor-core path (training and inference).  "fp32": validation path, forward only, fp32
@@ -232,17 +233,19 @@ class MMBertForPretraining(_Node):
     def _backward_hooks_for(self, plan):
         return self._bwd_hooks(plan) if self._bwd_hooks is not None else None
 
-    def _plan(self, B, T, Lv, La, device):
+    def _plan(self, B, T, Lv, La, device, needs_grad):
         if self.precision not in ("bf16", "fp32"):
             raise capi.MMBError(f"precision must be 'bf16' or 'fp32', not {self.precision!r}")
         fp32 = self.precision == "fp32"
-        key = (B, T, Lv, La, self.training, fp32)
+        # everything that is baked into a plan when it is built is part of its key
+        p_joint = float(self.bert.jointEmbeddings.dropout.p)
+        key = (B, T, Lv, La, bool(needs_grad), bool(self.training), fp32, p_joint, bool(self.dense_mlm),
+               float(self.config.hidden_dropout_prob), float(self.config.attention_probs_dropout_prob))
         plan = self._plans.get(key)
         if plan is None and fp32:
             if len(self._plans) >= 4:
                 self._plans.clear()
-            p_any = max(float(self.config.hidden_dropout_prob), float(self.config.attention_probs_dropout_prob),
-                        float(self.bert.jointEmbeddings.dropout.p))
+            p_any = max(float(self.config.hidden_dropout_prob), float(self.config.attention_probs_dropout_prob), p_joint)
             if self.training and p_any > 0:
                 raise capi.MMBError("the fp32 validation path is dropout-free: call .eval() or set the dropout "
                                     "probabilities to 0 (the reference parity recipe)")
@@ -252,9 +255,8 @@ class MMBertForPretraining(_Node):
         if plan is None:
             if len(self._plans) >= 4:          # bound the activation memory held by stale shapes
                 self._plans.clear()
-            p_joint = self.bert.jointEmbeddings.dropout.p
-            plan = Plan(self.config, self.bert.dataset, self._store, B, T, Lv, La, self.training, device,
-                        p_joint=p_joint, dense_mlm=self.dense_mlm)
+            plan = Plan(self.config, self.bert.dataset, self._store, B, T, Lv, La, bool(needs_grad), device,
+                        p_joint=p_joint, dense_mlm=self.dense_mlm, dropout=bool(self.training))
             self._plans[key] = plan
             plan._frame_sig = None
         return plan
@@ -274,7 +276,18 @@ class MMBertForPretraining(_Node):
         ids_t, vis, aud = input_ids[0], input_ids[1], input_ids[2]
         B, T = ids_t.shape
         Lv, La = vis.shape[1], aud.shape[1]
-        plan = self._plan(B, T, Lv, La, dev)
+        fp32 = self.precision == "fp32"
+        needs_grad = torch.is_grad_enabled() and not fp32
+        classify = self.num_labels not in (1, 7)
+        if classify:
+            # MMBertForPretraining.py:437-442: CrossEntropyLoss()(logits [B, 1], sentiment).  classifier1_2 is always
+            # Linear(H, 1) (:311-314 — num_labels is 7 when it is built), so this is a ONE-class problem: torch accepts
+            # integer class indices only here (a float target must have the logits' shape) and every index must be 0.
+            if sentiment.is_floating_point() or sentiment.dim() != 1:
+                raise capi.MMBError("num_labels not in (1, 7) selects the reference's CrossEntropyLoss branch "
+                                    "(MMBertForPretraining.py:437-442): sentiment must be an integer class-index tensor "
+                                    "of shape [B] (torch raises for a floating-point [B] target against [B, 1] logits)")
+        plan = self._plan(B, T, Lv, La, dev, needs_grad)
         plan.set_loss_weights(self.alpha, self.beta, self.num_labels)
         self._keep = plan.bind_inputs(input_ids, token_type_ids, attention_mask, masked_labels, ap_label, sentiment)
         sig = self._signature()
@@ -282,26 +295,32 @@ class MMBertForPretraining(_Node):
         if plan._frame_sig != sig:
             plan.refresh_frame_weights()
             plan._frame_sig = sig
-        if self.precision == "fp32":           # forward only: the losses carry no autograd graph
-            Plan.run(plan.fwd)
-            self.launches += len(plan.fwd)
-            joint = plan.losses[0].clone()
-        elif torch.is_grad_enabled() and self.training:
+        if self.training:
             plan.set_seed(int(torch.randint(0, 2 ** 62, (1,)).item()))
+        if needs_grad:
             anchor = self._params["classifier1_2.bias"]
             joint = _StepFn.apply(anchor, self, plan)
-        else:
-            if self.training:
-                plan.set_seed(int(torch.randint(0, 2 ** 62, (1,)).item()))
+        else:                                   # no_grad, or the forward-only fp32 validation path
             Plan.run(plan.fwd)
             self.launches += len(plan.fwd)
-            joint = plan.losses[0].clone()
-        losses = plan.losses
+            joint = None
+        # The plan's buffers are overwritten by the next step: every small result is handed out as a fresh copy (one
+        # device copy), so callers may accumulate them across batches as trainer.py:165-180 does.  The pred_* outputs
+        # stay views of the packed decoder output (up to 4.5 GB): valid until the next forward.
+        small = plan.small_out.clone()
+        losses = small[:8]
+        if joint is None:
+            joint = losses[0]
         V = self.config.vocab_size
         b1, b2 = B * T, B * T + B * (T + Lv)
         pred_t = plan.logits[:b1, :V].view(B, T, V)
         pred_v = plan.logits[b1:b2, :V].view(B, T + Lv, V)
         pred_s = plan.logits[b2:, :V].view(B, T + La, V)
-        outputs = (joint, None, None, None, losses[2], losses[3], losses[4], pred_t, plan.rel_out, pred_v,
-                   plan.align_out[:B], pred_s, plan.align_out[B:])
-        return outputs, plan.logits_out.view(B, 1)
+        rel = small[8 + B:8 + 3 * B].view(B, 2)
+        align = small[8 + 3 * B:].view(2 * B, 2)
+        outputs = (joint, None, None, None, losses[2], losses[3], losses[4], pred_t, rel, pred_v,
+                   align[:B], pred_s, align[B:])
+        logits = small[8:8 + B]
+        if classify:
+            return outputs, logits.long()       # torch.argmax(sigmoid(logits [B, 1]), dim=1): all zeros
+        return outputs, logits.view(B, 1)

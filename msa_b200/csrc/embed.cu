@@ -54,7 +54,7 @@ struct PrepParams {
     int mask_text_dt[3];
     const void* mask_frame[2];  // [B,L,D] for pass 1, 2 (feature 0 is read)
     int mask_frame_dt[2];
-    int frame_dim[2];
+    int mask_frame_stride[2];   // elements per frame in mask_frame (D, or 1 for a [B,L] mask)
     const long long* labels[3]; // [B, S(pass)]
     float* keybias;             // [rows]
     int* cu_seqlens;            // [3B + 1]
@@ -71,7 +71,7 @@ __global__ void pack_prepare_kernel(const PrepParams p) {
         if (c.s < p.d.T) {
             m = load_as_float(p.mask_text[c.pass], p.mask_text_dt[c.pass], (int64_t)c.b * p.d.T + c.s);
         } else {
-            const int L = c.pass == 1 ? p.d.L1 : p.d.L2, D = p.frame_dim[c.pass - 1];
+            const int L = c.pass == 1 ? p.d.L1 : p.d.L2, D = p.mask_frame_stride[c.pass - 1];
             m = load_as_float(p.mask_frame[c.pass - 1], p.mask_frame_dt[c.pass - 1], ((int64_t)c.b * L + (c.s - p.d.T)) * D);
         }
         p.keybias[row] = (1.0f - m) * -10000.0f;
@@ -519,7 +519,8 @@ extern "C" int mmb_pack_prepare(const mmb_pack_args* a, void* stream) {
         MMB_REQUIRE(a->L[i] == 0 || a->mask_frame[i] != nullptr, "pack_prepare: null frame mask %d", i);
         p.mask_frame[i] = a->mask_frame[i];
         p.mask_frame_dt[i] = a->mask_frame_dtype[i];
-        p.frame_dim[i] = a->frame_dim[i];
+        MMB_REQUIRE(a->mask_frame_stride[i] >= 0, "pack_prepare: negative frame mask stride %d", i);
+        p.mask_frame_stride[i] = a->mask_frame_stride[i] > 0 ? a->mask_frame_stride[i] : a->frame_dim[i];
     }
     p.keybias = a->keybias;
     p.cu_seqlens = a->cu_seqlens;

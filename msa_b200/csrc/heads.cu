@@ -323,7 +323,7 @@ struct LossParams {
     const int* label_count;   // [3]
     const float* nce;         // [1]
     float* losses;            // [8]: joint, mlm, ap, label, nce, mlm_t, mlm_v, mlm_s
-    float* logits_out;        // [B] (tanh applied iff num_labels == 1)
+    float* logits_out;        // [B] (tanh applied iff num_labels == 1; zeros in the classification branch)
     float* dal;               // [2B,2]  backward
     float* dlogit;            // [B]     backward
     const float* gscale;
@@ -343,8 +343,17 @@ final_losses_kernel(const LossParams p) {
         const long long lab = p.ap[mod][b];
         ap_acc += (lse - (lab == 0 ? a0 : a1)) / (float)p.B;
     }
+    const bool classify = p.num_labels != 1 && p.num_labels != 7;
     for (int i = threadIdx.x; i < p.B; i += 256) {
         float o = p.logit[i];
+        if (classify) {
+            // MMBertForPretraining.py:437-442 with classifier1_2 = Linear(H, 1) (:311-314): cross entropy over ONE class is
+            // lse - logit[target] = 0 for target 0; any other target is out of bounds (torch raises) -> NaN here.
+            // Returned "logits" = argmax(sigmoid(logits), dim=1) = 0.
+            p.logits_out[i] = 0.f;
+            if (p.sentiment[i] != 0.f) mse_acc += __int_as_float(0x7fc00000);
+            continue;
+        }
         if (p.num_labels == 1) o = tanhf(o);
         p.logits_out[i] = o;
         const float d = o - p.sentiment[i];
@@ -394,11 +403,12 @@ final_losses_bwd_kernel(const LossParams p) {
         p.dal[2 * i] = c * (e0 * inv - (lab == 0 ? 1.f : 0.f));
         p.dal[2 * i + 1] = c * (e1 * inv - (lab == 1 ? 1.f : 0.f));
     }
+    const bool classify = p.num_labels != 1 && p.num_labels != 7;
     for (int i = threadIdx.x; i < p.B; i += 256) {
         const float o = p.logits_out[i];
         float d = gs * 2.f * (o - p.sentiment[i]) / (float)p.B;
         if (p.num_labels == 1) d *= (1.f - o * o);
-        p.dlogit[i] = d;
+        p.dlogit[i] = classify ? 0.f : d;     // one-class cross entropy: softmax - onehot == 0
     }
 }
 __global__ void tanh_bwd_kernel(float* __restrict__ dP, const float* __restrict__ P, int n) {  // dZ = dP (1 - P^2), in place

@@ -13,6 +13,8 @@ slice of that buffer: nothing is copied or re-packed before the collective.
 
 Params without gradient (W_cv, W_cs, cls.seq_relationship) live outside [0, trainable_end) and are never sent.
 """
+import contextlib
+
 import torch
 import torch.distributed as dist
 
@@ -56,9 +58,22 @@ class GradReducer:
         self.pending = []
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.bytes_per_step = 4 * store.trainable_end
+        # False = accumulate locally (DistributedDataParallel.no_sync semantics).  The all-reduce is an in-place SUM over
+        # the flat gradient buffer that backward also accumulates into, so with gradient accumulation ONLY the backward
+        # that precedes optimizer.step() may reduce: reducing an earlier micro-batch and then again with the next one
+        # would weight it world_size times (AR(AR(g1) + g2) = world * AR(g1) + AR(g2)).
+        self.sync = True
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        old, self.sync = self.sync, False
+        try:
+            yield
+        finally:
+            self.sync = old
 
     def reduce_bucket(self, ranges):
-        if self.world == 1:
+        if self.world == 1 or not self.sync:
             return
         for a, b in ranges:
             self.pending.append(dist.all_reduce(self.store.grad[a:b], op=dist.ReduceOp.SUM, group=self.group,
@@ -97,6 +112,7 @@ class GradReducer:
 
         model._bwd_hooks = hooks
         model._post_backward = self.finish
+        model._reducer = self
         return self
 
 

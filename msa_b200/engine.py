@@ -43,7 +43,11 @@ def _split_k(M_out, N_out, K, clusters=74):
 
 
 class Plan:
-    def __init__(self, cfg, dataset, store, B, T, Lv, La, training, device, p_joint=0.5, dense_mlm=True):
+    def __init__(self, cfg, dataset, store, B, T, Lv, La, training, device, p_joint=0.5, dense_mlm=True, dropout=None):
+        # ``training``: keep the activations and build the backward plan.  ``dropout`` (default: same as training):
+        # apply the dropout probabilities — a forward with autograd enabled on an eval() model keeps the
+        # activations but drops nothing, exactly what the reference's modules would do.
+        dropout = training if dropout is None else dropout
         self.cfg, self.store, self.training, self.device = cfg, store, training, device
         self.B, self.T, self.Lv, self.La = B, T, Lv, La
         self.Dv, self.Da = DATASET_DIMS[dataset]
@@ -56,9 +60,9 @@ class Plan:
         self.M = M = B * (3 * T + Lv + La)
         self.nfr = nfr = B * (Lv + La)
         self.max_S = T + max(Lv, La)
-        self.p_hidden = float(cfg.hidden_dropout_prob) if training else 0.0
-        self.p_attn = float(cfg.attention_probs_dropout_prob) if training else 0.0
-        self.p_joint = float(p_joint) if training else 0.0
+        self.p_hidden = float(cfg.hidden_dropout_prob) if dropout else 0.0
+        self.p_attn = float(cfg.attention_probs_dropout_prob) if dropout else 0.0
+        self.p_joint = float(p_joint) if dropout else 0.0
         self.dense_mlm = dense_mlm
         self.alpha, self.beta, self.num_labels = 1.0, 1.0, 7
         dev = device
@@ -99,8 +103,11 @@ class Plan:
         self.row_lse = buf(M, dtype=F32)
         self.ce_sum = buf(4, dtype=F32)
         self.heads_ws = torch.empty(capi.heads_workspace_bytes(B, H) // 4 + 16, device=dev, dtype=F32)
-        self.losses = buf(8, dtype=F32)
-        self.logits_out, self.rel_out, self.align_out = buf(B, dtype=F32), buf(B, 2, dtype=F32), buf(2 * B, 2, dtype=F32)
+        # every small user-visible result lives in ONE buffer, so that forward() hands out fresh copies with a single
+        # device-to-device copy (the plan's buffers are overwritten by the next step)
+        self.small_out = buf(8 + 7 * B, dtype=F32)
+        self.losses, self.logits_out = self.small_out[:8], self.small_out[8:8 + B]
+        self.rel_out, self.align_out = self.small_out[8 + B:8 + 3 * B].view(B, 2), self.small_out[8 + 3 * B:].view(2 * B, 2)
         self.wT = [buf(self.Dv, H, dtype=F32), buf(self.Da, H, dtype=F32)]
         self.gscale = torch.ones(1, device=dev, dtype=F32)
         if training:
@@ -348,8 +355,13 @@ class Plan:
         if tuple(labs[1].shape) != (B, T + self.Lv) or tuple(labs[2].shape) != (B, T + self.La):
             raise capi.MMBError("masked_labels of the joint passes must have shape [B, T+L] "
                                 "(the reference cats the text labels onto the frame half, trainer.py:50,53)")
+        for t, L, D in zip(mf, (self.Lv, self.La), (self.Dv, self.Da)):
+            # [B,L,D] as the reference's collate builds them (only feature 0 is read), or already [B,L] (:74-77)
+            if tuple(t.shape) not in ((B, L, D), (B, L)):
+                raise capi.MMBError(f"frame attention mask must be [B, L, D] or [B, L], got {tuple(t.shape)}")
         capi.fill(self.pack_args, mask_text=mt, mask_text_dtype=[capi.dtype_code(t) for t in mt],
-                  mask_frame=mf, mask_frame_dtype=[capi.dtype_code(t) for t in mf], labels=labs)
+                  mask_frame=mf, mask_frame_dtype=[capi.dtype_code(t) for t in mf],
+                  mask_frame_stride=[0 if t.dim() == 3 else 1 for t in mf], labels=labs)
         capi.fill(self.embed_args, ids=ids, token_type=tt, frames=frames,
                   frames_dtype=[capi.dtype_code(t) for t in frames])
         capi.fill(self.ce_args, labels=labs)

@@ -48,8 +48,9 @@ class PlanF32:
         self.logits = buf(M, V)
         self.row_lse, self.ce_sum = buf(M), buf(4)
         self.heads_ws = torch.empty(capi.heads_workspace_bytes(B, H) // 4 + 16, device=device, dtype=F32)
-        self.losses = buf(8)
-        self.logits_out, self.rel_out, self.align_out = buf(B), buf(B, 2), buf(2 * B, 2)
+        self.small_out = buf(8 + 7 * B)                   # see engine.Plan: one copy hands out all small results
+        self.losses, self.logits_out = self.small_out[:8], self.small_out[8:8 + B]
+        self.rel_out, self.align_out = self.small_out[8 + B:8 + 3 * B].view(B, 2), self.small_out[8 + 3 * B:].view(2 * B, 2)
         self.wT = [buf(self.Dv, H), buf(self.Da, H)]
         self._frame_sig = None
         self._build()

@@ -28,13 +28,15 @@ class FusedAdamW(torch.optim.Optimizer):
         self._m = torch.zeros(st.trainable_end, device=st.flat.device, dtype=torch.float32)
         self._v = torch.zeros_like(self._m)
         self._step = 0
+        self._flat_ptr = st.flat.data_ptr()     # the buffers the moments belong to (checked on every step)
         self.grad_scale = 1.0      # 1/world_size after a SUM all-reduce
 
     @torch.no_grad()
     def step(self, closure=None):
         st = self.model._store
-        if st.flat.data_ptr() != self._m_owner_ptr():
-            raise capi.MMBError("model storage was re-materialised after the optimizer was built")
+        if st is None or st.flat is None or st.flat.data_ptr() != self._flat_ptr or st.flat.device != self._m.device:
+            raise capi.MMBError("model storage was re-materialised after the optimizer was built (build FusedAdamW "
+                                "after .cuda() / set_joint_embeddings)")
         self._step += 1
         for (a, b), group in zip(self._ranges, self.param_groups):
             args = capi.fill(capi.AdamwArgs(), p=st.flat[a:b], g=st.grad[a:b], m=self._m[a:b], v=self._v[a:b],
@@ -49,10 +51,22 @@ class FusedAdamW(torch.optim.Optimizer):
             plan._frame_sig = None
         return None
 
-    def _m_owner_ptr(self):
-        if not hasattr(self, "_flat_ptr"):
-            self._flat_ptr = self.model._store.flat.data_ptr()
-        return self._flat_ptr
+    def state_dict(self):
+        """torch's param_groups plus the fused state: step count and the two flat moment buffers (the per-parameter
+        ``state`` of a stock optimizer is empty here — the moments live in two flat tensors)."""
+        sd = super().state_dict()
+        sd["fused"] = {"step": self._step, "exp_avg": self._m.clone(), "exp_avg_sq": self._v.clone(), "grad_scale": self.grad_scale}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        fused = state_dict.get("fused")
+        super().load_state_dict({k: v for k, v in state_dict.items() if k != "fused"})
+        if fused is not None:
+            if fused["exp_avg"].numel() != self._m.numel():
+                raise capi.MMBError("optimizer state belongs to a model of another shape")
+            self._step = int(fused["step"])
+            self._m.copy_(fused["exp_avg"])
+            self._v.copy_(fused["exp_avg_sq"])
 
     def zero_grad(self, set_to_none=False):
         """Zeroes the flat gradient buffer with one memset and keeps the ``.grad`` views attached."""

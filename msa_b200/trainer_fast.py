@@ -8,7 +8,10 @@ every step removed:
   once at the end of the epoch;
 * MLM masking through Python lists and boolean-index writes (model_utils.py:6-39, three times per step) — one kernel
   launch per id tensor (``msa_b200.data.mask_tokens``);
-* pageable, blocking host->device copies (trainer.py:49-64) — pinned buffers and ``non_blocking`` copies.
+* pageable, blocking host->device copies (trainer.py:49-64) — the collate output is staged through three reused
+  pinned buffer sets and copied on a copy stream one batch ahead (``DevicePrefetcher(stage=True)``); what is copied is
+  the compact form of ``compact_host``: float32 frames and the feature-0 column of the frame masks (bit-identical
+  results, a quarter of the bytes).
 
 ``DevicePrefetcher`` (double-buffered host->device copies on a copy stream) and ``DeferredScalars`` (per-step loss
 read-back that arrives a step late instead of stalling the launch queue) are the building blocks for loops that still want
@@ -57,7 +60,9 @@ class DevicePrefetcher:
     Replaces the blocking per-tensor ``.to(DEVICE)`` calls of trainer.py:49-72.
     """
 
-    def __init__(self, batches, device):
+    def __init__(self, batches, device, stage=False):
+        """``stage=True``: the host batches are pageable (a DataLoader's collate output); each is first copied into one of
+        three REUSED pinned buffer sets (no ``pin_memory()`` allocation per step), from which the asynchronous copy runs."""
         self.batches = batches
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -66,6 +71,23 @@ class DevicePrefetcher:
         self._slots = [None, None]      # device trees
         self._sig = [None, None]        # (shape, dtype) signature of each slot
         self._free = [None, None]       # event on the consumer stream: the slot may be overwritten after it
+        self.stage = stage
+        self._pin = [None, None, None]  # pinned host trees
+        self._pin_sig = [None, None, None]
+        self._pin_done = [None, None, None]   # event on the copy stream: the H2D copy out of the pinned set has finished
+        self.h2d_bytes = 0              # bytes copied host->device so far (bench.py reports them)
+
+    def _staged(self, i, host_batch):
+        k = i % 3
+        sig = tuple((tuple(t.shape), t.dtype) for t in _tree_leaves(host_batch, []))
+        if self._pin_sig[k] != sig:
+            self._pin[k] = _tree_like(host_batch, lambda t: torch.empty(t.shape, dtype=t.dtype).pin_memory())
+            self._pin_sig[k] = sig
+        elif self._pin_done[k] is not None:
+            self._pin_done[k].synchronize()        # three batches back: long finished
+        for d, h in zip(_tree_leaves(self._pin[k], []), _tree_leaves(host_batch, [])):
+            d.copy_(h)
+        return self._pin[k], k
 
     def _slot_for(self, s, host_batch, main):
         sig = tuple((tuple(t.shape), t.dtype) for t in _tree_leaves(host_batch, []))
@@ -81,13 +103,19 @@ class DevicePrefetcher:
 
     def _launch(self, i, host_batch, main):
         s = i % 2
+        k = None
+        if self.stage:
+            host_batch, k = self._staged(i, host_batch)
         dst = self._slot_for(s, host_batch, main)
         self.copy_stream.wait_event(self._free[s])
         with torch.cuda.stream(self.copy_stream):
             for d, h in zip(_tree_leaves(dst, []), _tree_leaves(host_batch, [])):
                 d.copy_(h, non_blocking=True)
+                self.h2d_bytes += h.numel() * h.element_size()
             ready = torch.cuda.Event()
             ready.record(self.copy_stream)
+        if k is not None:
+            self._pin_done[k] = ready
         return dst, ready
 
     def __iter__(self):
@@ -150,39 +178,72 @@ class DeferredScalars:
         return out
 
 
-def _to_dev(t, device):
-    if not torch.is_tensor(t):
-        t = torch.as_tensor(t)
-    if t.device.type == "cpu" and device.type == "cuda":
-        t = t.pin_memory()
-    return t.to(device, non_blocking=True)
+def _as_tensor(t):
+    return t if torch.is_tensor(t) else torch.as_tensor(t)
 
 
-def unpack_batch(batch, device, tokenizer=None, args=None):
-    """trainer.py:41-64: collate output -> keyword arguments of MMBertForPretraining.forward (tensors on ``device``)."""
+def unpack_host(batch):
+    """trainer.py:41-72 without the device copies: collate output -> keyword arguments of MMBertForPretraining.forward as
+    HOST tensors.  ``masked_labels`` is left out: it is derived from the ids on the device (``finish_on_device``)."""
     text_batch, visual_batch, speech_batch, attention_batch = batch[0], batch[1], batch[2], batch[3]
-    text_ids, twv_ids, tws_ids = (_to_dev(x, device) for x in (text_batch[0], visual_batch[0], speech_batch[0]))
+    t = _as_tensor
+    return dict(
+        input_ids=(t(text_batch[0]), t(visual_batch[1]), t(speech_batch[1]), t(visual_batch[0]), t(speech_batch[0])),
+        token_type_ids=(t(text_batch[2]), t(visual_batch[3]), t(speech_batch[3])),
+        attention_mask=(t(text_batch[3]), (t(attention_batch[0]), t(visual_batch[4])), (t(attention_batch[1]), t(speech_batch[4]))),
+        ap_label=(t(visual_batch[2]), t(speech_batch[2])),
+        sentiment=t(text_batch[-1]),
+    )
+
+
+def compact_host(kw):
+    """Shrinks what crosses PCIe without changing a bit of the result (second half):
+
+    * frames float64 -> float32: the first thing the reference does with them is ``pair_ids.float()``
+      (MMBertEmbedding.py:62), so the rounding is the same one, done on the host instead of the device;
+    * frame attention masks [B,L,D] -> their feature-0 column [B,L]: the only part the reference reads
+      (MMBertForPretraining.py:74-77 ``torch.narrow(attention_mask, 2, 0, 1)``); collate builds the mask as
+      ``frames != 0`` in float64 / int64 (model_utils.py:124-125,132-133) — 8 bytes per FEATURE for one bit per frame.
+
+    MOSEI-unaligned, B=64: 56.6 MB -> 14.2 MB per step."""
+    ids_t, vis, aud, ids_v, ids_s = kw["input_ids"]
+    m_t, (m_tv, m_v), (m_ts, m_s) = kw["attention_mask"]
+    f32 = lambda x: x if x.dtype == torch.float32 else x.to(torch.float32)
+    col0 = lambda m: m[:, :, 0].contiguous() if m.dim() == 3 else m
+    out = dict(kw)
+    out["input_ids"] = (ids_t, f32(vis), f32(aud), ids_v, ids_s)
+    out["attention_mask"] = (m_t, (m_tv, col0(m_v)), (m_ts, col0(m_s)))
+    return out
+
+
+def finish_on_device(kw, tokenizer=None, args=None):
+    """trainer.py:45-53 on device tensors: MLM masking of the three id tensors (in place — ``kw`` owns them) and the
+    label duplication ``cat((labels, labels), -1)``.  Returns ``kw`` with ``masked_labels`` added."""
+    text_ids, vis, aud, twv_ids, tws_ids = kw["input_ids"]
     if args is not None and getattr(args, "mlm", False):
-        # mask_tokens modifies its input in place (like the reference): work on device copies
-        text_ids, twv_ids, tws_ids = text_ids.clone(), twv_ids.clone(), tws_ids.clone()
         text_ids, text_lab = data.mask_tokens(text_ids, tokenizer, args)
         twv_ids, vis_lab = data.mask_tokens(twv_ids, tokenizer, args)
         tws_ids, sp_lab = data.mask_tokens(tws_ids, tokenizer, args)
     else:
         text_lab, vis_lab, sp_lab = text_ids, twv_ids, tws_ids                     # trainer.py:45-47, else branch
-    visual_inputs, speech_inputs = _to_dev(visual_batch[1], device), _to_dev(speech_batch[1], device)
-    vis_lab = torch.cat((vis_lab, vis_lab), dim=-1)                                  # trainer.py:50
-    sp_lab = torch.cat((sp_lab, sp_lab), dim=-1)                                     # trainer.py:53
-    return dict(
-        input_ids=(text_ids, visual_inputs, speech_inputs, twv_ids, tws_ids),
-        token_type_ids=(_to_dev(text_batch[2], device), _to_dev(visual_batch[3], device), _to_dev(speech_batch[3], device)),
-        attention_mask=(_to_dev(text_batch[3], device),
-                        (_to_dev(attention_batch[0], device), _to_dev(visual_batch[4], device)),
-                        (_to_dev(attention_batch[1], device), _to_dev(speech_batch[4], device))),
-        masked_labels=(text_lab, vis_lab, sp_lab),
-        ap_label=(_to_dev(visual_batch[2], device), _to_dev(speech_batch[2], device)),
-        sentiment=_to_dev(text_batch[-1], device),
-    )
+    out = dict(kw)
+    out["input_ids"] = (text_ids, vis, aud, twv_ids, tws_ids)
+    out["masked_labels"] = (text_lab, torch.cat((vis_lab, vis_lab), dim=-1),        # trainer.py:50
+                            torch.cat((sp_lab, sp_lab), dim=-1))                    # trainer.py:53
+    return out
+
+
+def unpack_batch(batch, device, tokenizer=None, args=None):
+    """trainer.py:41-64 in one call (no prefetching): collate output -> keyword arguments of
+    MMBertForPretraining.forward with every tensor on ``device``."""
+    device = torch.device(device)
+    kw = compact_host(unpack_host(batch))
+    kw = _tree_like(kw, lambda t: t.to(device, non_blocking=True))
+    if args is not None and getattr(args, "mlm", False):
+        # mask_tokens modifies its input in place (like the reference): twv / tws may alias the text ids
+        ids = kw["input_ids"]
+        kw["input_ids"] = (ids[0].clone(), ids[1], ids[2], ids[3].clone(), ids[4].clone())
+    return finish_on_device(kw, tokenizer, args)
 
 
 def _world():
@@ -191,7 +252,7 @@ def _world():
 
 
 def train_epoch(args, model, traindata, optimizer, scheduler, tokenizer, *, collate_fn=None, device=None,
-                faithful_stepping=True, epoch=0):
+                faithful_stepping=True, epoch=0, sampler_shuffle=True):
     """One process per GPU (``torch.distributed`` initialised, world size > 1): every rank draws its own shard of a
     common shuffle (``DistributedSampler`` seeded by ``epoch``; ``args.train_batch_size`` is per rank), gradients are
     reduced by the model's ``GradReducer`` as usual, and the returned loss averages are over all ranks' batches (one
@@ -199,21 +260,33 @@ def train_epoch(args, model, traindata, optimizer, scheduler, tokenizer, *, coll
     if collate_fn is None:
         import model_utils                      # the reference's module (on PYTHONPATH in the drop-in setting)
         collate_fn = model_utils.collate
-    if device is None:
-        device = next(model.parameters()).device
+    device = torch.device(next(model.parameters()).device if device is None else device)
     world = _world()
     if world > 1:
         from torch.utils.data.distributed import DistributedSampler
         sampler = DistributedSampler(traindata, shuffle=True, drop_last=False)
         sampler.set_epoch(epoch)
-    else:
+    elif sampler_shuffle:
         sampler = RandomSampler(traindata)
+    else:                                   # tests / experiments that fix the batch order themselves
+        from torch.utils.data import SequentialSampler
+        sampler = SequentialSampler(traindata)
     loader = DataLoader(traindata, sampler=sampler, batch_size=args.train_batch_size, collate_fn=collate_fn)
     sums = torch.zeros(5, device=device, dtype=torch.float64)      # train, text, visual, speech, label
     n, ap_last = 0, None
     model.train()
-    for step, batch in enumerate(loader):
-        outputs, _ = model(**unpack_batch(batch, device, tokenizer, args))
+    accum = args.gradient_accumulation_step
+    reducer = getattr(model, "_reducer", None)
+    if device.type == "cuda":
+        # pageable collate output -> reused pinned buffers -> copy stream, one batch ahead of the compute stream
+        batches = DevicePrefetcher((compact_host(unpack_host(b)) for b in loader), device, stage=True)
+    else:
+        batches = (compact_host(unpack_host(b)) for b in loader)
+    for step, kw in enumerate(batches):
+        do_step = ((step + 1) & accum) == 0 if faithful_stepping else ((step + 1) % accum) == 0
+        if reducer is not None:
+            reducer.sync = do_step                                 # accumulate locally until the stepping backward
+        outputs, _ = model(**finish_on_device(kw, tokenizer, args))
         loss = outputs[0]
         loss.mean().backward()
         with torch.no_grad():
@@ -224,12 +297,12 @@ def train_epoch(args, model, traindata, optimizer, scheduler, tokenizer, *, coll
             sums[4] += outputs[5].detach().mean()
             ap_last = outputs[4]
         n += 1
-        accum = args.gradient_accumulation_step
-        do_step = ((step + 1) & accum) == 0 if faithful_stepping else ((step + 1) % accum) == 0
         if do_step:
             optimizer.step()
             scheduler.step()
             optimizer.zero_grad()
+    if reducer is not None:
+        reducer.sync = True
     if n == 0:
         raise ValueError("empty training set")
     if world > 1:
@@ -267,8 +340,8 @@ def eval_epoch(args, model, valDataset, tokenizer, *, collate_fn=None, device=No
                     sums[i] += outputs[i].mean()
             sums[4] += outputs[5].mean()
             ap_last = outputs[4]
-            preds.append(logits.detach().float())
-            labels.append(kw["sentiment"].detach())
+            preds.append(logits.detach().float().clone())      # never an alias of a buffer the next batch overwrites
+            labels.append(kw["sentiment"].detach().clone())
             n += 1
     if n == 0:
         raise ValueError("empty validation set")

@@ -10,9 +10,11 @@ from msa_b200.params import seeded_state_dict
 from oracle import mmbert_oracle as O
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN = ("tiny_mosi_aligned", "tiny_mosei_unaligned")
-# further fixtures that (so far) pin the CPU oracle only: UR-FUNNY's wide frame dims, a one-sample batch
-GOLDEN_ORACLE_ONLY = ("tiny_ur_funny", "tiny_mosi_single")
+# four fixtures generated from the unmodified reference (tests/golden/make_golden.py): MOSI-aligned, MOSEI-unaligned,
+# UR-FUNNY's wide frame dims (371 / 81) and a one-sample batch (the in-batch CPC terms degenerate to 0).  All four pin
+# the CPU oracle AND are GPU parity cases.
+GOLDEN = ("tiny_mosi_aligned", "tiny_mosei_unaligned", "tiny_ur_funny", "tiny_mosi_single")
+GOLDEN_ORACLE_ONLY = ()
 OUT_NAMES = ("joint_loss", None, None, None, "ap_loss", "label_loss", "nce", "pred_t", "rel_t", "pred_v",
              "align_v", "pred_s", "align_s")
 

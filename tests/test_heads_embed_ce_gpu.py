@@ -80,7 +80,11 @@ def test_heads_forward_backward_exact(num_labels):
 
 
 def test_embeddings_forward_exact_and_backward():
-    """x0 of the CUDA path vs BertEmbeddings + JointEmbeddings restated in torch (oracle.bert_pass with 0 layers)."""
+    """x0 of the CUDA path vs BertEmbeddings + JointEmbeddings restated in torch (oracle.bert_pass with 0 layers), at
+    UR-FUNNY's frame dims (371 / 81: the padded-leading-dimension tensor-core projection wgrad), forward AND backward:
+    mmb_embed_bwd is run alone on a known upstream gradient and every gradient it produces is compared with autograd
+    through the restatement (word / position / token-type tables, both LayerNorms, Wv / Ws and their biases)."""
+    from msa_b200.engine import Plan
     shape = _small_shape()
     shape.num_hidden_layers = 1
     sd = seeded_state_dict(shape, "ur_funny", seed=22)
@@ -91,15 +95,39 @@ def test_embeddings_forward_exact_and_backward():
     m(**synth.tree_to(batch, "cuda"))
     plan = next(iter(m._plans.values()))
     ocfg = O.Cfg(128, 0, 2, 256, 300, 64)
+    names = ("bert.embeddings.word_embeddings.weight", "bert.embeddings.position_embeddings.weight",
+             "bert.embeddings.token_type_embeddings.weight", "bert.embeddings.LayerNorm.weight", "bert.embeddings.LayerNorm.bias",
+             "bert.jointEmbeddings.LayerNorm.weight", "bert.jointEmbeddings.LayerNorm.bias",
+             "bert.jointEmbeddings.Wv.weight", "bert.jointEmbeddings.Wv.bias",
+             "bert.jointEmbeddings.Ws.weight", "bert.jointEmbeddings.Ws.bias")
     sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    for n in names:
+        sd64[n] = sd64[n].clone().requires_grad_(True)
     ids_t, vis, aud, ids_v, ids_s = batch["input_ids"]
     m_t, (m_tv, m_v), (m_ts, m_s) = batch["attention_mask"]
     ref = torch.cat([O.bert_pass(sd64, ocfg, ids_t, m_t, batch["token_type_ids"][0])[0].reshape(-1, 128),
                      O.bert_pass(sd64, ocfg, ids_v, m_tv, None, vis, m_v)[0].reshape(-1, 128),
                      O.bert_pass(sd64, ocfg, ids_s, m_ts, None, aud, m_s)[0].reshape(-1, 128)])
     # fp32 residual-stream copy: only the bf16 rounding of the frame projection separates it from the oracle
-    assert rel_err(plan.x32[0], ref) < 6e-3
-    assert rel_err(plan.x[0].float(), ref) < 8e-3
+    assert rel_err(plan.x32[0], ref.detach()) < 6e-3
+    assert rel_err(plan.x[0].float(), ref.detach()) < 8e-3
+    # ---- backward: dL/dx0 = g (bf16 part) + g32 (fp32 residual-stream part)
+    torch.manual_seed(7)
+    g = torch.randn(plan.M, 128, device="cuda").to(torch.bfloat16)
+    g32 = torch.randn(plan.M, 128, device="cuda") * 0.5
+    m._prepare_grads()
+    m._store.grad.zero_()
+    plan.GA.copy_(g)
+    plan.GB.copy_(g32)
+    Plan.run([plan.bwd[-1]])                        # mmb_embed_bwd alone
+    torch.cuda.synchronize()
+    (ref * (g.float() + g32).cpu().double()).sum().backward()
+    named = dict(m.named_parameters())
+    for n in names:
+        want = sd64[n].grad
+        tol = 2e-2 if n.endswith(("Wv.weight", "Ws.weight")) else 1e-2     # projection wgrad: bf16 frames x bf16 dpre
+        assert rel_err(named[n].grad, want, floor=1e-6) < tol, (n, rel_err(named[n].grad, want, floor=1e-6))
+    assert float(named["bert.embeddings.word_embeddings.weight"].grad[0].abs().max()) == 0.0     # padding_idx row
 
 
 def test_vocab_cross_entropy_exact():

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     assert len(capi.DECLARED_FUNCTIONS) >= 20
     for name in capi.DECLARED_FUNCTIONS:
         assert hasattr(L, name), name
-    assert L.mmb_version() == 101
+    assert L.mmb_version() == 200
     assert capi.launch_count() >= 0
 
 
@@ -189,6 +189,22 @@ def _ddp_worker(rank, world, port, q):
         red.reduce_bucket(ranges)
     red.finish()
     ok = bool((st.grad[:st.trainable_end] == sum(range(1, world + 1))).all()) and bool((st.grad[st.trainable_end:] == -7.0).all())
+    # gradient accumulation: two micro-batches accumulate into the buffer the in-place SUM all-reduce works on; only the
+    # backward that precedes optimizer.step() may reduce (no_sync on the first), else micro-batch 1 counts world times
+    st.grad.zero_()
+    g1, g2 = float(rank + 1), 10.0 * (rank + 1)
+    with red.no_sync():
+        st.grad[:st.trainable_end] += g1
+        for _, ranges in red.sched:
+            red.reduce_bucket(ranges)
+        red.finish()
+    ok = ok and bool((st.grad[:st.trainable_end] == g1).all())                       # nothing was communicated
+    st.grad[:st.trainable_end] += g2
+    for _, ranges in red.sched:
+        red.reduce_bucket(ranges)
+    red.finish()
+    want = sum((r + 1) + 10.0 * (r + 1) for r in range(world))                       # sum over ranks of (g1 + g2)
+    ok = ok and bool((st.grad[:st.trainable_end] == want).all())
     q.put((rank, ok, red.bytes_per_step))
     dist.destroy_process_group()
 

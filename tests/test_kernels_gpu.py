@@ -281,6 +281,43 @@ def test_attention_dropout_forward_backward_use_the_same_mask():
     assert _rel(dV, Pd.t() @ dctx.float()) < 2e-2
 
 
+@pytest.mark.parametrize("p", [0.1, 0.5])
+def test_attention_dropout_mask_is_the_documented_generator(p):
+    """V = identity makes ctx the dropped probability matrix itself, so its zero pattern IS the kernel's mask: it must be
+    bit for bit the mask of the counter-based generator restated in oracle/dropout_rng.py (whose joint statistics —
+    pairs, 2 x 2 minors — are tested on > 10^6 samples in tests/test_dropout_rng.py), for every (sequence, head) of a
+    packed batch, and the backward must use the same mask (dV = (P o mask / (1-p))^T dO)."""
+    import numpy as np
+    from msa_b200 import capi
+    from oracle import dropout_rng as R
+    torch.manual_seed(31)
+    nh, S, nseq, seed, stream = 4, 64, 5, 2 ** 40 + 17, (7 << 8) | 1
+    H, rows = nh * 64, nseq * S
+    qkv = _bf(torch.randn(rows, 3 * H, device="cuda") * 0.3)
+    eye = torch.eye(S, device="cuda").to(torch.bfloat16)
+    for h in range(nh):
+        qkv[:, 2 * H + h * 64:2 * H + (h + 1) * 64] = eye.repeat(nseq, 1)
+    keybias = torch.zeros(rows, device="cuda")
+    cu_t = torch.arange(0, rows + 1, S, device="cuda", dtype=torch.int32)
+    ctx = torch.empty(rows, H, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(nh, rows, device="cuda")
+    dctx = _bf(torch.randn(rows, H, device="cuda"))
+    dqkv = torch.zeros(rows, 3 * H, device="cuda", dtype=torch.bfloat16)
+    a = capi.attn_args(qkv, ctx, lse, keybias, cu_t, H, nh, S, p_drop=p, seed=seed, rng_stream=stream, dctx=dctx, dqkv=dqkv,
+                       bwd_ws=capi.attn_bwd_workspace(rows, nh, "cuda"))
+    capi.call("attn_fwd", a)
+    capi.call("attn_bwd", a)
+    Pd = ctx.float().view(nseq, S, nh, 64)                # [seq, q, head, k]
+    for i in range(nseq):
+        for h in range(nh):
+            ids = h * rows + i * S + np.arange(S)
+            want = torch.from_numpy(R.attn_keep_mask(seed, stream, ids, ids, p)).cuda()
+            got = Pd[i, :, h, :] != 0
+            assert torch.equal(got, want), (i, h, int((got != want).sum()))
+            dV = dqkv[i * S:(i + 1) * S, 2 * H + h * 64:2 * H + (h + 1) * 64].float()
+            assert _rel(dV, Pd[i, :, h, :].t() @ dctx[i * S:(i + 1) * S, h * 64:(h + 1) * 64].float()) < 2e-2
+
+
 def test_attention_masked_tail_skipping_is_exact():
     """kv_end lets the kernels skip whole key tiles behind the last unmasked key; results must be identical to the
     full computation (forward context / LSE and all three gradients)."""

@@ -71,6 +71,14 @@ def test_train_epoch_matches_the_reference_loop():
     assert abs(out[0] - tl / nb) < 1e-9 and abs(out[5] - ll / nb) < 1e-9
     assert out[1] == out[2] == out[3] == 0.0
     assert torch.allclose(out[4], ap_last / nb)                    # the reference's "last ap_loss / steps" quirk
+    # a data-parallel model (GradReducer attached): gradients are exchanged only by the backward that precedes
+    # optimizer.step(); the micro-batches in between accumulate locally
+    model3 = _FakeModel()
+    model3._reducer = types.SimpleNamespace(sync=True)
+    seen = []
+    model3.register_forward_pre_hook(lambda m, a: seen.append(m._reducer.sync))
+    trainer_fast.train_epoch(args, model3, data, _Opt(), _Opt(), None, collate_fn=_collate, device=torch.device("cpu"))
+    assert seen == [False, True, False, True, False] and model3._reducer.sync is True
     # modulo stepping on request
     model2, opt2 = _FakeModel(), _Opt()
     trainer_fast.train_epoch(args, model2, data, opt2, _Opt(), None, collate_fn=_collate, device=torch.device("cpu"),
