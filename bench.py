@@ -1,21 +1,29 @@
 """bench.py — MMBert train samples/sec on B200 (BASELINE.json metric), one JSON line on rank 0.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference] [--mode train|infer-sweep]
 
 A "step" is one pass of the hot path over one synthetic batch: packed 3-pass forward, backward, (N>1) gradient
 all-reduce over NCCL overlapped with backward, fused AdamW.  One "sample" = one dataset item = the reference's
-three encoder passes.  Default workload = BASELINE.json configs[1]: MOSI-aligned shape
-(text 50 + audio 50x74 + visual 50x47), batch 64 per GPU, bert-base, bf16 GEMMs with fp32 master weights.
+three encoder passes.  Default workload = the configuration BASELINE.json's targets are quoted on
+(configs[2], it fits one GPU): CMU-MOSEI unaligned shape (text 50 + audio 500x74 + visual 500x35), batch 64 per GPU,
+bert-base, bf16 GEMMs with fp32 master weights.  --workload mosi_aligned_b64 (configs[1]) / ur_funny_b64 (configs[3]).
 
   value     whole-job samples/s with the inputs already resident in HBM (CUDA events, max over ranks)
-  e2e       the same through the public API with HOST inputs: pinned H2D copy of every step's tensors and a
-            D2H read of every step's loss inside the timed region, through the package's prefetching loop
-            (msa_b200.trainer_fast); e2e.blocking_value = the reference loop's copy / step / .item() pattern
-  roofline  dominant kernel = the tcgen05 GEMM: sum of algorithmic FLOPs of its launches / sum of their
-            CUDA-event durations inside a step, against MEASURED_PEAKS.json's sustained bf16 figure
-  cpu_baseline  the CPU oracle (a port of the reference's path, oracle/mmbert_oracle.py) on the host cores
+  e2e       the same through the public API with HOST inputs: H2D copy of every step's tensors and a D2H read of every
+            step's loss inside the timed region, through the package's prefetching loop (msa_b200.trainer_fast);
+            e2e.blocking_value = the reference loop's copy / step / .item() pattern
+  roofline  dominant kernel = the tcgen05 CTA-pair GEMM: frac = sum of algorithmic FLOPs of its launches / sum of their
+            CUDA-event durations inside a step, against MEASURED_PEAKS.json's sustained bf16 figure;
+            step_frac = the WHOLE step (value x algorithmic GFLOP per sample) against the same peak, step_frac_burst
+            against the burst figure
+  cpu_baseline        the reference's CPU path on the host cores (bounded sample; the live reference when $MSA_REF
+                      points at a checkout, else the oracle port)
+  gpu_torch_baseline  the same model as plain PyTorch on this GPU (fused torch ops: cuBLASLt / SDPA), fp32 TF32-off,
+                      TF32-on and autocast-bf16 — the bar the hand-written kernels have to beat
 
---impl reference times that CPU port alone on the same workload/config (bounded sample per step).
+--impl reference times the CPU reference alone (same workload / config, bounded sample per step, optimizer step included).
+--mode infer-sweep: BASELINE.json configs[4], forward-only batch 1-1024 x concatenated length 150-2048, one JSON line
+per point and a summary line.
 """
 import argparse
 import json
@@ -126,51 +134,255 @@ def profile_gemm(model, plan):
 
 def measured_traffic(workload_name):
     """DRAM bytes per GEMM launch measured under ncu for this workload (profiles/r1_gemm_traffic.json), or None."""
-    p = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
-    try:
-        d = json.load(open(p)).get(workload_name)
-        return None if d is None else float(d["traffic_bytes_per_launch"])
-    except (OSError, ValueError, KeyError):
-        return None
+    for tag in ("r2", "r1"):
+        p = os.path.join(ROOT, "profiles", f"{tag}_gemm_traffic.json")
+        try:
+            d = json.load(open(p)).get(workload_name)
+            if d is not None:
+                return float(d["traffic_bytes_per_launch"])
+        except (OSError, ValueError, KeyError):
+            continue
+    return None
 
 
-def cpu_baseline(shape, workload, batch=4, steps=2, warmup=1):
-    """Times the CPU oracle (port of the reference path, fp32, all host threads) on a bounded sample of the
-    workload: forward + backward of ``batch`` samples per step.  Returns samples/s."""
+def config_dict(workload, shape, world):
+    B = workload.batch
+    return {"workload": workload.name, "model": f"bert-base shape ({shape.num_hidden_layers} layers), random init",
+            "batch_per_gpu": B, "global_batch": B * world, "positions_per_sample": workload.positions,
+            "packed_rows_per_gpu": B * workload.positions, "parallelism": f"dp{world}",
+            "mlm": "dense (all positions, as the reference)", "optimizer": "AdamW (HF semantics)",
+            "l2": "no explicit flush: one training step streams GiBs of saved activations (>> 126 MB L2) and 4 distinct "
+                  "input batches are cycled"}
+
+
+class _HFAdamW:
+    """transformers(<=4.x).AdamW.step restated for a list of leaf tensors (train.py:76-92): the optimizer the reference
+    builds, so that the CPU reference arm times a whole training step like the GPU arm does."""
+
+    def __init__(self, named, lr=1e-5, b1=0.9, b2=0.999, eps=1e-6, wd=0.01):
+        self.named, self.lr, self.b1, self.b2, self.eps, self.wd, self.t = named, lr, b1, b2, eps, wd, 0
+        self.m = {k: torch.zeros_like(v) for k, v in named.items()}
+        self.v = {k: torch.zeros_like(v) for k, v in named.items()}
+
+    @torch.no_grad()
+    def step(self, grads):
+        self.t += 1
+        s = self.lr * (1 - self.b2 ** self.t) ** 0.5 / (1 - self.b1 ** self.t)
+        for k, p in self.named.items():
+            g = grads.get(k)
+            if g is None:
+                continue
+            self.m[k].mul_(self.b1).add_(g, alpha=1 - self.b1)
+            self.v[k].mul_(self.b2).addcmul_(g, g, value=1 - self.b2)
+            p.addcdiv_(self.m[k], self.v[k].sqrt().add_(self.eps), value=-s)
+            if not ("bias" in k or "LayerNorm.weight" in k):
+                p.mul_(1 - self.lr * self.wd)
+
+
+def _cpu_reference_step(shape, workload):
+    """Returns (kind, describe, step(batch) -> None): one CPU training step (forward, backward, AdamW) of the reference's
+    path in fp32 on all host threads — the UNMODIFIED reference when a checkout is reachable ($MSA_REF, default
+    /root/reference: the build container), else the oracle port (the GPU box: the reference is Python on top of
+    transformers, lives outside the repo and does not travel)."""
     from oracle import mmbert_oracle as O
+    from oracle import ref_loader
     from msa_b200.params import seeded_state_dict
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     ocfg = O.Cfg(shape.hidden_size, shape.num_hidden_layers, shape.num_attention_heads, shape.intermediate_size,
                  shape.vocab_size, shape.max_position_embeddings, shape.layer_norm_eps)
     sd = seeded_state_dict(ocfg, workload.dataset, seed=0, std=0.02)
+    if ref_loader.available():
+        from transformers import BertConfig
+        cfg = BertConfig(hidden_size=shape.hidden_size, num_hidden_layers=shape.num_hidden_layers,
+                         num_attention_heads=shape.num_attention_heads, intermediate_size=shape.intermediate_size,
+                         vocab_size=shape.vocab_size, max_position_embeddings=shape.max_position_embeddings)
+        model = ref_loader.build_model(cfg, workload.dataset, eager=False).train()
+        model.load_state_dict(sd, strict=False)
+        named = {k: p for k, p in model.named_parameters()}
+        opt = _HFAdamW({k: p.data for k, p in named.items()})
+
+        def step(batch):
+            out, _ = model(**batch)
+            out[0].mean().backward()
+            opt.step({k: p.grad for k, p in named.items()})
+            for p in named.values():
+                p.grad = None
+
+        return "reference", f"unmodified reference ({ref_loader.REF_DIR}) forward + backward + AdamW, dropout on", step
+    params = {k: v.float().clone() for k, v in sd.items() if k not in O.TIED}
+    opt = _HFAdamW(params)
+    drop = O.Dropout(0.1, 0.1, 0.5, seed=0)
+
+    def step(batch):
+        full = dict(params)
+        for alias, canon in O.TIED.items():
+            full[alias] = params[canon]
+        _, _, grads = O.forward_backward(full, ocfg, batch, dtype=torch.float32, dropout=drop)
+        opt.step(grads)
+
+    return "port", "oracle/mmbert_oracle.py forward + backward + AdamW (HF rule), dropout on", step
+
+
+def cpu_baseline(shape, workload, steps=2, warmup=1, batch=None, target_s=4.0):
+    """Times the CPU reference on a BOUNDED sample of the workload: ``batch`` samples per step, chosen from a one-sample
+    probe so that a step takes about ``target_s`` seconds.  Returns (cpu_baseline dict, seconds per step)."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kind, what, step = _cpu_reference_step(shape, workload)
+    probe = None
+    if batch is None:
+        t0 = time.perf_counter()
+        step(synth.make_workload_batch(workload, seed=1233, batch=1))
+        probe = time.perf_counter() - t0
+        batch = max(1, min(8, int(target_s / probe)))
     data = synth.make_workload_batch(workload, seed=1234, batch=batch)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.forward_backward(sd, ocfg, data, dtype=torch.float32)
+        step(data)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
-    return dict(value=batch / sec, unit=UNIT, cores=cores, kind="port",
-                sample=f"oracle/mmbert_oracle.py fwd+bwd fp32, {batch} samples/step x {steps} steps (+{warmup} warm-up), "
-                       f"torch {torch.get_num_threads()} threads; no optimizer step"), sec
+    return dict(value=batch / sec, unit=UNIT, cores=cores, kind=kind,
+                sample=f"{what}; fp32, {torch.get_num_threads()} torch threads; {batch} of the workload's {workload.batch} "
+                       f"samples per step x {steps} steps (+{warmup} warm-up"
+                       + (f", batch chosen from a {probe:.1f} s one-sample probe" if probe else "") + ")"), sec
 
 
 def run_reference(args, workload, shape):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, sec = cpu_baseline(shape, workload, batch=args.cpu_batch, steps=args.steps, warmup=args.warmup)
+    base, sec = cpu_baseline(shape, workload, steps=args.steps, warmup=args.warmup, batch=args.cpu_batch)
     line = {"metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": workload.name, "model": "bert-base shape, random init",
-                       "sample_batch": args.cpu_batch, "positions_per_sample": workload.positions},
+            "config": config_dict(workload, shape, 1),
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def gpu_torch_baseline(shape, workload, device, steps=3, warmup=2):
+    """The same model as plain PyTorch on THIS GPU (oracle/torch_baseline.py: F.linear / SDPA / F.layer_norm / F.gelu /
+    F.cross_entropy, dropout on, torch.optim.AdamW(fused=True)): one training step at the workload's batch in fp32 with
+    TF32 off, TF32 on, and under torch.autocast(bfloat16).  Halves the batch on out-of-memory.  Returns a dict."""
+    from oracle import mmbert_oracle as O
+    from oracle import torch_baseline as TB
+    from msa_b200.params import seeded_state_dict
+    ocfg = O.Cfg(shape.hidden_size, shape.num_hidden_layers, shape.num_attention_heads, shape.intermediate_size,
+                 shape.vocab_size, shape.max_position_embeddings, shape.layer_norm_eps)
+    sd = seeded_state_dict(ocfg, workload.dataset, seed=0, std=0.02)
+    params = {k: v.to(device).requires_grad_(True) for k, v in sd.items() if k not in O.TIED}
+    opt = torch.optim.AdamW(list(params.values()), lr=1e-5, eps=1e-6, weight_decay=0.01, fused=True)
+    full = dict(params)
+    for alias, canon in O.TIED.items():
+        full[alias] = params[canon]
+    out = {"kind": "port", "what": "oracle/torch_baseline.py: the reference's path on torch's fused ops (cuBLASLt GEMMs, "
+                                   "scaled_dot_product_attention, fused LayerNorm / GELU / cross entropy / dropout), "
+                                   "forward + backward + torch.optim.AdamW(fused=True)", "unit": UNIT, "steps": steps}
+    old_tf32 = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+
+    def run(mode, B):
+        batch = synth.tree_to(synth.make_workload_batch(workload, seed=1234, batch=B), device)
+        tf32 = mode != "fp32"
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(warmup + steps):
+            if i == warmup:
+                torch.cuda.synchronize()
+                ev0.record()
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "autocast_bf16")):
+                o, _ = TB.forward(full, ocfg, training=True, **batch)
+            o[0].backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        return B * steps / (ev0.elapsed_time(ev1) / 1e3)
+
+    try:
+        for mode in ("autocast_bf16", "tf32", "fp32"):
+            B = workload.batch
+            while True:
+                try:
+                    out[mode] = {"value": run(mode, B), "batch": B}
+                    break
+                except torch.OutOfMemoryError:
+                    torch.cuda.empty_cache()
+                    if B == 1:
+                        out[mode] = {"error": "out of memory at batch 1"}
+                        break
+                    B //= 2
+    except Exception as e:                                  # a baseline must never take the bench line down
+        out["error"] = f"{type(e).__name__}: {e}"[:300]
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old_tf32
+    return out
+
+
+def infer_sweep(args, shape, device):
+    """BASELINE.json configs[4]: forward-only (eval, no_grad) sweep, batch 1-1024 x concatenated length 150-2048 (T = 50
+    text tokens, Lv = La = (S - 50) / 2 frames), MOSI feature dims, one B200; CUDA-graph replay of the launch plan.
+    The CPU reference is timed beside the smallest length (bounded: batch 1 and 4)."""
+    lines = []
+    model = None
+    free_gb = torch.cuda.mem_get_info(device)[0] / 2 ** 30
+    for S in [int(x) for x in args.lengths.split(",")]:
+        T, L = 50, (S - 50) // 2
+        for B in [int(x) for x in args.batches.split(",")]:
+            rows = B * (3 * T + 2 * L)
+            per_row = 768 * 40 + 3072 * 4 + (30528 * 2 if args.materialize_logits else 0)
+            est = rows * per_row / 2 ** 30
+            if est > 0.8 * free_gb:
+                lines.append({"batch": B, "concat_len": S, "skipped": f"needs ~{est:.0f} GiB"})
+                print(json.dumps(lines[-1]), flush=True)
+                continue
+            w = synth.Workload(f"infer_b{B}_s{S}", "mosi", T, L, L, B)
+            if model is None:
+                model = build_model(shape, w, device).eval()
+                model.materialize_logits = bool(args.materialize_logits)
+                model.use_cuda_graph = not args.no_cuda_graph
+                model._ensure_store(device)
+            model._plans.clear()
+            torch.cuda.empty_cache()
+            batch = synth.tree_to(synth.make_workload_batch(w, seed=7), device)
+            with torch.no_grad():
+                for _ in range(3):
+                    model(**batch)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.reps):
+                    model(**batch)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.reps
+            lines.append({"batch": B, "concat_len": S, "encoder_positions_per_sample": 3 * T + 2 * L, "ms": round(ms, 3),
+                          "samples_per_s": round(B / ms * 1e3, 1)})
+            print(json.dumps(lines[-1]), flush=True)
+    cpu = []
+    if not args.no_cpu_baseline:
+        from oracle import mmbert_oracle as O
+        from msa_b200.params import seeded_state_dict
+        torch.set_num_threads(os.cpu_count() or 1)
+        ocfg = O.Cfg(num_hidden_layers=shape.num_hidden_layers)
+        sd = {k: v for k, v in seeded_state_dict(ocfg, "mosi", seed=0, std=0.02).items()}
+        S0 = int(args.lengths.split(",")[0])
+        for B in (1, 4):
+            w = synth.Workload(f"infer_b{B}_s{S0}", "mosi", 50, (S0 - 50) // 2, (S0 - 50) // 2, B)
+            b = synth.make_workload_batch(w, seed=7)
+            with torch.no_grad():
+                O.forward(sd, ocfg, dtype=torch.float32, **b)
+                t0 = time.perf_counter()
+                O.forward(sd, ocfg, dtype=torch.float32, **b)
+                sec = time.perf_counter() - t0
+            cpu.append({"batch": B, "concat_len": S0, "ms": round(sec * 1e3, 1), "samples_per_s": round(B / sec, 2),
+                        "cores": os.cpu_count(), "kind": "port", "what": "oracle forward, fp32, all host threads"})
+    print(json.dumps({"mode": "infer-sweep", "metric": "mmbert_forward_samples_per_sec", "unit": UNIT, "dtype": "bf16",
+                      "cuda_graph": not args.no_cuda_graph, "materialize_logits": bool(args.materialize_logits),
+                      "points": lines, "cpu_reference": cpu}), flush=True)
 
 
 def main():
@@ -178,12 +390,22 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="mosi_aligned_b64", choices=sorted(synth.WORKLOADS))
+    ap.add_argument("--workload", default="mosei_unaligned_b64", choices=sorted(synth.WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="train", choices=["train", "infer-sweep"])
     ap.add_argument("--layers", type=int, default=12)
-    ap.add_argument("--cpu-batch", type=int, default=4)
+    ap.add_argument("--cpu-batch", type=int, default=None, help="samples per CPU-reference step (default: ~4 s per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-torch-baseline", action="store_true")
+    ap.add_argument("--batches", default="1,4,16,64,256,1024", help="infer-sweep")
+    ap.add_argument("--lengths", default="150,512,1024,2048", help="infer-sweep")
+    ap.add_argument("--reps", type=int, default=5, help="infer-sweep")
+    ap.add_argument("--materialize-logits", type=int, default=0, help="infer-sweep: keep the [rows, V] decoder output")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="infer-sweep: launch the plan kernel by kernel")
     ap.add_argument("--lr", type=float, default=1e-5)
+    ap.add_argument("--reserve-sms", type=int, default=None,
+                    help="N>1: SMs the persistent kernels leave to NCCL (default 4; MMB_RESERVE_SMS overrides)")
+    ap.add_argument("--nccl-ctas", type=int, default=None, help="N>1: NCCL_MAX_CTAS (default 4; 0 = NCCL's own choice)")
     args = ap.parse_args()
     workload = synth.WORKLOADS[args.workload]
     shape = BertShape(num_hidden_layers=args.layers)
@@ -200,11 +422,28 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    dp = {"reserved_sms": 0, "nccl_max_ctas": None}
     if world > 1:
+        # One gradient all-reduce per layer runs under the backward sweep.  Its bandwidth need is small (460 MB per step),
+        # but the persistent GEMM / attention kernels own every SM: an NCCL kernel then waits for a kernel boundary and the
+        # next persistent wave runs short of the SMs NCCL took.  So NCCL is capped to a few CTAs and the persistent kernels
+        # leave that many SMs free.
+        ctas = 4 if args.nccl_ctas is None else args.nccl_ctas
+        if ctas > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(ctas))
+        dp["nccl_max_ctas"] = os.environ.get("NCCL_MAX_CTAS")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
     capi.check(capi.lib().mmb_check_device(), "mmb_check_device")
+    if world > 1:
+        reserve = args.reserve_sms
+        if reserve is None:
+            reserve = int(os.environ.get("MMB_RESERVE_SMS", "4"))
+        capi.check(capi.lib().mmb_set_reserved_sms(int(reserve)), "mmb_set_reserved_sms")
+        dp["reserved_sms"] = int(reserve)
     peaks = load_peaks()
+    if args.mode == "infer-sweep":
+        return infer_sweep(args, shape, device)
 
     model = build_model(shape, workload, device)
     model._ensure_store(device)
@@ -252,11 +491,15 @@ def main():
     # ---------------- timed region 2: end to end from pinned host memory, every step's loss read on the host.
     # The loop a user of the package writes (msa_b200.trainer_fast): batch i+1 is copied on a copy stream while batch i
     # computes, and the loss of step i is read two steps later — every copy and every read is inside the timed region.
-    prefetch, reader = DevicePrefetcher(None, device), DeferredScalars(device)
+    # What crosses PCIe is the compact form (msa_b200.trainer_fast.compact_host: float32 frames, feature-0 column of the
+    # frame masks — bit-identical results); the compaction and the staging copy into reused pinned buffers run on the
+    # host INSIDE the timed region, as they do in train_epoch.
+    from msa_b200.trainer_fast import compact_host
+    prefetch, reader = DevicePrefetcher(None, device, stage=True), DeferredScalars(device)
 
     def pipelined(n):
         losses = []
-        prefetch.batches = (pinned[i % nb] for i in range(n))
+        prefetch.batches = (compact_host(host[i % nb]) for i in range(n))
         for dev_batch in prefetch:
             v = reader.push(step(dev_batch))
             if v is not None:
@@ -265,17 +508,19 @@ def main():
 
     pipelined(3)                                   # untimed: copy stream, the two device buffer sets, the pinned loss slots
     barrier()
+    h2d0 = prefetch.h2d_bytes
     t0 = time.perf_counter()
     losses = pipelined(args.steps)
     barrier()
     pipe_s = time.perf_counter() - t0
+    pipe_h2d = (prefetch.h2d_bytes - h2d0) // args.steps
     assert len(losses) == args.steps
     # ---------------- timed region 3: the same with the reference loop's blocking pattern (trainer.py:49-93): copy, step,
     # ``float(loss)`` — host and device take turns
     def blocking(n):
         for i in range(n):
             dev_batch = synth.tree_to(pinned[i % nb], device, non_blocking=True)
-            val = float(step(dev_batch))           # D2H read of the loss (trainer.py:85)
+            val = float(step(dev_batch).detach())  # D2H read of the loss (trainer.py:85)
         return val
 
     blocking(2)
@@ -302,38 +547,51 @@ def main():
         opt.zero_grad()
         achieved = flops / (gemm_ms / 1e3) / 1e12
         gf = train_gflop_per_sample(shape, workload)
-        act_bytes = sum(t.numel() * t.element_size() for L in plan.layers for t in L.values() if torch.is_tensor(t))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload.name, "model": f"bert-base shape ({shape.num_hidden_layers} layers), random init",
-                       "batch_per_gpu": B, "global_batch": B * world, "positions_per_sample": workload.positions,
-                       "packed_rows_per_gpu": B * workload.positions, "parallelism": f"dp{world}",
-                       "mlm": "dense (all positions, as the reference)", "optimizer": "fused AdamW (HF semantics)",
-                       "l2": f"no explicit flush: one step streams {act_bytes / 2**30:.1f} GiB of saved activations "
-                             f"(>> 126 MB L2) and 4 distinct input batches are cycled"},
+            "config": config_dict(workload, shape, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": synth.tree_bytes(host[0]), "d2h_bytes_per_step": 4,
+                    "h2d_bytes_per_step": int(pipe_h2d) if e2e_loop == "pipelined" else synth.tree_bytes(host[0]),
+                    "d2h_bytes_per_step": 4,
                     "loop": e2e_loop,
                     "pipelined_value": world * B * args.steps / (pipe_ms / 1e3),
-                    "pipelined_loop": "msa_b200.trainer_fast.DevicePrefetcher + DeferredScalars: pinned H2D copy of batch "
-                                      "i+1 on a copy stream under step i; every step's loss read on the host two steps late",
+                    "pipelined_h2d_bytes_per_step": int(pipe_h2d),
+                    "pipelined_loop": "msa_b200.trainer_fast: compact_host (float32 frames, feature-0 mask column) -> reused "
+                                      "pinned staging buffers -> H2D copy of batch i+1 on a copy stream under step i "
+                                      "(DevicePrefetcher); every step's loss read on the host two steps late (DeferredScalars)",
                     "blocking_value": world * B * args.steps / (blocking_ms / 1e3),
-                    "blocking_loop": "copy, step, float(loss) in turn, as trainer.py:49-93"},
+                    "blocking_h2d_bytes_per_step": synth.tree_bytes(host[0]),
+                    "blocking_loop": "copy the collate-format tensors, step, float(loss) in turn, as trainer.py:49-93"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peaks["tflops"],
+            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_2cta_kernel<8|16> (CTA-pair tcgen05 GEMM, csrc/gemm_tcgen05.cu)",
+                         "achieved": achieved, "peak": peaks["tflops"],
                          "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": measured_traffic(workload.name),
-                         "traffic_note": "DRAM read+write bytes per GEMM launch, averaged over the ~160 GEMM launches of one "
-                                         "step (ncu, profiles/r1_gemm_traffic.json); algorithmic_bytes = the same average "
+                         "traffic_note": "DRAM read+write bytes per GEMM launch, averaged over the GEMM launches of one "
+                                         "step (ncu, profiles/*_gemm_traffic.json); algorithmic_bytes = the same average "
                                          "computed from the launch shapes",
                          "algorithmic_bytes": gemm_bytes / n_gemm,
                          "peak_source": peaks["source"], "launches_per_step": n_gemm,
-                         "gemm_share_of_step": gemm_ms / (ms / args.steps)},
+                         "gemm_share_of_step": gemm_ms / (ms / args.steps),
+                         # the WHOLE step (every kernel, launch gaps, optimizer; dense-faithful FLOPs of SURVEY.md §8d)
+                         "step_achieved": value / world * gf / 1e3,
+                         "step_frac": value / world * gf / 1e3 / peaks["tflops"],
+                         "step_frac_burst": value / world * gf / 1e3 / peaks["burst"],
+                         "peak_burst": peaks["burst"], "train_gflop_per_sample": gf},
             "model_flops": {"train_gflop_per_sample": gf, "achieved_tflops_per_gpu": value / world * gf / 1e3,
                             "frac_of_peak": value / world * gf / 1e3 / peaks["tflops"]},
+            "dp": dp,
             "clocks": clocks, "final_loss": loss_val,
         }
+        if world == 1 and not args.no_gpu_torch_baseline:
+            model._plans.clear()                    # hand the activation buffers back before the PyTorch model runs
+            del plan
+            torch.cuda.empty_cache()
+            line["gpu_torch_baseline"] = gpu_torch_baseline(shape, workload, device)
+            ab = line["gpu_torch_baseline"].get("autocast_bf16", {}).get("value")
+            if ab:
+                line["gpu_torch_baseline"]["ours_over_autocast_bf16"] = value / ab
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _ = cpu_baseline(shape, workload, batch=args.cpu_batch, steps=2, warmup=1)
         print(json.dumps(line), flush=True)

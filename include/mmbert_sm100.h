@@ -43,6 +43,11 @@ int mmb_check_device(void);
 /* Number of CUDA kernels this library has launched in the calling process (monotonic; bench.py reports the
  * per-step difference as gpu_launches). */
 long long mmb_launch_count(void);
+/* Data-parallel runs (msa_b200/ddp.py; the reference has no distributed code): the persistent kernels (GEMM, attention:
+ * one CTA or CTA pair per SM) leave n SMs idle so that the concurrent NCCL all-reduce kernels start at once on free
+ * SMs instead of waiting for, and then delaying, a persistent wave.  0 (default; also the MMB_RESERVE_SMS environment
+ * variable) = use every SM.  Process-wide. */
+int mmb_set_reserved_sms(int n);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense bf16 GEMM on tcgen05 tensor cores (TMA -> smem ring -> tcgen05.mma -> TMEM -> epilogue).

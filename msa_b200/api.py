@@ -150,6 +150,8 @@ class MMBertForPretraining(_Node):
         self._reducer = None       # msa_b200.ddp.GradReducer once attached (train_epoch toggles its ``sync`` flag)
         self.launches = 0          # kernel-launching C calls issued so far (bench.py reports the per-step count)
         self.dense_mlm = True
+        # Forward-only (no_grad) calls on an eval() model replay the launch plan as one CUDA graph (engine.Plan.forward_graph).
+        self.use_cuda_graph = False
         # "bf16": tcgen05 tensor-core path (training and inference).  "fp32": validation path, forward only, fp32
         # storage and CUDA-core arithmetic (engine_f32.PlanF32) for the reference's 1e-4 fp32 tolerance.
         self.precision = "bf16"
@@ -289,7 +291,9 @@ class MMBertForPretraining(_Node):
                                     "of shape [B] (torch raises for a floating-point [B] target against [B, 1] logits)")
         plan = self._plan(B, T, Lv, La, dev, needs_grad)
         plan.set_loss_weights(self.alpha, self.beta, self.num_labels)
-        self._keep = plan.bind_inputs(input_ids, token_type_ids, attention_mask, masked_labels, ap_label, sentiment)
+        graph = self.use_cuda_graph and not needs_grad and not self.training and not fp32
+        if not graph:
+            self._keep = plan.bind_inputs(input_ids, token_type_ids, attention_mask, masked_labels, ap_label, sentiment)
         sig = self._signature()
         store.refresh_bf16(sig)
         if plan._frame_sig != sig:
@@ -300,6 +304,9 @@ class MMBertForPretraining(_Node):
         if needs_grad:
             anchor = self._params["classifier1_2.bias"]
             joint = _StepFn.apply(anchor, self, plan)
+        elif graph:
+            self.launches += plan.forward_graph(input_ids, token_type_ids, attention_mask, masked_labels, ap_label, sentiment)
+            joint = None
         else:                                   # no_grad, or the forward-only fp32 validation path
             Plan.run(plan.fwd)
             self.launches += len(plan.fwd)

@@ -570,7 +570,7 @@ int launch_pass(const CUtensorMap& q128, const CUtensorMap& q64, const CUtensorM
                 const CUtensorMap& aux64, const BwdTcParams& p, cudaStream_t stream) {
     MMB_ENSURE_SMEM(smem_bytes<kIsDq>(), attn_bwd_ws_kernel<kIsDq, kDrop>);
     const int items = p.tiles * p.nheads * p.nseq;
-    const int grid = items < num_sms() ? items : num_sms();
+    const int grid = items < persistent_sms() ? items : persistent_sms();
     attn_bwd_ws_kernel<kIsDq, kDrop><<<grid, kWsThreads, smem_bytes<kIsDq>(), stream>>>(q128, q64, dmap, aux128, aux64, p);
     return check_launch(kIsDq ? "attn_bwd_ws_kernel<dQ>" : "attn_bwd_ws_kernel<dKV>");
 }

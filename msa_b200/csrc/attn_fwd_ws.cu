@@ -463,7 +463,7 @@ template <bool kDrop>
 int launch(const CUtensorMap& q128, const CUtensorMap& q64, const FwParams& p, cudaStream_t stream) {
     MMB_ENSURE_SMEM(kFwSmem, attn_fwd_ws_kernel<kDrop>);
     const int items = p.tiles * p.nheads * p.nseq;
-    const int grid = items < num_sms() ? items : num_sms();
+    const int grid = items < persistent_sms() ? items : persistent_sms();
     attn_fwd_ws_kernel<kDrop><<<grid, kFwThreads, kFwSmem, stream>>>(q128, q64, p);
     return check_launch("attn_fwd_ws_kernel");
 }

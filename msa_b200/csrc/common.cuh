@@ -35,6 +35,7 @@ int check_launch(const char* what, int kernels = 1);  // MMB_OK / MMB_ECUDA afte
     } while (0)
 
 int num_sms();
+int persistent_sms();   // num_sms() minus the SMs reserved for concurrent collectives (mmb_set_reserved_sms)
 
 // Opt-in to more than 48 KB of dynamic shared memory.  The attribute is per device and must be set before the first
 // launch there: one flag word per call site, bit = device ordinal (mod 64).  Two threads racing only repeat the call.

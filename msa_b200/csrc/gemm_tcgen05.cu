@@ -919,7 +919,7 @@ static int launch_gemm(const mmb_gemm_args* a, cudaStream_t stream) {
     GemmParams p;
     fill_common(p, a, BM, BN);
     MMB_ENSURE_SMEM(Cfg::kSmemBytes, gemm_tcgen05_kernel<BN>);
-    const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    const int grid = p.total_tiles < persistent_sms() ? p.total_tiles : persistent_sms();
     gemm_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
     return check_launch("gemm_tcgen05_kernel");
 }
@@ -968,7 +968,7 @@ static int launch_gemm_2cta(const mmb_gemm_args* a, cudaStream_t stream) {
     fill_common(p, a, 256, 256);
     MMB_ENSURE_SMEM(Cfg2<8>::kSmemBytes, gemm_tcgen05_2cta_kernel<8>);
     MMB_ENSURE_SMEM(Cfg2<16>::kSmemBytes, gemm_tcgen05_2cta_kernel<16>);
-    const int pairs = num_sms() / 2;
+    const int pairs = persistent_sms() / 2;
     const int clusters = p.total_tiles < pairs ? p.total_tiles : pairs;
     // GELU epilogues are long latency chains: 16 epilogue warps; everything else: 8 (dbg bit 6 flips the choice, for A/B runs)
     bool wide = a->epilogue == MMB_EPI_GELU_BF16 || a->epilogue == MMB_EPI_GELU_GRAD_BF16;

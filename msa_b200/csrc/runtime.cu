@@ -1,5 +1,6 @@
 // Library-wide host plumbing: thread-local error string, device checks, version.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -39,8 +40,32 @@ int num_sms() {
     return n;
 }
 
+// SMs left free by the persistent kernels (one CTA / CTA pair per SM: GEMM, attention) so that a concurrent NCCL
+// kernel finds idle SMs instead of waiting for — and then delaying — a whole persistent wave.
+static std::atomic<int> g_reserved{-1};
+int persistent_sms() {
+    int r = g_reserved.load(std::memory_order_relaxed);
+    if (r < 0) {
+        const char* e = getenv("MMB_RESERVE_SMS");
+        r = e ? atoi(e) : 0;
+        if (r < 0) r = 0;
+        g_reserved.store(r, std::memory_order_relaxed);
+    }
+    int n = num_sms() - r;
+    n &= ~1;                      // CTA pairs
+    return n < 2 ? 2 : n;
+}
+
 }  // namespace mmb
 
+extern "C" int mmb_set_reserved_sms(int n) {
+    if (n < 0 || n > 64) {
+        mmb::set_last_error("mmb_set_reserved_sms: %d out of range [0, 64]", n);
+        return MMB_EINVAL;
+    }
+    mmb::g_reserved.store(n, std::memory_order_relaxed);
+    return MMB_OK;
+}
 extern "C" long long mmb_launch_count(void) { return mmb::g_launches.load(std::memory_order_relaxed); }
 extern "C" int mmb_version(void) { return MMB_VERSION; }
 extern "C" const char* mmb_last_error(void) { return mmb::g_err; }

@@ -326,18 +326,17 @@ class Plan:
         self.bwd = b
 
     # ------------------------------------------------------------------ per-step binding
-    def bind_inputs(self, input_ids, token_type_ids, attention_mask, masked_labels, ap_label, sentiment):
-        """Points the input-consuming launches at this step's tensors (device, contiguous; dtypes as the
-        reference's collate produces them).  Returns the list of tensors that must stay alive."""
+    def convert_inputs(self, input_ids, token_type_ids, attention_mask, masked_labels, ap_label, sentiment):
+        """The step's 16 input tensors on the plan's device, contiguous, in the dtypes the kernels read (dtypes of the
+        masks and frames are kept as the reference's collate produces them and passed as dtype codes), shape-checked.
+        Order: ids x3, token types, frames x2, text masks x3, frame masks x2, labels x3, ap labels x2, sentiment."""
         ids_t, vis, aud, ids_v, ids_s = input_ids
         m_t, (m_tv, m_v), (m_ts, m_s) = attention_mask
         lab_t, lab_v, lab_s = masked_labels
-        keep = []
 
         def dev(t, dtype=None):
             if t.device != self.device or (dtype is not None and t.dtype != dtype) or not t.is_contiguous():
                 t = t.to(device=self.device, dtype=dtype).contiguous()
-            keep.append(t)
             return t
 
         ids = [dev(ids_t, torch.int64), dev(ids_v, torch.int64), dev(ids_s, torch.int64)]
@@ -359,6 +358,11 @@ class Plan:
             # [B,L,D] as the reference's collate builds them (only feature 0 is read), or already [B,L] (:74-77)
             if tuple(t.shape) not in ((B, L, D), (B, L)):
                 raise capi.MMBError(f"frame attention mask must be [B, L, D] or [B, L], got {tuple(t.shape)}")
+        return ids + [tt] + frames + mt + mf + labs + ap + [sent]
+
+    def bind_tensors(self, ts):
+        """Points the input-consuming launches at the 16 tensors of ``convert_inputs``."""
+        ids, tt, frames, mt, mf, labs, ap, sent = ts[0:3], ts[3], ts[4:6], ts[6:9], ts[9:11], ts[11:14], ts[14:16], ts[16]
         capi.fill(self.pack_args, mask_text=mt, mask_text_dtype=[capi.dtype_code(t) for t in mt],
                   mask_frame=mf, mask_frame_dtype=[capi.dtype_code(t) for t in mf],
                   mask_frame_stride=[0 if t.dim() == 3 else 1 for t in mf], labels=labs)
@@ -366,7 +370,40 @@ class Plan:
                   frames_dtype=[capi.dtype_code(t) for t in frames])
         capi.fill(self.ce_args, labels=labs)
         capi.fill(self.heads_args, ap_label=ap, sentiment=sent)
+
+    def bind_inputs(self, input_ids, token_type_ids, attention_mask, masked_labels, ap_label, sentiment):
+        """Points the input-consuming launches at this step's tensors (device, contiguous; dtypes as the
+        reference's collate produces them).  Returns the list of tensors that must stay alive."""
+        keep = self.convert_inputs(input_ids, token_type_ids, attention_mask, masked_labels, ap_label, sentiment)
+        self.bind_tensors(keep)
         return keep
+
+    # ------------------------------------------------------------------ CUDA-graph replay (forward-only, dropout-free plans)
+    def forward_graph(self, input_ids, token_type_ids, attention_mask, masked_labels, ap_label, sentiment):
+        """Replays the whole forward plan as ONE CUDA graph (the C5 inference sweep at small batches is launch-bound:
+        ~190 launches for a 12-layer forward).  The graph reads fixed input buffers owned by the plan; each call copies
+        the step's tensors into them and replays.  Everything baked into the kernel arguments at capture time (loss
+        weights, input dtypes / layouts) is part of the capture key; a change re-captures."""
+        if self.training or max(self.p_hidden, self.p_attn, self.p_joint) > 0:
+            raise capi.MMBError("CUDA-graph replay is for forward-only, dropout-free plans (dropout seeds are kernel arguments)")
+        conv = self.convert_inputs(input_ids, token_type_ids, attention_mask, masked_labels, ap_label, sentiment)
+        key = (tuple((t.dtype, tuple(t.shape)) for t in conv), self.alpha, self.beta, self.num_labels)
+        if getattr(self, "_graph_key", None) != key:
+            self._graph_static = [torch.empty_like(t) for t in conv]
+            self.bind_tensors(self._graph_static)
+            for s, t in zip(self._graph_static, conv):
+                s.copy_(t)
+            Plan.run(self.fwd)                      # warm-up outside capture: function attributes, TMA descriptor cache
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                Plan.run(self.fwd)
+            self._graph, self._graph_key = g, key
+        else:
+            for s, t in zip(self._graph_static, conv):
+                s.copy_(t, non_blocking=True)
+        self._graph.replay()
+        return len(self.fwd)
 
     def set_seed(self, seed):
         for a in self._seeded:

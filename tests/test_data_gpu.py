@@ -124,6 +124,64 @@ def test_sync_free_train_epoch_on_the_cuda_model():
     assert not torch.equal(w0, m.classifier1_1.weight.detach())
 
 
+def test_eval_epoch_on_the_cuda_model_keeps_every_batch_predictions():
+    """trainer_fast.eval_epoch over THREE batches of the real model: the model's outputs live in buffers of a cached
+    launch plan that the next batch overwrites, so predictions must be handed out as copies — the collected [N, 1] array
+    must equal per-batch forward passes (an alias would repeat the last batch), and so must the loss averages."""
+    from msa_b200 import trainer_fast
+    from msa_b200.params import seeded_state_dict
+    from tests.test_model_gpu import _build
+    ocfg = O.Cfg(hidden_size=128, num_hidden_layers=1, num_attention_heads=2, intermediate_size=256, vocab_size=30522,
+                 max_position_embeddings=64)
+    sd = seeded_state_dict(ocfg, "mosi", seed=1, std=0.03)
+    m = _build(ocfg, "mosi", sd)
+    N, T, bs = 12, 16, 4
+    full = synth.make_batch(N, T, T, T, 47, 74, seed=4, min_len=6, mlm=False)
+
+    def collate(idx):
+        i = torch.tensor(idx)
+        ids, vis, aud = full["input_ids"][0][i], full["input_ids"][1][i], full["input_ids"][2][i]
+        m_t, (m_tv, m_v), (m_ts, m_s) = full["attention_mask"]
+        tt = full["token_type_ids"][0][i]
+        text = (ids, None, tt, m_t[i], full["sentiment"][i])
+        visual = (ids.clone(), vis, full["ap_label"][0][i], tt, m_v[i], None)
+        speech = (ids.clone(), aud, full["ap_label"][1][i], tt, m_s[i], None)
+        return text, visual, speech, (m_tv[i], m_ts[i]), None, None
+
+    args = types.SimpleNamespace(val_batch_size=bs, mlm=False, mlm_probability=0.15)
+    torch.manual_seed(5)
+    out = trainer_fast.eval_epoch(args, m, list(range(N)), _Tok(), collate_fn=collate)
+    preds, labels = out[6], out[7]
+    assert preds.shape == (N, 1) and labels.shape == (N,)
+    # direct evaluation, sample by sample lookup through the sentiment values (unique floats identify the sample)
+    m.eval()
+    want = {}
+    losses = []
+    with torch.no_grad():
+        for b0 in range(0, N, bs):
+            kw = trainer_fast.unpack_batch(collate(list(range(b0, b0 + bs))), "cuda", _Tok(), args)
+            o, lg = m(**kw)
+            for s_, l_ in zip(full["sentiment"][b0:b0 + bs].tolist(), lg.view(-1).tolist()):
+                want[round(s_, 6)] = l_
+    got = {round(float(s_), 6): float(p_) for s_, p_ in zip(labels, preds[:, 0])}
+    assert len(got) == N                                            # every sample once (no repeated last batch)
+    # batches are drawn in another order, so CPC's in-batch negatives differ; the regression head itself does not
+    # depend on the other samples of a batch
+    for k, v in want.items():
+        assert abs(got[k] - v) < 1e-4, (k, got[k], v)
+    assert len(set(round(v, 5) for v in got.values())) > N // 2     # not one value repeated
+
+
+def test_staged_prefetcher_reuses_pinned_buffers_for_pageable_batches():
+    from msa_b200.trainer_fast import DevicePrefetcher
+    batches = [{"x": torch.full((300, 33), float(i)), "y": (torch.arange(5) + i,)} for i in range(9)]
+    pf = DevicePrefetcher(iter(batches), "cuda", stage=True)
+    got = [(float(d["x"].mean()), int(d["y"][0][0])) for d in pf]
+    assert got == [(float(i), i) for i in range(9)]
+    assert pf.h2d_bytes == 9 * (300 * 33 * 4 + 5 * 8)
+    assert all(t.is_pinned() for t in (pf._pin[0]["x"], pf._pin[1]["x"], pf._pin[2]["x"]))
+
+
 def test_prefetcher_and_deferred_reads_deliver_every_batch_in_order():
     """DevicePrefetcher reuses two device buffer sets while copies run ahead on a copy stream: with a slow consumer
     every batch must still arrive intact and in order (a buffer overwritten early would show the next batch's values),

@@ -364,3 +364,66 @@ def test_sentiment_mae_after_k_steps_bert_base_width_with_dropout_and_reference_
     r = kstep.run(ocfg, "mosi", K=6, B=6, T=16, L=16, seeds=2, lr=5e-4)
     assert r["gap"] < 1e-2, r
     assert max(r["std_cuda"], r["std_oracle"]) < 2e-2, r
+
+
+def test_cuda_graph_replay_matches_launch_by_launch_forward():
+    """model.use_cuda_graph: a no_grad forward of an eval() model replays the whole launch plan as one CUDA graph reading
+    plan-owned input buffers; results must be bit-identical to the launch-by-launch forward, across different batches of
+    the same shape, and a changed loss weight must re-capture."""
+    recipe, _ = load_golden("tiny_mosei_unaligned")
+    ocfg, sd, batch = expand_recipe(recipe)
+    dv, da = synth.DATASET_DIMS[recipe["dataset"]]
+    batch2 = synth.make_batch(recipe["B"], recipe["T"], recipe["Lv"], recipe["La"], dv, da, vocab_size=ocfg.vocab_size,
+                              seed=99, min_len=recipe["min_len"])
+    m = _build(ocfg, recipe["dataset"], sd).eval()
+    ref = []
+    with torch.no_grad():
+        for b in (batch, batch2):
+            out, logits = m(**synth.tree_to(b, "cuda"))
+            ref.append(([None if o is None else o.clone() for o in out], logits.clone()))
+        m.use_cuda_graph = True
+        for rep in range(2):
+            for b, (ro, rl) in zip((batch, batch2), ref):
+                out, logits = m(**synth.tree_to(b, "cuda"))
+                assert torch.equal(logits, rl)
+                for a, c in zip(out, ro):
+                    assert (a is None) == (c is None)
+                    if a is not None:
+                        assert torch.equal(a, c)
+        plan = next(iter(m._plans.values()))
+        g0 = plan._graph
+        m.set_alpha_beta(0.5, 2.0)
+        out, _ = m(**synth.tree_to(batch, "cuda"))
+        assert plan._graph is not g0
+        m.use_cuda_graph = False
+        out2, _ = m(**synth.tree_to(batch, "cuda"))
+        assert torch.equal(out[0], out2[0])
+
+
+def test_classification_branch_matches_the_reference_semantics():
+    """num_labels not in (1, 7): MMBertForPretraining.py:437-442 — CrossEntropyLoss on the [B, 1] classifier output
+    (classifier1_2 is always Linear(H, 1), :311-314).  With the only valid target (class 0) the label loss is 0, the
+    returned logits are argmax(sigmoid(.)) = 0 (int64), and the remaining losses / gradients are those of the oracle run
+    with the same setting; a floating-point sentiment raises, as torch does."""
+    from msa_b200 import capi
+    recipe, _ = load_golden("tiny_mosi_aligned")
+    ocfg, sd, batch = expand_recipe(recipe)
+    m = _build(ocfg, recipe["dataset"], sd).train()
+    m.num_labels = 3
+    dbatch = synth.tree_to(batch, "cuda")
+    with pytest.raises(capi.MMBError):
+        m(**dbatch)                                   # float sentiment
+    batch = dict(batch)
+    batch["sentiment"] = torch.zeros(recipe["B"], dtype=torch.int64)
+    out, logits = m(**synth.tree_to(batch, "cuda"))
+    out[0].backward()
+    import copy
+    c3 = copy.copy(ocfg)
+    c3.num_labels = 3
+    ref_out, ref_logits, ref_grads = O.forward_backward(sd, c3, batch)
+    assert logits.dtype == torch.int64 and tuple(logits.shape) == tuple(ref_logits.shape) and int(logits.abs().sum()) == 0
+    assert float(out[5]) == 0.0 and float(ref_out[5]) == 0.0
+    assert rel_err(out[0].detach().float(), ref_out[0].detach()) < TOL_OUT
+    _check_param_grads(m, ref_grads, NO_GRAD)
+    named = dict(m.named_parameters())
+    assert float(named["classifier1_2.weight"].grad.abs().max()) == 0.0        # no label gradient reaches it

@@ -65,3 +65,23 @@ def test_oracle_matches_live_reference_bert_base_shape():
         else:
             assert rel_err(a, b) < TOL
     assert rel_err(logits, ref_logits) < TOL
+
+
+def test_fused_torch_baseline_equals_the_oracle():
+    """oracle/torch_baseline.py (the port bench.py times on the GPU as the PyTorch / cuBLASLt / SDPA bar) is the same
+    arithmetic as the pinned oracle: fp64, eval mode, every output to 1e-12."""
+    from msa_b200 import synth
+    from msa_b200.params import seeded_state_dict
+    from oracle import torch_baseline as TB
+    cfg = O.Cfg(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256, vocab_size=512,
+                max_position_embeddings=64)
+    sd = seeded_state_dict(cfg, "mosei", seed=3, std=0.05)
+    batch = synth.make_batch(3, 10, 24, 17, 35, 74, vocab_size=512, seed=5, min_len=4)
+    with torch.no_grad():
+        o1, l1 = O.forward(sd, cfg, alpha=0.7, beta=0.3, **batch)
+        o2, l2 = TB.forward({k: v.double() for k, v in sd.items()}, cfg, alpha=0.7, beta=0.3, **batch)
+    for a, b in zip(o1, o2):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert rel_err(b, a) < 1e-12
+    assert rel_err(l2, l1) < 1e-12
