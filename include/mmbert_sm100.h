@@ -27,7 +27,8 @@
 extern "C" {
 #endif
 
-#define MMB_VERSION 200 /* round 2; 200: mmb_pack_args.mask_frame_stride */
+#define MMB_VERSION 201 /* round 2; 200: mmb_pack_args.mask_frame_stride; 201: MMB_EPI_CE_STATS, mmb_gemm_args.aux2,
+                           mmb_pack_args.row_label / vocab, mmb_ce_sparse_*, mmb_embed_args.err_count */
 
 enum mmb_status {
     MMB_OK = 0,
@@ -73,7 +74,15 @@ enum {
     MMB_EPI_GELU_GRAD_BF16 = 6, /* C(bf16) = gelu_erf(acc + bias); aux(bf16, out) = gelu_erf'(acc + bias): the
                                    forward of BertIntermediate saves the activation's derivative instead of the
                                    pre-activation, so that its backward is a plain multiply (next mode)   */
-    MMB_EPI_MUL_AUX_BF16 = 7    /* C(bf16) = acc * aux[m,n]; aux is an INPUT                           */
+    MMB_EPI_MUL_AUX_BF16 = 7,   /* C(bf16) = acc * aux[m,n]; aux is an INPUT                           */
+    MMB_EPI_CE_STATS = 8        /* tied-decoder GEMM fused with the masked-LM cross entropy: the [M,N] logits are NOT
+                                   written.  aux = int32 row_label[M] (vocabulary id or -100, from mmb_pack_prepare);
+                                   for every labelled row the epilogue keeps an online (max, sum exp) of acc + bias per
+                                   128-column group, the label's logit, and — if C != NULL — stores that row's logits
+                                   (bf16, row stride ldc) into C, which is the buffer mmb_ce_sparse_bwd turns into
+                                   dlogits in place.  aux2 = float workspace of mmb_ce_stats_floats(M, N) floats (planes
+                                   of M: max / sum per group, label logit, row-written flag; zero it once, the flag
+                                   plane must persist across steps).  Unlabelled rows cost no epilogue work.  N > 128. */
 };
 
 typedef struct mmb_gemm_args {
@@ -81,6 +90,7 @@ typedef struct mmb_gemm_args {
     const void* B;
     void* C;
     void* aux;         /* see epilogue; row stride = ldaux */
+    void* aux2;        /* MMB_EPI_CE_STATS workspace, else NULL */
     const float* bias; /* [N] f32 or NULL */
     int64_t lda, ldb, ldc, ldaux;
     int32_t M, N, K;
@@ -93,6 +103,8 @@ typedef struct mmb_gemm_args {
 } mmb_gemm_args;
 
 int mmb_gemm(const mmb_gemm_args* a, void* stream);
+/* floats of the MMB_EPI_CE_STATS workspace for an [M, N] decoder GEMM */
+size_t mmb_ce_stats_floats(int M, int N);
 
 /* ------------------------------------------------------------------------------------------------
  * dropout + residual + LayerNorm (warp-per-row, HBM-bound).
@@ -234,9 +246,14 @@ typedef struct mmb_pack_args {
     int32_t mask_frame_stride[2]; /* elements between consecutive frames of mask_frame: 0 = frame_dim (a [B,L,D] mask),
                                      1 = a [B,L] mask (the reference takes those too, :74) */
     const void* labels[3]; /* int64 [B,T], [B,T+Lv], [B,T+La]; may be NULL */
+    int32_t* row_label;    /* [rows] out or NULL: the label of every packed row as int32 (-100 = none), for the fused CE.
+                              With vocab > 0 a label outside [0, vocab) counts as an ERROR: it is treated as -100 and
+                              label_count[3] is incremented (mmb_heads_fwd then returns a NaN joint loss — torch's
+                              CrossEntropyLoss device-asserts there) */
+    int32_t vocab;
     float* keybias;        /* [rows] */
     int32_t* cu_seqlens;   /* [3B+1] */
-    int32_t* label_count;  /* [3] */
+    int32_t* label_count;  /* [4]: labelled rows per pass, [3] = count of out-of-range labels / ids */
     int32_t* kv_end;       /* [3B] or NULL: 1 + index of the last key whose mask is set, per sequence */
     int32_t B, T;
     int32_t L[2];
@@ -286,6 +303,8 @@ typedef struct mmb_embed_args {
      *   gw_pad[m]:      [H, ldf] f32 scratch (zeroed and consumed by mmb_embed_bwd) */
     void* frames_bf16[2];
     float* gw_pad[2];
+    int32_t* err_count; /* or NULL: incremented for every token id outside [0, V) (such an id reads the padding row 0
+                           instead of out-of-bounds memory; torch's nn.Embedding device-asserts there) */
 } mmb_embed_args;
 int mmb_embed_fwd(const mmb_embed_args* a, void* stream);
 int mmb_embed_bwd(const mmb_embed_args* a, void* stream);
@@ -299,7 +318,7 @@ int mmb_embed_bwd(const mmb_embed_args* a, void* stream);
  * decoder dgrad/wgrad GEMMs over all rows; dense keeps that work faithful.
  */
 typedef struct mmb_ce_args {
-    const void* logits;    /* [rows, ldl] bf16 */
+    const void* logits;    /* [rows, ldl] bf16 (unused by the mmb_ce_sparse_* entry points) */
     void* dlogits;         /* [rows, ldl] bf16 (bwd) */
     const void* labels[3]; /* int64 per pass */
     const int32_t* label_count; /* [3] from mmb_pack_prepare */
@@ -316,6 +335,34 @@ typedef struct mmb_ce_args {
 } mmb_ce_args;
 int mmb_ce_fwd(const mmb_ce_args* a, void* stream);
 int mmb_ce_bwd(const mmb_ce_args* a, void* stream);
+
+/* The same cross entropy WITHOUT a materialised [rows, V] logits matrix (training default; SURVEY.md §2.1 "fused CE").
+ * Forward: the decoder GEMM runs with MMB_EPI_CE_STATS; mmb_ce_sparse_fwd merges the per-group (max, sum exp) records of
+ * the labelled rows into row_lse and loss_sum[pass] += lse - logit[label].
+ * Backward: mmb_ce_sparse_bwd rewrites, in place in dlogits, the labelled rows (they hold their bf16 logits) into
+ * coef * gscale / count[pass] * (softmax - onehot) and zeroes rows that were labelled in an earlier step but are not now
+ * (row-written flags in the stats workspace) — every other row of dlogits is still zero from the plan's one-time
+ * initialisation, so the dense decoder dgrad / wgrad GEMMs read exactly the matrix the reference's autograd forms.
+ * mmb_colsum_rows_bf16 adds the column sums of the labelled rows to the decoder bias gradient (the unlabelled rows are
+ * zero).  HBM traffic per step: the labelled rows only (~1 % of the rows) instead of four full passes over [rows, V]. */
+typedef struct mmb_ce_sparse_args {
+    const int32_t* row_label;   /* [rows] from mmb_pack_prepare */
+    float* stats;               /* mmb_ce_stats_floats(rows, V) floats (the GEMM's aux2) */
+    void* dlogits;              /* [rows, ldl] bf16 (bwd) */
+    const int32_t* label_count; /* [3] */
+    float* row_lse;             /* [rows] */
+    float* loss_sum;            /* [3]: zeroed and filled by fwd */
+    const float* gscale;        /* device scalar upstream gradient, NULL = 1 */
+    float* dbias;               /* [V] f32 decoder-bias gradient, accumulated by mmb_colsum_rows_bf16 */
+    float coef;                 /* alpha / 3 */
+    int32_t V;
+    int64_t ldl;
+    int32_t B, T;
+    int32_t L[2];
+} mmb_ce_sparse_args;
+int mmb_ce_sparse_fwd(const mmb_ce_sparse_args* a, void* stream);
+int mmb_ce_sparse_bwd(const mmb_ce_sparse_args* a, void* stream);
+int mmb_colsum_rows_bf16(const mmb_ce_sparse_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Pooler + alignment/NSP heads + score-attention fusion + sentiment head + CPC x3 + loss combination

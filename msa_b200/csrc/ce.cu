@@ -39,7 +39,7 @@ ce_fwd_kernel(const CeParams p) {
     const int row = blockIdx.x;
     int pass;
     const long long label = row_label(p, row, pass);
-    if (label == -100) return;
+    if (label < 0 || label >= p.V) return;     // -100 = ignore; anything else out of range is counted by mmb_pack_prepare
     const __nv_bfloat16* x = p.logits + (int64_t)row * p.ldl;
     float m = -INFINITY, s = 0.f;
     const int nvec = (p.V + 7) / 8;
@@ -91,7 +91,7 @@ ce_bwd_kernel(const CeParams p) {
     const long long label = row_label(p, row, pass);
     __nv_bfloat16* dx = p.dlogits + (int64_t)row * p.ldl;
     const int nvec = (int)(p.ldl / 8);
-    if (label == -100) {
+    if (label < 0 || label >= p.V) {
         if (p.dense)
             for (int i = threadIdx.x; i < nvec; i += 256) reinterpret_cast<uint4*>(dx)[i] = make_uint4(0, 0, 0, 0);
         return;
@@ -131,7 +131,7 @@ ce_fwd_f32_kernel(const CeParams p) {
     const int row = blockIdx.x;
     int pass;
     const long long label = row_label(p, row, pass);
-    if (label == -100) return;
+    if (label < 0 || label >= p.V) return;
     const float* x = reinterpret_cast<const float*>(p.logits) + (int64_t)row * p.ldl;
     float m = -INFINITY, s = 0.f;
     for (int i = threadIdx.x; i < p.V; i += 256) {
@@ -164,6 +164,142 @@ ce_fwd_f32_kernel(const CeParams p) {
         p.row_lse[row] = lse;
         atomicAdd(p.loss_sum + pass, lse - x[label]);
     }
+}
+
+// ------------------------------------------------------------------ fused-CE path (no materialised logits)
+// The decoder GEMM (MMB_EPI_CE_STATS, gemm_tcgen05.cu: ce_stats_warp) left, for every labelled row, one (max, sum exp)
+// record per 128-column group, the label's logit and the row's bf16 logits in the dlogits buffer.
+struct CeSparseParams {
+    const int* row_label;   // [rows]
+    float* stats;           // planes of `rows` floats: [2g] max, [2g+1] sum, [2G] label logit, [2G+1] row-written flag
+    __nv_bfloat16* dlogits; // [rows, ldl]
+    const int* label_count; // [3]
+    float* row_lse;
+    float* loss_sum;        // [3]
+    const float* gscale;
+    float* dbias;           // [V]
+    int pass_base[4];
+    float coef;
+    int V, G, rows;
+    int64_t ldl;
+};
+
+// one warp per row: merges the G group records of a labelled row
+__global__ void __launch_bounds__(256)
+ce_sparse_fwd_kernel(const CeSparseParams p) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= p.rows) return;
+    if (p.row_label[row] == -100) return;
+    float m = -INFINITY, s = 0.f;
+    for (int g = lane; g < p.G; g += 32)
+        online_merge(m, s, p.stats[(size_t)(2 * g) * p.rows + row], p.stats[(size_t)(2 * g + 1) * p.rows + row]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        online_merge(m, s, m2, s2);
+    }
+    if (lane == 0) {
+        const float lse = m + logf(s);
+        p.row_lse[row] = lse;
+        const int pass = row < p.pass_base[1] ? 0 : (row < p.pass_base[2] ? 1 : 2);
+        atomicAdd(p.loss_sum + pass, lse - p.stats[(size_t)(2 * p.G) * p.rows + row]);
+    }
+}
+
+// one CTA per row.  Labelled: logits (bf16, written by the GEMM epilogue) -> coef * gscale / count * (softmax - onehot),
+// in place.  Unlabelled but written in an earlier step: back to zero.  Everything else is already zero.
+__global__ void __launch_bounds__(256)
+ce_sparse_bwd_kernel(const CeSparseParams p) {
+    const int row = blockIdx.x;
+    const int label = p.row_label[row];
+    float* flag = p.stats + (size_t)(2 * p.G + 1) * p.rows + row;
+    __nv_bfloat16* dx = p.dlogits + (int64_t)row * p.ldl;
+    const int nvec = (int)(p.ldl / 8);
+    if (label == -100) {
+        if (*flag != 0.f) {
+            for (int i = threadIdx.x; i < nvec; i += 256) reinterpret_cast<uint4*>(dx)[i] = make_uint4(0, 0, 0, 0);
+            __syncthreads();
+            if (threadIdx.x == 0) *flag = 0.f;
+        }
+        return;
+    }
+    const int pass = row < p.pass_base[1] ? 0 : (row < p.pass_base[2] ? 1 : 2);
+    const float lse = p.row_lse[row];
+    const float scale = p.coef * (p.gscale ? *p.gscale : 1.f) / (float)p.label_count[pass];
+    for (int i = threadIdx.x; i < nvec; i += 256) {
+        const uint4 q = reinterpret_cast<const uint4*>(dx)[i];
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(w[j]);
+            v[2 * j] = f.x;
+            v[2 * j + 1] = f.y;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int col = i * 8 + j;
+            float g = col < p.V ? __expf(v[j] - lse) : 0.f;
+            if (col == label) g -= 1.f;
+            v[j] = g * scale;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]);
+        o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]);
+        o.w = pack_bf16x2(v[6], v[7]);
+        reinterpret_cast<uint4*>(dx)[i] = o;
+    }
+}
+
+// decoder-bias gradient: column sums of dlogits over the LABELLED rows (all other rows are zero).
+// grid (column strips of 512, row slices); each thread owns a column pair.
+constexpr int kRowSlice = 1024;
+__global__ void __launch_bounds__(256)
+colsum_rows_kernel(const CeSparseParams p) {
+    const int col = (blockIdx.x * 256 + threadIdx.x) * 2;
+    const int r0 = blockIdx.y * kRowSlice, r1 = min(p.rows, r0 + kRowSlice);
+    __shared__ int s_rows[kRowSlice];
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int r = r0 + threadIdx.x; r < r1; r += 256)
+        if (p.row_label[r] != -100) s_rows[atomicAdd(&s_n, 1)] = r;
+    __syncthreads();
+    const int n = s_n;
+    if (n == 0 || col >= p.V) return;
+    float a0 = 0.f, a1 = 0.f;
+    for (int k = 0; k < n; ++k) {
+        const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.dlogits + (int64_t)s_rows[k] * p.ldl + col));
+        a0 += f.x;
+        a1 += f.y;
+    }
+    atomicAdd(p.dbias + col, a0);
+    if (col + 1 < p.V) atomicAdd(p.dbias + col + 1, a1);
+}
+
+static int fill_sparse(CeSparseParams& p, const mmb_ce_sparse_args* a) {
+    MMB_REQUIRE(a && a->row_label && a->stats && a->label_count && a->row_lse, "ce_sparse: null pointer");
+    MMB_REQUIRE(a->V > 128 && a->ldl >= (a->V + 7) / 8 * 8 && a->ldl % 8 == 0, "ce_sparse: V=%d ldl=%lld", a->V, (long long)a->ldl);
+    p.row_label = a->row_label;
+    p.stats = a->stats;
+    p.dlogits = (__nv_bfloat16*)a->dlogits;
+    p.label_count = a->label_count;
+    p.row_lse = a->row_lse;
+    p.loss_sum = a->loss_sum;
+    p.gscale = a->gscale;
+    p.dbias = a->dbias;
+    const int B = a->B, T = a->T;
+    p.pass_base[0] = 0;
+    p.pass_base[1] = B * T;
+    p.pass_base[2] = p.pass_base[1] + B * (T + a->L[0]);
+    p.pass_base[3] = p.pass_base[2] + B * (T + a->L[1]);
+    p.rows = p.pass_base[3];
+    p.coef = a->coef;
+    p.V = a->V;
+    p.G = (a->V + 127) / 128;
+    p.ldl = a->ldl;
+    return MMB_OK;
 }
 
 static int fill(CeParams& p, const mmb_ce_args* a) {
@@ -215,4 +351,33 @@ extern "C" int mmb_ce_bwd(const mmb_ce_args* a, void* stream) {
     MMB_REQUIRE(!a->logits_f32, "ce_bwd: the fp32 validation path is forward-only");
     ce_bwd_kernel<<<p.pass_base[3], 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("ce_bwd_kernel");
+}
+
+extern "C" int mmb_ce_sparse_fwd(const mmb_ce_sparse_args* a, void* stream) {
+    CeSparseParams p;
+    int rc = fill_sparse(p, a);
+    if (rc != MMB_OK) return rc;
+    MMB_REQUIRE(a->loss_sum != nullptr, "ce_sparse_fwd: null loss_sum");
+    MMB_CUDA(cudaMemsetAsync(a->loss_sum, 0, 3 * sizeof(float), (cudaStream_t)stream));
+    ce_sparse_fwd_kernel<<<(p.rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("ce_sparse_fwd_kernel");
+}
+
+extern "C" int mmb_ce_sparse_bwd(const mmb_ce_sparse_args* a, void* stream) {
+    CeSparseParams p;
+    int rc = fill_sparse(p, a);
+    if (rc != MMB_OK) return rc;
+    MMB_REQUIRE(a->dlogits != nullptr, "ce_sparse_bwd: null dlogits");
+    ce_sparse_bwd_kernel<<<p.rows, 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("ce_sparse_bwd_kernel");
+}
+
+extern "C" int mmb_colsum_rows_bf16(const mmb_ce_sparse_args* a, void* stream) {
+    CeSparseParams p;
+    int rc = fill_sparse(p, a);
+    if (rc != MMB_OK) return rc;
+    MMB_REQUIRE(a->dlogits != nullptr && a->dbias != nullptr, "colsum_rows: null pointer");
+    dim3 grid((p.V + 511) / 512, (p.rows + kRowSlice - 1) / kRowSlice);
+    colsum_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("colsum_rows_kernel");
 }

@@ -58,8 +58,10 @@ struct PrepParams {
     const long long* labels[3]; // [B, S(pass)]
     float* keybias;             // [rows]
     int* cu_seqlens;            // [3B + 1]
-    int* label_count;           // [3]
+    int* label_count;           // [3] (+ [3]: error count)
     int* kv_end;                // [3B] or null
+    int* row_label;             // [rows] or null
+    int vocab;                  // > 0: labels outside [0, vocab) are errors (counted in label_count[3], treated as -100)
 };
 
 __global__ void pack_prepare_kernel(const PrepParams p) {
@@ -76,7 +78,13 @@ __global__ void pack_prepare_kernel(const PrepParams p) {
         }
         p.keybias[row] = (1.0f - m) * -10000.0f;
         if (p.kv_end != nullptr && m >= 0.5f) atomicMax(p.kv_end + c.pass * p.d.B + c.b, c.s + 1);
-        if (p.labels[c.pass] != nullptr && p.labels[c.pass][(int64_t)c.b * p.d.S(c.pass) + c.s] != -100) cnt[c.pass]++;
+        long long lab = p.labels[c.pass] != nullptr ? p.labels[c.pass][(int64_t)c.b * p.d.S(c.pass) + c.s] : -100;
+        if (lab != -100 && p.vocab > 0 && (lab < 0 || lab >= p.vocab)) {
+            atomicAdd(p.label_count + 3, 1);
+            lab = -100;
+        }
+        if (lab != -100) cnt[c.pass]++;
+        if (p.row_label != nullptr) p.row_label[row] = (int)lab;
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -526,7 +534,9 @@ extern "C" int mmb_pack_prepare(const mmb_pack_args* a, void* stream) {
     p.cu_seqlens = a->cu_seqlens;
     p.label_count = a->label_count;
     p.kv_end = a->kv_end;
-    MMB_CUDA(cudaMemsetAsync(a->label_count, 0, 3 * sizeof(int), (cudaStream_t)stream));
+    p.row_label = a->row_label;
+    p.vocab = a->vocab;
+    MMB_CUDA(cudaMemsetAsync(a->label_count, 0, 4 * sizeof(int), (cudaStream_t)stream));
     if (a->kv_end) MMB_CUDA(cudaMemsetAsync(a->kv_end, 0, 3 * (size_t)a->B * sizeof(int), (cudaStream_t)stream));
     const int rows = p.d.rows();
     const int grid = min((rows + 255) / 256, num_sms() * 2);

@@ -41,6 +41,7 @@ struct GemmCfg {
 struct GemmParams {
     void* C;
     void* aux;
+    void* aux2;
     const float* bias;
     int64_t ldc, ldaux;
     int M, N, K;
@@ -302,6 +303,85 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[3
     }
 }
 
+// MMB_EPI_CE_STATS: masked-LM cross entropy fused into the tied-decoder GEMM (MMBertForPretraining.py:293 + :381-384).
+// The logits are never written.  Each epilogue thread owns one row and this warp's 128 columns (column group g =
+// colw / 128): a labelled row keeps an online (max, sum exp) over acc * alpha + bias, picks the label's logit, and stores
+// its bf16 logits into the dlogits buffer for the backward.  A warp without a labelled row returns without touching TMEM:
+// ~99 % of the rows (frame positions, unselected tokens) cost nothing.  Workspace planes of M floats: [2g] = max,
+// [2g + 1] = sum, [2G] = label logit, [2G + 1] = row-written flag, G = ceil(N / 128).  Warp-collective.
+constexpr int kCeGroupCols = 128;
+__device__ __forceinline__ void ce_stats_warp(const GemmParams& p, uint32_t taddr0, int row_base, int lane, int colw) {
+    const int row = row_base + lane;
+    const int label = row < p.M ? __ldg(reinterpret_cast<const int*>(p.aux) + row) : -100;
+    const bool on = label != -100;
+    if (!__any_sync(0xffffffffu, on)) return;
+    constexpr float kLog2e = 1.4426950408889634f;
+    float m = -INFINITY, s = 0.f, picked = 0.f;
+    bool has_pick = false;
+    __nv_bfloat16* crow = p.C != nullptr ? reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)(on ? row : 0) * p.ldc : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < kCeGroupCols; c += 32) {
+        const int col0 = colw + c;
+        if (col0 >= p.N) break;   // warp-uniform
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(taddr0 + c, raw);
+        ptx::tmem_ld_wait();
+        if (on) {
+            const int nvalid = min(32, p.N - col0);
+            float v[32];
+            if (nvalid == 32) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[4 * i + 0] = fmaf(__uint_as_float(raw[4 * i + 0]), p.alpha, b.x);
+                    v[4 * i + 1] = fmaf(__uint_as_float(raw[4 * i + 1]), p.alpha, b.y);
+                    v[4 * i + 2] = fmaf(__uint_as_float(raw[4 * i + 2]), p.alpha, b.z);
+                    v[4 * i + 3] = fmaf(__uint_as_float(raw[4 * i + 3]), p.alpha, b.w);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    v[i] = i < nvalid ? fmaf(__uint_as_float(raw[i]), p.alpha, p.bias ? __ldg(p.bias + col0 + i) : 0.f) : -INFINITY;
+            }
+            float cm = v[0];
+#pragma unroll
+            for (int i = 1; i < 32; ++i) cm = fmaxf(cm, v[i]);
+            const float mn = fmaxf(m, cm);
+            const float off = -mn * kLog2e;
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc += ex2_approx(fmaf(v[i], kLog2e, off));     // exp2(-inf) = 0 for the padded tail
+            s = fmaf(s, ex2_approx((m - mn) * kLog2e), acc);
+            m = mn;
+            const int rel = label - col0;
+            if (rel >= 0 && rel < 32) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i == rel) picked = v[i];
+                has_pick = true;
+            }
+            if (crow != nullptr) {
+                if (nvalid == 32) {
+                    store_bf16x32(crow + col0, v, 32);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (i < nvalid) crow[col0 + i] = __float2bfloat16_rn(v[i]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (on) {
+        float* st = reinterpret_cast<float*>(p.aux2);
+        const int g = colw / kCeGroupCols, G = (p.N + kCeGroupCols - 1) / kCeGroupCols;
+        st[(size_t)(2 * g) * p.M + row] = m;
+        st[(size_t)(2 * g + 1) * p.M + row] = s;
+        if (has_pick) st[(size_t)(2 * G) * p.M + row] = picked;
+        if (g == 0 && crow != nullptr) st[(size_t)(2 * G + 1) * p.M + row] = 1.0f;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- 1-CTA kernel
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -437,8 +517,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
             const int row_base = m_blk * BM + quarter * 32;
+            if constexpr (kColsPerWarp == kCeGroupCols) {
+                if (p.epilogue == MMB_EPI_CE_STATS && n_blk * BN + half * kColsPerWarp < p.N)
+                    ce_stats_warp(p, tmem_base + acc * BN + half * kColsPerWarp + ((uint32_t)(quarter * 32) << 16), row_base, lane,
+                                  n_blk * BN + half * kColsPerWarp);
+            }
 #pragma unroll 1
-            for (int c = 0; c < kColsPerWarp; c += 32) {
+            for (int c = p.epilogue == MMB_EPI_CE_STATS ? kColsPerWarp : 0; c < kColsPerWarp; c += 32) {
                 const int col0 = n_blk * BN + half * kColsPerWarp + c;
                 if (col0 >= p.N) break;  // warp-uniform
                 if (p.dbg & 32) continue;
@@ -723,6 +808,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
+            if constexpr (kColsPerWarp == kCeGroupCols) {
+                if (p.epilogue == MMB_EPI_CE_STATS && colw < p.N)
+                    ce_stats_warp(p, tmem_base + acc * TN + half * kColsPerWarp + ((uint32_t)(quarter * 32) << 16), row_base, lane, colw);
+            }
             if (aux_pref) {
                 __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(p.C);
 #pragma unroll
@@ -750,7 +839,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 }
             }
 #pragma unroll 1
-            for (int c = aux_pref ? kColsPerWarp : 0; c < kColsPerWarp; c += 32) {
+            for (int c = (aux_pref || p.epilogue == MMB_EPI_CE_STATS) ? kColsPerWarp : 0; c < kColsPerWarp; c += 32) {
                 const int col0 = n_blk * TN + half * kColsPerWarp + c;
                 if (col0 >= p.N) break;
                 if (p.dbg & 32) continue;
@@ -864,6 +953,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, 
 static void fill_common(GemmParams& p, const mmb_gemm_args* a, int tile_m, int tile_n) {
     p.C = a->C;
     p.aux = a->aux;
+    p.aux2 = a->aux2;
     p.bias = a->bias;
     p.ldc = a->ldc;
     p.ldaux = a->ldaux;
@@ -982,25 +1072,37 @@ static int launch_gemm_2cta(const mmb_gemm_args* a, cudaStream_t stream) {
 
 }  // namespace mmb
 
+extern "C" size_t mmb_ce_stats_floats(int M, int N) {
+    if (M <= 0 || N <= 0) return 0;
+    const size_t G = ((size_t)N + mmb::kCeGroupCols - 1) / mmb::kCeGroupCols;
+    return (2 * G + 2) * (size_t)M;
+}
+
 extern "C" int mmb_gemm(const mmb_gemm_args* a, void* stream) {
     using namespace mmb;
     MMB_REQUIRE(a != nullptr, "mmb_gemm: null args");
-    MMB_REQUIRE(a->A && a->B && a->C, "mmb_gemm: null operand");
     MMB_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "mmb_gemm: empty problem M=%d N=%d K=%d", a->M, a->N, a->K);
     MMB_REQUIRE((a->lda % 8) == 0 && (a->ldb % 8) == 0, "mmb_gemm: lda/ldb must be multiples of 8 (got %lld, %lld)",
                 (long long)a->lda, (long long)a->ldb);
+    const bool ce = a->epilogue == MMB_EPI_CE_STATS;
+    MMB_REQUIRE(a->A && a->B && (a->C || ce), "mmb_gemm: null operand");
     const bool f32_out = a->epilogue == MMB_EPI_STORE_F32 || a->epilogue == MMB_EPI_ATOMIC_ADD_F32;
     MMB_REQUIRE((a->ldc % (f32_out ? 4 : 8)) == 0, "mmb_gemm: ldc=%lld misaligned", (long long)a->ldc);
     MMB_REQUIRE(((uintptr_t)a->A % 16) == 0 && ((uintptr_t)a->B % 16) == 0 && ((uintptr_t)a->C % 16) == 0,
                 "mmb_gemm: operands must be 16-byte aligned");
-    MMB_REQUIRE(a->epilogue >= 0 && a->epilogue <= MMB_EPI_MUL_AUX_BF16, "mmb_gemm: bad epilogue %d", a->epilogue);
+    MMB_REQUIRE(a->epilogue >= 0 && a->epilogue <= MMB_EPI_CE_STATS, "mmb_gemm: bad epilogue %d", a->epilogue);
+    if (ce) {
+        MMB_REQUIRE(a->aux && a->aux2, "mmb_gemm: MMB_EPI_CE_STATS needs aux (row labels) and aux2 (stats workspace)");
+        MMB_REQUIRE(a->N > 128, "mmb_gemm: MMB_EPI_CE_STATS needs N > 128 (128-column statistic groups)");
+        MMB_REQUIRE(a->split_k <= 1 && !(a->dbg_flags & (1 | 64)), "mmb_gemm: MMB_EPI_CE_STATS: no split-K / narrow tiles");
+    }
     MMB_REQUIRE(a->split_k <= 1 || a->epilogue == MMB_EPI_ATOMIC_ADD_F32, "mmb_gemm: split_k needs ATOMIC_ADD_F32");
     if (a->epilogue == MMB_EPI_DGELU_BF16 || a->epilogue == MMB_EPI_GELU_GRAD_BF16 || a->epilogue == MMB_EPI_MUL_AUX_BF16)
         MMB_REQUIRE(a->aux != nullptr && (a->ldaux % 8) == 0, "mmb_gemm: this epilogue needs aux with ldaux %% 8 == 0");
     if (a->epilogue == MMB_EPI_GELU_BF16 && a->aux) MMB_REQUIRE((a->ldaux % 8) == 0, "mmb_gemm: ldaux %% 8 != 0");
     const int min_lda = a->a_major == MMB_MAJOR_K ? a->K : a->M;
     const int min_ldb = a->b_major == MMB_MAJOR_K ? a->K : a->N;
-    MMB_REQUIRE(a->lda >= min_lda && a->ldb >= min_ldb && a->ldc >= a->N, "mmb_gemm: leading dimension too small");
+    MMB_REQUIRE(a->lda >= min_lda && a->ldb >= min_ldb && (a->ldc >= a->N || (ce && !a->C)), "mmb_gemm: leading dimension too small");
     // Dispatch: the CTA-pair kernel (256 x 256 tiles) whenever the problem has more than one 128-row tile and
     // more than 128 columns; otherwise the single-CTA kernel (128 x 256, or 128 x 128 for N <= 128).
     // dbg_flags: bit 0 forces the 128 x 128 tile, bit 3 forces the single-CTA 128 x 256 kernel.
