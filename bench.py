@@ -150,7 +150,7 @@ def config_dict(workload, shape, world):
     return {"workload": workload.name, "model": f"bert-base shape ({shape.num_hidden_layers} layers), random init",
             "batch_per_gpu": B, "global_batch": B * world, "positions_per_sample": workload.positions,
             "packed_rows_per_gpu": B * workload.positions, "parallelism": f"dp{world}",
-            "mlm": "dense (all positions, as the reference)", "optimizer": "AdamW (HF semantics)",
+            "mlm": "dense (decoder GEMM, dgrad and wgrad over all positions, as the reference); cross entropy fused into the decoder epilogue, logits not materialised", "optimizer": "AdamW (HF semantics)",
             "l2": "no explicit flush: one training step streams GiBs of saved activations (>> 126 MB L2) and 4 distinct "
                   "input batches are cycled"}
 

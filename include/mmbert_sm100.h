@@ -27,8 +27,9 @@
 extern "C" {
 #endif
 
-#define MMB_VERSION 201 /* round 2; 200: mmb_pack_args.mask_frame_stride; 201: MMB_EPI_CE_STATS, mmb_gemm_args.aux2,
-                           mmb_pack_args.row_label / vocab, mmb_ce_sparse_*, mmb_embed_args.err_count */
+#define MMB_VERSION 202 /* round 2; 200: mmb_pack_args.mask_frame_stride; 201: MMB_EPI_CE_STATS, mmb_gemm_args.aux2,
+                           mmb_pack_args.row_label / vocab, mmb_ce_sparse_*, mmb_embed_args.err_count;
+                           202: mmb_attn_schedule_args.row_label (zero-gradient query tail skipped by the backward) */
 
 enum mmb_status {
     MMB_OK = 0,
@@ -215,12 +216,23 @@ int mmb_attn_bwd(const mmb_attn_args* a, void* stream);
  * (sequence, head), sequences ordered by effective key count (length, or kv_end where that is smaller), longest first
  * — an item of the forward and of the dQ pass costs ceil(effective keys / 64) steps; [1 + cap, 1 + 2 cap): the 128-key
  * tiles of the dK/dV pass, first those that hold an unmasked key (sequences ordered by length: ceil(length / 64) steps
- * each), then the fully masked ones (zero fill only).  nseq <= 8192. */
+ * each), then the fully masked ones (zero fill only).  nseq <= 8192.
+ *
+ * Zero-gradient query tail (row_label != NULL).  In this model the loss reaches the encoder output only at rows that
+ * carry a masked-LM label and at row 0 of every sequence (pooler / alignment heads, MMBertForPretraining.py:295-302,
+ * 406-425).  A row at or behind kv_end is a masked key for every query, so no gradient reaches it through K or V
+ * either: if no such row is labelled, dctx is EXACTLY zero on the rows >= kv_end of every layer, and those query rows
+ * contribute exactly nothing to dQ (their own rows: zero), dK and dV.  mmb_attn_schedule verifies the premise on the
+ * device (every row_label at or behind kv_end is -100) and, if it holds, sets bit 30 of the header's cap field and
+ * orders the dK/dV list by effective key count; mmb_attn_bwd then runs the dK/dV pass over ceil(kv_end / 64) query steps
+ * instead of ceil(length / 64), and the dQ pass over the dK/dV list (query tiles behind kv_end only store zeros).
+ * Same results bit for bit as the full sweep; the forward is unaffected (those rows' outputs are defined). */
 typedef struct mmb_attn_schedule_args {
     const int32_t* cu_seqlens; /* [nseq + 1] */
     const int32_t* kv_end;     /* [nseq] or NULL */
     void* work;                /* out: mmb_attn_schedule_bytes(...) bytes, 16-byte aligned */
     int32_t nseq, nheads, max_seqlen;
+    const int32_t* row_label;  /* [rows] from mmb_pack_prepare, or NULL (no query-tail skipping) */
 } mmb_attn_schedule_args;
 size_t mmb_attn_schedule_bytes(int nseq, int nheads, int max_seqlen);
 int mmb_attn_schedule(const mmb_attn_schedule_args* a, void* stream);

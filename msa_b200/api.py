@@ -150,6 +150,10 @@ class MMBertForPretraining(_Node):
         self._reducer = None       # msa_b200.ddp.GradReducer once attached (train_epoch toggles its ``sync`` flag)
         self.launches = 0          # kernel-launching C calls issued so far (bench.py reports the per-step count)
         self.dense_mlm = True
+        # False (default): the masked-LM cross entropy is fused into the tied-decoder GEMM and the [rows, vocab] logits are
+        # never written — pred_t / pred_v / pred_s (outputs[7], [9], [11]; trainer.py never reads them) come back as None.
+        # True: the reference's full output tuple, at the price of 61 KB of HBM per sequence position.
+        self.materialize_logits = False
         # Forward-only (no_grad) calls on an eval() model replay the launch plan as one CUDA graph (engine.Plan.forward_graph).
         self.use_cuda_graph = False
         # "bf16": tcgen05 tensor-core path (training and inference).  "fp32": validation path, forward only, fp32
@@ -242,6 +246,7 @@ class MMBertForPretraining(_Node):
         # everything that is baked into a plan when it is built is part of its key
         p_joint = float(self.bert.jointEmbeddings.dropout.p)
         key = (B, T, Lv, La, bool(needs_grad), bool(self.training), fp32, p_joint, bool(self.dense_mlm),
+               bool(self.materialize_logits),
                float(self.config.hidden_dropout_prob), float(self.config.attention_probs_dropout_prob))
         plan = self._plans.get(key)
         if plan is None and fp32:
@@ -258,7 +263,8 @@ class MMBertForPretraining(_Node):
             if len(self._plans) >= 4:          # bound the activation memory held by stale shapes
                 self._plans.clear()
             plan = Plan(self.config, self.bert.dataset, self._store, B, T, Lv, La, bool(needs_grad), device,
-                        p_joint=p_joint, dense_mlm=self.dense_mlm, dropout=bool(self.training))
+                        p_joint=p_joint, dense_mlm=self.dense_mlm, dropout=bool(self.training),
+                        materialize_logits=self.materialize_logits)
             self._plans[key] = plan
             plan._frame_sig = None
         return plan
@@ -268,7 +274,8 @@ class MMBertForPretraining(_Node):
         """Same contract as MMBertForPretraining.forward (MMBertForPretraining.py:392-449): returns
         ``((joint_loss, None, None, None, ap_loss, label_loss, nce, pred_t, rel_t, pred_v, align_v, pred_s, align_s),
         logits)``.  ``joint_loss`` is differentiable (``.backward()`` fills every parameter's ``.grad``); the other
-        outputs are plain tensors.  ``pred_*`` are bf16 views of the decoder output of the packed batch."""
+        outputs are plain tensors.  ``pred_*`` are bf16 views of the decoder output of the packed batch when
+        ``self.materialize_logits`` is set, else None (fused cross entropy, the default)."""
         dev = self.bert.embeddings.word_embeddings.weight.device
         if dev.type != "cuda":
             raise capi.MMBError("MMBertForPretraining.forward needs the model on a CUDA (sm_100) device: "
@@ -320,9 +327,12 @@ class MMBertForPretraining(_Node):
             joint = losses[0]
         V = self.config.vocab_size
         b1, b2 = B * T, B * T + B * (T + Lv)
-        pred_t = plan.logits[:b1, :V].view(B, T, V)
-        pred_v = plan.logits[b1:b2, :V].view(B, T + Lv, V)
-        pred_s = plan.logits[b2:, :V].view(B, T + La, V)
+        if plan.logits is None:                 # fused cross entropy (materialize_logits = False)
+            pred_t = pred_v = pred_s = None
+        else:
+            pred_t = plan.logits[:b1, :V].view(B, T, V)
+            pred_v = plan.logits[b1:b2, :V].view(B, T + Lv, V)
+            pred_s = plan.logits[b2:, :V].view(B, T + La, V)
         rel = small[8 + B:8 + 3 * B].view(B, 2)
         align = small[8 + 3 * B:].view(2 * B, 2)
         outputs = (joint, None, None, None, losses[2], losses[3], losses[4], pred_t, rel, pred_v,

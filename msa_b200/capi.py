@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmmbert_sm100.so")
 MMB_OK, MMB_EINVAL, MMB_EARCH, MMB_ECUDA = 0, -1, -2, -3
 MAJOR_K, MAJOR_MN = 0, 1
 (EPI_STORE_BF16, EPI_GELU_BF16, EPI_RELU_BF16, EPI_STORE_F32, EPI_ATOMIC_ADD_F32, EPI_DGELU_BF16, EPI_GELU_GRAD_BF16,
- EPI_MUL_AUX_BF16) = range(8)
+ EPI_MUL_AUX_BF16, EPI_CE_STATS) = range(9)
 
 _lib = None
 
@@ -111,6 +111,7 @@ AttnScheduleArgs = _make_struct("mmb_attn_schedule_args")
 PackArgs = _make_struct("mmb_pack_args")
 EmbedArgs = _make_struct("mmb_embed_args")
 CeArgs = _make_struct("mmb_ce_args")
+CeSparseArgs = _make_struct("mmb_ce_sparse_args")
 HeadsArgs = _make_struct("mmb_heads_args")
 AdamwArgs = _make_struct("mmb_adamw_args")
 MlmMaskArgs = _make_struct("mmb_mlm_mask_args")
@@ -149,11 +150,11 @@ def fill(struct, **kw):
 
 
 def gemm_args(A, B, C, M, N, K, *, a_major=MAJOR_K, b_major=MAJOR_K, epilogue=EPI_STORE_BF16, bias=None, aux=None,
-              split_k=1, alpha=1.0, lda=None, ldb=None, ldc=None, ldaux=None, dbg_flags=0):
+              aux2=None, split_k=1, alpha=1.0, lda=None, ldb=None, ldc=None, ldaux=None, dbg_flags=0):
     a = GemmArgs()
-    return fill(a, A=A, B=B, C=C, aux=aux, bias=bias,
+    return fill(a, A=A, B=B, C=C, aux=aux, aux2=aux2, bias=bias,
                 lda=A.stride(0) if lda is None else lda, ldb=B.stride(0) if ldb is None else ldb,
-                ldc=C.stride(0) if ldc is None else ldc,
+                ldc=(C.stride(0) if C is not None else 0) if ldc is None else ldc,
                 ldaux=((aux.stride(0) if aux is not None else 0) if ldaux is None else ldaux),
                 M=M, N=N, K=K, a_major=a_major, b_major=b_major, epilogue=epilogue, split_k=split_k, alpha=alpha,
                 dbg_flags=dbg_flags)
@@ -216,9 +217,9 @@ def attn_schedule_buffer(nseq, nheads, max_seqlen, device):
     return torch.empty(L.mmb_attn_schedule_bytes(nseq, nheads, max_seqlen) // 16, 4, device=device, dtype=torch.int32)
 
 
-def attn_schedule_args(cu_seqlens, kv_end, work, nheads, max_seqlen):
+def attn_schedule_args(cu_seqlens, kv_end, work, nheads, max_seqlen, row_label=None):
     return fill(AttnScheduleArgs(), cu_seqlens=cu_seqlens, kv_end=kv_end, work=work, nseq=cu_seqlens.numel() - 1,
-                nheads=nheads, max_seqlen=max_seqlen)
+                nheads=nheads, max_seqlen=max_seqlen, row_label=row_label)
 
 
 def cast_bf16(src, dst):
@@ -237,6 +238,13 @@ def launch_count():
     L = lib()
     L.mmb_launch_count.restype = ctypes.c_longlong
     return L.mmb_launch_count()
+
+
+def ce_stats_floats(M, N):
+    L = lib()
+    L.mmb_ce_stats_floats.restype = ctypes.c_size_t
+    L.mmb_ce_stats_floats.argtypes = [ctypes.c_int, ctypes.c_int]
+    return L.mmb_ce_stats_floats(M, N)
 
 
 def heads_workspace_bytes(B, H):

@@ -71,8 +71,8 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dctx, const __nv_bfloat16
 constexpr int kSchedThreads = 1024;
 constexpr int kSchedMaxSeqs = 8192;
 __global__ void __launch_bounds__(kSchedThreads)
-attn_schedule_kernel(const int* __restrict__ cu, const int* __restrict__ kv_end, int4* __restrict__ work, int nseq,
-                     int nheads, int cap) {
+attn_schedule_kernel(const int* __restrict__ cu, const int* __restrict__ kv_end, const int* __restrict__ row_label,
+                     int4* __restrict__ work, int nseq, int nheads, int cap) {
     extern __shared__ int sm[];
     int* len = sm;                 // sequence length
     int* eff = sm + nseq;          // keys before the all-masked tail
@@ -88,6 +88,15 @@ attn_schedule_kernel(const int* __restrict__ cu, const int* __restrict__ kv_end,
         eff[i] = (e > 0 && e < S) ? e : S;
     }
     __syncthreads();
+    // zero-gradient query tail (header): holds iff no row at or behind its sequence's kv_end carries a label
+    int labelled_tail = row_label == nullptr ? 1 : 0;
+    if (row_label != nullptr) {
+        for (int i = 0; i < nseq; ++i) {
+            const int r1 = cu[i + 1];
+            for (int r = cu[i] + eff[i] + tid; r < r1; r += kSchedThreads) labelled_tail |= row_label[r] != -100 ? 1 : 0;
+        }
+    }
+    const bool qskip = __syncthreads_or(labelled_tail) == 0;
     for (int i = tid; i < nseq; i += kSchedThreads) {
         const int ei = eff[i], li = len[i];
         int rq = 0, rkv = 0;
@@ -97,7 +106,7 @@ attn_schedule_kernel(const int* __restrict__ cu, const int* __restrict__ kv_end,
             rkv += (lj > li || (lj == li && j < i)) ? 1 : 0;
         }
         ord_q[rq] = i;
-        ord_kv[rkv] = i;
+        ord_kv[qskip ? rq : rkv] = i;      // query tail skipped: a dK/dV item costs ceil(eff / 64) steps, not ceil(len / 64)
     }
     __syncthreads();
     int* off_z = ord_q;            // sequence -> first record of its fully masked key tiles (reuses ord_q once consumed)
@@ -115,7 +124,7 @@ attn_schedule_kernel(const int* __restrict__ cu, const int* __restrict__ kv_end,
             off_z[i] = nz;
             nz += nheads * ((len[i] + 127) / 128 - (eff[i] + 127) / 128);
         }
-        work[0] = make_int4(nq, nz, cap, nkv);
+        work[0] = make_int4(nq, nz, cap | (qskip ? (1 << 30) : 0), nkv);
     }
     __syncthreads();
     // records: (head, tile) in index order within a sequence, so that the CTAs working side by side share K / V in L2
@@ -167,8 +176,8 @@ extern "C" int mmb_attn_schedule(const mmb_attn_schedule_args* a, void* stream) 
     const int smem = 6 * a->nseq * (int)sizeof(int);
     if (smem > 48 * 1024)
         MMB_CUDA(cudaFuncSetAttribute(attn_schedule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attn_schedule_kernel<<<1, kSchedThreads, smem, (cudaStream_t)stream>>>(a->cu_seqlens, a->kv_end, (int4*)a->work,
-                                                                           a->nseq, a->nheads, (int)cap);
+    attn_schedule_kernel<<<1, kSchedThreads, smem, (cudaStream_t)stream>>>(a->cu_seqlens, a->kv_end, a->row_label,
+                                                                           (int4*)a->work, a->nseq, a->nheads, (int)cap);
     return check_launch("attn_schedule_kernel");
 }
 

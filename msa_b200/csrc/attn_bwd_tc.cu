@@ -165,8 +165,11 @@ __device__ __forceinline__ ItemRaw fetch_item(const BwdTcParams& p, const int4* 
     }
     return r;
 }
+// qskip (mmb_attn_schedule verified it): dctx is exactly zero on the rows >= kv_end of every sequence, so those QUERY rows
+// add nothing to dK / dV and their dQ is zero — the dK/dV pass stops at ceil(eff / 64) query steps and a dQ tile behind
+// kv_end only stores zeros
 template <bool kIsDq>
-__device__ __forceinline__ Item make_item(const BwdTcParams& p, const ItemRaw& r, int total, bool listed) {
+__device__ __forceinline__ Item make_item(const BwdTcParams& p, const ItemRaw& r, int total, bool listed, bool qskip) {
     Item it;
     if (listed) {
         it.tile = r.ht & 0xffff;
@@ -182,8 +185,8 @@ __device__ __forceinline__ Item make_item(const BwdTcParams& p, const ItemRaw& r
     int eff = it.S;                         // keys at index >= eff are all masked: P == 0 exactly (see mmb_attn_args)
     if (r.kvend > 0 && r.kvend < it.S) eff = r.kvend;
     if (!it.valid) it.nsteps = 0;
-    else if (kIsDq) it.nsteps = (eff + kStep - 1) / kStep;
-    else it.nsteps = (it.tile * kRows >= eff) ? 0 : (it.S + kStep - 1) / kStep;
+    else if (kIsDq) it.nsteps = (qskip && it.tile * kRows >= eff) ? 0 : (eff + kStep - 1) / kStep;
+    else it.nsteps = (it.tile * kRows >= eff) ? 0 : ((qskip ? eff : it.S) + kStep - 1) / kStep;
     return it;
 }
 
@@ -290,10 +293,14 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
     const uint32_t tmem = lds32_b(tmem_slot);
     int total_items = p.tiles * p.nheads * p.nseq;
     const int4* wl = nullptr;
+    bool qskip = false;
     if (p.work != nullptr) {
-        const int4 hdr = __ldg(p.work);                      // {items of the forward / dQ list, of the dK/dV list, capacity}
-        total_items = kIsDq ? hdr.x : hdr.y;
-        wl = p.work + 1 + (kIsDq ? 0 : hdr.z);
+        const int4 hdr = __ldg(p.work);      // {items of the forward / dQ list, of the dK/dV list, capacity | qskip << 30}
+        qskip = (hdr.z >> 30) & 1;
+        const int cap = hdr.z & 0x3fffffff;
+        // with the query tail skipped both passes walk the dK/dV list: live tiles by effective length, zero-fill tiles last
+        total_items = (kIsDq && !qskip) ? hdr.x : hdr.y;
+        wl = p.work + 1 + ((kIsDq && !qskip) ? 0 : cap);
     }
     const bool listed = wl != nullptr;
     const int stride = gridDim.x;
@@ -307,7 +314,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
         uint32_t g = 0, n = 0;
         ItemRaw raw = fetch_item(p, wl, m_cu, m_kv, blockIdx.x, total_items);
         for (int idx = blockIdx.x; idx < total_items; idx += stride) {
-            const Item cur = make_item<kIsDq>(p, raw, total_items, listed);
+            const Item cur = make_item<kIsDq>(p, raw, total_items, listed, qskip);
             raw = fetch_item(p, wl, m_cu, m_kv, idx + stride, total_items);
             if (cur.nsteps == 0) continue;
             const int rb = n & 1;
@@ -357,7 +364,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
         uint32_t g = 0, n = 0;
         ItemRaw raw = fetch_item(p, wl, m_cu, m_kv, blockIdx.x, total_items);
         for (int idx = blockIdx.x; idx < total_items; idx += stride) {
-            const Item cur = make_item<kIsDq>(p, raw, total_items, listed);
+            const Item cur = make_item<kIsDq>(p, raw, total_items, listed, qskip);
             raw = fetch_item(p, wl, m_cu, m_kv, idx + stride, total_items);
             if (cur.nsteps == 0) continue;
             const int rb = n & 1;
@@ -386,7 +393,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
         uint32_t g = 0, n = 0;
         ItemRaw raw = fetch_item(p, wl, m_cu, m_kv, blockIdx.x, total_items);
         for (int idx = blockIdx.x; idx < total_items; idx += stride) {
-            const Item cur = make_item<kIsDq>(p, raw, total_items, listed);
+            const Item cur = make_item<kIsDq>(p, raw, total_items, listed, qskip);
             raw = fetch_item(p, wl, m_cu, m_kv, idx + stride, total_items);
             if (cur.nsteps == 0) continue;
             const int a = n & 1;
@@ -487,11 +494,17 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
         };
         ItemRaw raw = fetch_item(p, wl, m_cu, m_kv, blockIdx.x, total_items);
         for (int idx = blockIdx.x; idx < total_items; idx += stride) {
-            const Item cur = make_item<kIsDq>(p, raw, total_items, listed);
+            const Item cur = make_item<kIsDq>(p, raw, total_items, listed, qskip);
             raw = fetch_item(p, wl, m_cu, m_kv, idx + stride, total_items);
             if (!cur.valid) continue;
             const int rr = cur.tile * kRows + r;        // this thread's query (dQ pass) / key (dKV pass)
             if (cur.nsteps == 0) {
+                if (kIsDq && rr < cur.S) {
+                    // dQ pass, query tile behind kv_end with the zero-gradient tail verified: dQ = 0
+                    __nv_bfloat16* o = p.dqkv + (int64_t)(cur.row0 + rr) * ld + cur.head * kHd + cq * 16;
+                    *reinterpret_cast<uint4*>(o) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4*>(o + 8) = make_uint4(0, 0, 0, 0);
+                }
                 // dKV pass, every key of the tile masked: P == 0 exactly, so dK = dV = 0
                 if (!kIsDq && rr < cur.S) {
                     __nv_bfloat16* o = p.dqkv + (int64_t)(cur.row0 + rr) * ld + p.H + cur.head * kHd + cq * 16;

@@ -136,6 +136,7 @@ struct EmbedParams {
     float* g_wb[2];                // [H]
     __nv_bfloat16* frames_bf16[2]; // optional [B*L, ldf] bf16 copy of the frames (ldf = D rounded up to 8)
     float* gw_pad[2];              // optional [H, ldf] scratch of the tensor-core projection wgrad
+    int* err_count;                // optional: count of token ids / token types outside their tables (forward only)
 };
 
 constexpr uint32_t kStreamEmb1 = 0x100, kStreamEmb2 = 0x101;
@@ -154,7 +155,15 @@ template <int NCH>
 __device__ __forceinline__ void text_embed_row(const EmbedParams& p, const RowCoord& c, int lane, RowF<NCH>& e, long long& id,
                                                int& tt) {
     id = p.ids[c.pass][(int64_t)c.b * p.d.T + c.s];
-    tt = c.pass == 0 ? (int)p.token_type[(int64_t)c.b * p.d.T + c.s] : 0;
+    long long tt64 = c.pass == 0 ? p.token_type[(int64_t)c.b * p.d.T + c.s] : 0;
+    // nn.Embedding device-asserts on an index outside its table; here such an index reads row 0 (and gets no gradient)
+    // and is counted, which turns the step's joint loss into NaN (mmb_heads_fwd)
+    if (id < 0 || id >= p.V || tt64 < 0 || tt64 > 1) {
+        if (lane == 0 && p.err_count != nullptr) atomicAdd(p.err_count, 1);
+        if (id < 0 || id >= p.V) id = 0;
+        if (tt64 < 0 || tt64 > 1) tt64 = 0;
+    }
+    tt = (int)tt64;
     RowF<NCH> a;
     row_load_f32(e, p.word + (int64_t)id * p.H, p.H, lane);
     row_load_f32(a, p.type + (int64_t)tt * p.H, p.H, lane);
@@ -472,6 +481,7 @@ static int fill_embed(EmbedParams& p, const mmb_embed_args* a) {
     MMB_REQUIRE(a->T <= a->max_pos, "embed: T=%d exceeds max_position_embeddings=%d", a->T, a->max_pos);
     p.d.B = a->B; p.d.T = a->T; p.d.L1 = a->L[0]; p.d.L2 = a->L[1];
     p.H = a->H; p.V = a->V; p.max_pos = a->max_pos;
+    p.err_count = a->err_count;
     for (int i = 0; i < 3; ++i) p.ids[i] = (const long long*)a->ids[i];
     p.token_type = (const long long*)a->token_type;
     for (int i = 0; i < 2; ++i) {
@@ -579,6 +589,7 @@ extern "C" int mmb_embed_bwd(const mmb_embed_args* a, void* stream) {
     if (rc != MMB_OK) return rc;
     MMB_REQUIRE(p.dx0 && p.g_word && p.g_pos && p.g_type && p.g_ln1_g && p.g_ln1_b && p.g_ln2_g && p.g_ln2_b,
                 "embed_bwd: null pointer");
+    p.err_count = nullptr;      // counted once, by the forward
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)kEmbWarps * p.H * sizeof(float);
     const int ntext = 3 * p.d.B * p.d.T;

@@ -320,7 +320,7 @@ struct LossParams {
     const float* logit;       // [B] classifier output
     const float* sentiment;   // [B]
     const float* ce_loss_sum; // [3]
-    const int* label_count;   // [3]
+    const int* label_count;   // [4]: labelled rows per pass, [3] = out-of-range label / id count
     const float* nce;         // [1]
     float* losses;            // [8]: joint, mlm, ap, label, nce, mlm_t, mlm_v, mlm_s
     float* logits_out;        // [B] (tanh applied iff num_labels == 1; zeros in the classification branch)
@@ -381,6 +381,9 @@ final_losses_kernel(const LossParams p) {
             mlm += li;
         }
         mlm /= 3.f;
+        // label_count[3]: labels / token ids outside the vocabulary seen by mmb_pack_prepare / mmb_embed_fwd (torch's
+        // CrossEntropyLoss / nn.Embedding device-assert there): poison the loss instead of training on garbage
+        if (p.label_count[3] != 0) mlm = __int_as_float(0x7fc00000);
         const float ap = ap_tot * 0.5f, nce = p.nce[0];
         p.losses[0] = p.alpha * mlm + ap + mse - p.beta * nce;
         p.losses[1] = mlm;

@@ -43,7 +43,8 @@ def _split_k(M_out, N_out, K, clusters=74):
 
 
 class Plan:
-    def __init__(self, cfg, dataset, store, B, T, Lv, La, training, device, p_joint=0.5, dense_mlm=True, dropout=None):
+    def __init__(self, cfg, dataset, store, B, T, Lv, La, training, device, p_joint=0.5, dense_mlm=True, dropout=None,
+                 materialize_logits=False):
         # ``training``: keep the activations and build the backward plan.  ``dropout`` (default: same as training):
         # apply the dropout probabilities — a forward with autograd enabled on an eval() model keeps the
         # activations but drops nothing, exactly what the reference's modules would do.
@@ -64,6 +65,9 @@ class Plan:
         self.p_attn = float(cfg.attention_probs_dropout_prob) if dropout else 0.0
         self.p_joint = float(p_joint) if dropout else 0.0
         self.dense_mlm = dense_mlm
+        # False (default): the tied-decoder GEMM is fused with the cross entropy (MMB_EPI_CE_STATS) and the [M, V] logits are
+        # never written; True: the reference's pred_t / pred_v / pred_s are produced (parity tests, callers that read them)
+        self.materialize_logits = bool(materialize_logits)
         self.alpha, self.beta, self.num_labels = 1.0, 1.0, 7
         dev = device
 
@@ -73,6 +77,7 @@ class Plan:
         # ---- packed metadata
         self.keybias, self.cu = buf(M, dtype=F32), buf(3 * B + 1, dtype=I32)
         self.label_count = buf(4, dtype=I32)
+        self.row_label = buf(M, dtype=I32)
         self.kv_end = buf(3 * B, dtype=I32)     # per sequence: 1 + last unmasked key (attention skips the masked tail)
         # work lists of the persistent attention kernels (longest items first), rebuilt on the device for every batch
         # and shared by all layers; MMB_ATTN_SCHED=0 leaves the items in index order (A/B runs)
@@ -99,7 +104,11 @@ class Plan:
         self.gw_pad = [buf(H, l8, dtype=F32) for l8 in ldf] if training else [None, None]
         self.t_u, self.t_g, self.t_ln = buf(M, H), buf(M, H), buf(M, H)
         self.t_m, self.t_r = buf(M, dtype=F32), buf(M, dtype=F32)
-        self.logits = buf(M, self.Vp)
+        self.logits = buf(M, self.Vp) if self.materialize_logits else None
+        self.ce_stats = None
+        if not self.materialize_logits:
+            # per-row (max, sum exp) records of the fused CE + label logit + row-written flag; zeroed once (the flag plane persists)
+            self.ce_stats = torch.zeros(capi.ce_stats_floats(M, V), device=dev, dtype=F32)
         self.row_lse = buf(M, dtype=F32)
         self.ce_sum = buf(4, dtype=F32)
         self.heads_ws = torch.empty(capi.heads_workspace_bytes(B, H) // 4 + 16, device=dev, dtype=F32)
@@ -111,7 +120,9 @@ class Plan:
         self.wT = [buf(self.Dv, H, dtype=F32), buf(self.Da, H, dtype=F32)]
         self.gscale = torch.ones(1, device=dev, dtype=F32)
         if training:
-            self.dlogits = buf(M, self.Vp)
+            # fused CE: only the labelled rows are ever written (logits by the GEMM epilogue, then dlogits in place by
+            # mmb_ce_sparse_bwd); every other row stays zero from here on
+            self.dlogits = buf(M, self.Vp) if self.materialize_logits else torch.zeros(M, self.Vp, device=dev, dtype=BF16)
             self.GA, self.GC = buf(M, H), buf(M, H)                          # bf16: dgrad outputs / dense-output grads
             self.GB, self.GD = buf(M, H, dtype=F32), buf(M, H, dtype=F32)    # fp32: residual-stream gradients
             self.GT = buf(M, H)                                              # bf16 scratch (LM-head d_tln, dCtx)
@@ -146,10 +157,14 @@ class Plan:
         f = []
         self.pack_args = capi.fill(capi.PackArgs(), keybias=self.keybias, cu_seqlens=self.cu,
                                    label_count=self.label_count, kv_end=self.kv_end, B=self.B, T=self.T, L=[self.Lv, self.La],
-                                   frame_dim=[self.Dv, self.Da])
+                                   frame_dim=[self.Dv, self.Da], row_label=self.row_label, vocab=self.V)
         f.append((self._fn("pack_prepare"), self.pack_args))
         if self.attn_work is not None:
-            self.sched_args = capi.attn_schedule_args(self.cu, self.kv_end, self.attn_work, self.nh, self.max_S)
+            # row labels: lets the backward skip the query rows behind kv_end once it is verified that none is labelled
+            # (their upstream gradient is exactly zero; include/mmbert_sm100.h).  MMB_ATTN_QSKIP=0 for A/B runs.
+            qskip = self.training and os.environ.get("MMB_ATTN_QSKIP", "1") != "0"
+            self.sched_args = capi.attn_schedule_args(self.cu, self.kv_end, self.attn_work, self.nh, self.max_S,
+                                                      row_label=self.row_label if qskip else None)
             f.append((self._fn("attn_schedule"), self.sched_args))
         je = "bert.jointEmbeddings."
         self.embed_args = capi.fill(
@@ -162,7 +177,8 @@ class Plan:
             wT=self.wT, wb=[self._p(je + "Wv.bias"), self._p(je + "Ws.bias")],
             eps1=c.layer_norm_eps, eps2=1e-5, p_drop1=self.p_hidden, p_drop2=self.p_joint, seed=0,
             x0=self.x[0], x0_f32=self.x32[0], mean1=self.e_m1, rstd1=self.e_r1, mean2=self.e_m2, rstd2=self.e_r2, pframe=self.pframe,
-            B=self.B, T=self.T, L=[self.Lv, self.La], H=H, V=self.V, max_pos=c.max_position_embeddings)
+            B=self.B, T=self.T, L=[self.Lv, self.La], H=H, V=self.V, max_pos=c.max_position_embeddings,
+            err_count=self.label_count[3:])
         if self.training:
             capi.fill(self.embed_args, dpre=self.dpre, frames_bf16=self.frames_bf16, gw_pad=self.gw_pad,
                       g_word=self._g("bert.embeddings.word_embeddings.weight"),
@@ -217,14 +233,29 @@ class Plan:
         f.append((self._fn("dropout_residual_ln_fwd"),
                   capi.drln_fwd_args(self.t_g, None, self._p(tp + "LayerNorm.weight"), self._p(tp + "LayerNorm.bias"),
                                      self.t_ln, self.t_m, self.t_r, c.layer_norm_eps)))
-        self._gemm(f, self.t_ln, self._w("bert.embeddings.word_embeddings.weight"), self.logits, M, self.V, H,
-                   bias=self._p("cls.predictions.bias"))
-        self.ce_args = capi.fill(capi.CeArgs(), logits=self.logits, label_count=self.label_count, row_lse=self.row_lse,
-                                 loss_sum=self.ce_sum, gscale=self.gscale, coef=self.alpha / 3.0, V=self.V,
-                                 ldl=self.Vp, B=self.B, T=self.T, L=[self.Lv, self.La], dense=1 if self.dense_mlm else 0)
-        if self.training:
-            capi.fill(self.ce_args, dlogits=self.dlogits)
-        f.append((self._fn("ce_fwd"), self.ce_args))
+        word_bf = self._w("bert.embeddings.word_embeddings.weight")
+        if self.materialize_logits:
+            self._gemm(f, self.t_ln, word_bf, self.logits, M, self.V, H, bias=self._p("cls.predictions.bias"))
+            self.ce_args = capi.fill(capi.CeArgs(), logits=self.logits, label_count=self.label_count, row_lse=self.row_lse,
+                                     loss_sum=self.ce_sum, gscale=self.gscale, coef=self.alpha / 3.0, V=self.V,
+                                     ldl=self.Vp, B=self.B, T=self.T, L=[self.Lv, self.La], dense=1 if self.dense_mlm else 0)
+            if self.training:
+                capi.fill(self.ce_args, dlogits=self.dlogits)
+            f.append((self._fn("ce_fwd"), self.ce_args))
+        else:
+            # fused CE (MMBertForPretraining.py:293 + :381-384): the decoder GEMM keeps online softmax statistics of the
+            # labelled rows and stores only those rows' logits (training: into the dlogits buffer)
+            C = self.dlogits if self.training else None
+            self._gemm(f, self.t_ln, word_bf, C, M, self.V, H, bias=self._p("cls.predictions.bias"),
+                       epilogue=capi.EPI_CE_STATS, aux=self.row_label, aux2=self.ce_stats, ldc=self.Vp, ldaux=0)
+            gb0 = self.store.offsets["cls.predictions.bias"]
+            self.ce_args = capi.fill(capi.CeSparseArgs(), row_label=self.row_label, stats=self.ce_stats,
+                                     label_count=self.label_count, row_lse=self.row_lse, loss_sum=self.ce_sum,
+                                     gscale=self.gscale, coef=self.alpha / 3.0, V=self.V, ldl=self.Vp, B=self.B, T=self.T,
+                                     L=[self.Lv, self.La])
+            if self.training:
+                capi.fill(self.ce_args, dlogits=self.dlogits, dbias=self.store.grad[gb0:gb0 + self.V])
+            f.append((self._fn("ce_sparse_fwd"), self.ce_args))
         hp = dict(
             seq_out=self.seq_out, cu_seqlens=self.cu, workspace=self.heads_ws,
             w_pooler=self._p("bert.pooler.dense.weight"), b_pooler=self._p("bert.pooler.dense.bias"),
@@ -263,13 +294,16 @@ class Plan:
         MN, K_ = capi.MAJOR_MN, capi.MAJOR_K
         ATOM = capi.EPI_ATOMIC_ADD_F32
         word_bf = self._w("bert.embeddings.word_embeddings.weight")
-        b.append((self._fn("ce_bwd"), self.ce_args))
+        b.append((self._fn("ce_bwd" if self.materialize_logits else "ce_sparse_bwd"), self.ce_args))
         # tied decoder: d_tln = dlogits · Wword ; g_word += dlogits^T · t_ln ; g_dec_bias += colsum(dlogits)
         self._gemm(b, self.dlogits, word_bf, self.GT, M, H, V, b_major=MN)
         self._gemm(b, self.dlogits, self.t_ln, self._g("bert.embeddings.word_embeddings.weight"), V, H, M,
                    a_major=MN, b_major=MN, epilogue=ATOM, split_k=_split_k(V, H, M))
-        gbias = st.grad[st.offsets["cls.predictions.bias"]:st.offsets["cls.predictions.bias"] + self.Vp]
-        b.append((self._fn("colsum_bf16"), capi.colsum_args(self.dlogits, gbias)))
+        if self.materialize_logits:
+            gbias = st.grad[st.offsets["cls.predictions.bias"]:st.offsets["cls.predictions.bias"] + self.Vp]
+            b.append((self._fn("colsum_bf16"), capi.colsum_args(self.dlogits, gbias)))
+        else:
+            b.append((self._fn("colsum_rows_bf16"), self.ce_args))
         tp = "cls.predictions.transform."
         b.append((self._fn("dropout_residual_ln_bwd"),
                   capi.fill(capi.drln_bwd_args(self.GT, None, self.t_g, None, self.t_m, self.t_r,
@@ -368,7 +402,8 @@ class Plan:
                   mask_frame_stride=[0 if t.dim() == 3 else 1 for t in mf], labels=labs)
         capi.fill(self.embed_args, ids=ids, token_type=tt, frames=frames,
                   frames_dtype=[capi.dtype_code(t) for t in frames])
-        capi.fill(self.ce_args, labels=labs)
+        if self.materialize_logits:
+            capi.fill(self.ce_args, labels=labs)
         capi.fill(self.heads_args, ap_label=ap, sentiment=sent)
 
     def bind_inputs(self, input_ids, token_type_ids, attention_mask, masked_labels, ap_label, sentiment):

@@ -32,6 +32,7 @@ class PlanF32:
         nfr = B * (Lv + La)
         self.max_S = T + max(Lv, La)
         self.alpha, self.beta, self.num_labels = 1.0, 1.0, 7
+        self.materialize_logits = True                    # the validation path always produces pred_t / pred_v / pred_s
 
         def buf(*shape, dtype=F32):
             return torch.empty(*shape, device=device, dtype=dtype)
@@ -59,6 +60,8 @@ class PlanF32:
     _fn = Plan._fn
     refresh_frame_weights = Plan.refresh_frame_weights
     bind_inputs = Plan.bind_inputs
+    convert_inputs = Plan.convert_inputs
+    bind_tensors = Plan.bind_tensors
     set_loss_weights = Plan.set_loss_weights
     run = staticmethod(Plan.run)
 

@@ -37,7 +37,7 @@ for rep in range(reps):
             s.record(stream); capi.check(fn(ctypes.byref(a), sp), "launch"); e.record(stream)
             key = fn.__name__ if hasattr(fn, "__name__") else str(fn)
             if "gemm" in key:
-                epi = {0: "bf16", 1: "gelu", 2: "relu", 3: "f32", 4: "atomic", 5: "dgelu", 6: "gelu+grad", 7: "mul_aux"}[a.epilogue]
+                epi = {0: "bf16", 1: "gelu", 2: "relu", 3: "f32", 4: "atomic", 5: "dgelu", 6: "gelu+grad", 7: "mul_aux", 8: "ce_stats"}[a.epilogue]
                 key = f"gemm M={a.M} N={a.N} K={a.K} {'MN' if a.a_major else 'K'}{'MN' if a.b_major else 'K'} {epi} sk={a.split_k}"
                 fl = 2.0 * a.M * a.N * a.K
             else:

@@ -426,3 +426,61 @@ def test_attention_with_work_lists_is_bit_identical(p_drop):
     assert torch.isfinite(res[1][2]).all()
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
     assert torch.equal(res[0][2], res[1][2])
+
+
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_attention_backward_skips_the_zero_gradient_query_tail_exactly(p_drop):
+    """mmb_attn_schedule with row labels: when no row at or behind kv_end is labelled, the upstream gradient is exactly
+    zero there and the backward skips those QUERY rows (include/mmbert_sm100.h).  With a dctx that is zero on those rows,
+    all three gradients must be bit-identical to the full sweep; with a label in a tail the schedule must NOT set the
+    flag (and the results stay those of the full sweep even for a dctx that is non-zero there)."""
+    from msa_b200 import capi
+    g = torch.Generator().manual_seed(18)
+    nh = 12
+    lens = torch.randint(1, 551, (45,), generator=g).tolist() + [550, 40, 300, 129, 550]
+    valid = [int(torch.randint(1, s + 1, (1,), generator=g)) for s in lens[:-5]] + [131, 0, 300, 128, 64]
+    H, rows = nh * 64, sum(lens)
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    torch.manual_seed(19)
+    qkv = _bf(torch.randn(rows, 3 * H, device="cuda"))
+    keybias = torch.zeros(rows, device="cuda")
+    dctx = _bf(torch.randn(rows, H, device="cuda"))
+    row_label = torch.full((rows,), -100, device="cuda", dtype=torch.int32)
+    for i, (s, v) in enumerate(zip(lens, valid)):
+        keybias[cu[i] + v:cu[i] + s] = -10000.0
+        if v > 0:
+            dctx[cu[i] + v:cu[i] + s] = 0          # the premise the labels guarantee
+            row_label[cu[i] + int(torch.randint(0, v, (1,), generator=g))] = 5
+    kv_end = torch.tensor(valid, device="cuda", dtype=torch.int32)
+    cu_t = torch.tensor(cu, device="cuda", dtype=torch.int32)
+
+    def run(wl, d):
+        ctx = torch.zeros(rows, H, device="cuda", dtype=torch.bfloat16)
+        lse = torch.zeros(nh, rows, device="cuda")
+        dqkv = torch.full((rows, 3 * H), 7.0, device="cuda", dtype=torch.bfloat16)
+        bwd_ws = capi.attn_bwd_workspace(rows, nh, "cuda")
+        a = capi.attn_args(qkv, ctx, lse, keybias, cu_t, H, nh, max(lens), dctx=d, dqkv=dqkv, bwd_ws=bwd_ws,
+                           kv_end=kv_end, p_drop=p_drop, seed=4, rng_stream=1, work=wl)
+        capi.call("attn_fwd", a)
+        capi.call("attn_bwd", a)
+        return dqkv.float()
+
+    plain = capi.attn_schedule_buffer(len(lens), nh, max(lens), "cuda")
+    capi.call("attn_schedule", capi.attn_schedule_args(cu_t, kv_end, plain, nh, max(lens)))
+    skip = capi.attn_schedule_buffer(len(lens), nh, max(lens), "cuda")
+    capi.call("attn_schedule", capi.attn_schedule_args(cu_t, kv_end, skip, nh, max(lens), row_label=row_label))
+    assert (int(plain[0, 2]) >> 30) == 0 and (int(skip[0, 2]) >> 30) == 1
+    assert int(skip[0, 2]) & 0x3fffffff == int(plain[0, 2])
+    ref, got = run(plain, dctx), run(skip, dctx)
+    assert torch.isfinite(got).all()
+    assert torch.equal(ref, got)
+    # a label behind kv_end: the premise fails, the flag must stay clear
+    bad = row_label.clone()
+    i = lens.index(550)
+    bad[cu[i] + valid[i] + 3] = 9
+    capi.call("attn_schedule", capi.attn_schedule_args(cu_t, kv_end, skip, nh, max(lens), row_label=bad))
+    assert (int(skip[0, 2]) >> 30) == 0
+    dense = _bf(torch.randn(rows, H, device="cuda"))
+    assert torch.equal(run(plain, dense), run(skip, dense))
