@@ -54,6 +54,7 @@ struct GemmParams {
     // UMMA smem-descriptor parameters per operand (bytes): leading/stride byte offsets, per-UMMA_K advance
     uint32_t a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step;
     int dbg;  // bring-up only: bit 4 = epilogue skips global stores, bit 5 = epilogue skips the TMEM loads too
+    int tma_store;  // CTA-pair kernel: bf16 outputs leave through cp.async.bulk.tensor stores (tmC / tmAux)
 };
 
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], int ncols_valid) {
@@ -300,6 +301,93 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[3
             }
         } break;
         default: break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- TMA-store epilogue
+// CTA-pair kernel, bf16 outputs.  The per-warp staging tile is laid out exactly as a swizzled TMA box, so that ONE elected
+// lane hands the whole tile to the TMA unit (cp.async.bulk.tensor.2d.global.shared::cta): full-line writes, no LDS / STG
+// instructions, rows / columns beyond the matrix clipped by the tensor map.  Measured before (B200, K = 768 GEMMs of the
+// MOSEI shape): with the st.global epilogue the tile period followed the ~1.5 TB/s the 64-byte row segments reached
+// (QKV 1 198 TF/s against 1 575 with the epilogue's stores removed).
+//   8 epilogue warps : staging = 32 rows x 64 columns (128-byte rows, SWIZZLE_128B), two stores per 128-column strip
+//   16 epilogue warps: staging = 2 streams x (32 rows x 32 columns) (64-byte rows, SWIZZLE_64B: stage_off above)
+__device__ __forceinline__ uint32_t stage_off128(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
+
+__device__ __forceinline__ void bias_add_chunk(const GemmParams& p, float (&v)[32], int col0) {
+    const int nvalid = min(32, p.N - col0);
+    if (p.bias == nullptr) return;
+    if (nvalid == 32) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);
+            const float2 lo = add2(make_float2(v[4 * i], v[4 * i + 1]), make_float2(b.x, b.y));
+            const float2 hi = add2(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(b.z, b.w));
+            v[4 * i] = lo.x;
+            v[4 * i + 1] = lo.y;
+            v[4 * i + 2] = hi.x;
+            v[4 * i + 3] = hi.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < nvalid) v[i] += __ldg(p.bias + col0 + i);
+    }
+}
+
+// the staging tile may be rewritten once the TMA unit has read the previous store out of it (lane 0 issued it)
+__device__ __forceinline__ void stage_acquire(int lane) {
+    if (lane == 0) ptx::bulk_wait_read<0>();
+    __syncwarp();
+}
+// 8-warp layout: this lane's 32 values -> columns [32 * half, 32 * half + 32) of its row in the 64-column tile
+__device__ __forceinline__ void stage_row128(uint32_t st, const float (&v)[32], int lane, int half) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        sts128(st + stage_off128(lane, 4 * half + j), pack_bf16x2(v[8 * j + 0], v[8 * j + 1]),
+               pack_bf16x2(v[8 * j + 2], v[8 * j + 3]), pack_bf16x2(v[8 * j + 4], v[8 * j + 5]),
+               pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+}
+// all lanes' shared-memory writes -> visible to the async proxy -> one lane issues the store(s)
+__device__ __forceinline__ void stage_release(const CUtensorMap* tm0, uint32_t st0, const CUtensorMap* tm1, uint32_t st1,
+                                              int col, int row, int lane) {
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+        ptx::tma_store_2d(tm0, st0, col, row);
+        if (tm1 != nullptr) ptx::tma_store_2d(tm1, st1, col, row);
+        ptx::bulk_commit();
+    }
+}
+
+// element-wise part of the bf16 epilogues on one 32-column chunk (bias already added); MUL_AUX is handled by the caller.
+// Returns through v (the C values) and, for GELU_GRAD / GELU with aux, through w (the aux stream).
+__device__ __forceinline__ void activate_chunk(int epilogue, bool gelu_aux, float (&v)[32], float (&w)[32]) {
+    if (epilogue == MMB_EPI_GELU_GRAD_BF16) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            float2 g, dg;
+            gelu_fast2(make_float2(v[i], v[i + 1]), g, dg);
+            v[i] = g.x;
+            v[i + 1] = g.y;
+            w[i] = dg.x;
+            w[i + 1] = dg.y;
+        }
+    } else if (epilogue == MMB_EPI_GELU_BF16) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            float2 g, dg;
+            if (gelu_aux) {
+                w[i] = v[i];            // pre-activation (rounded to bf16 by the pack)
+                w[i + 1] = v[i + 1];
+            }
+            gelu_fast2(make_float2(v[i], v[i + 1]), g, dg);
+            v[i] = g.x;
+            v[i + 1] = g.y;
+        }
+    } else if (epilogue == MMB_EPI_RELU_BF16) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
     }
 }
 
@@ -586,18 +674,21 @@ constexpr uint32_t kPeerMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a
 template <int k2EpiWarps>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg2<k2EpiWarps>::kThreads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
                          const GemmParams p) {
     constexpr int k2Stages = Cfg2<k2EpiWarps>::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t smem_base = ptx::smem_u32(smem);
-    const uint32_t bar_base = smem_base + k2Stages * k2StageBytes;
+    // [operand ring][epilogue staging: k2EpiWarps x 4 KB, 1024-byte aligned (swizzled TMA-store boxes)][barriers]
+    constexpr int kBarOff = k2Stages * k2StageBytes + k2EpiWarps * kStageBytesPerWarp;
+    const uint32_t bar_base = smem_base + kBarOff;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (k2Stages + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * k2Stages + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * k2Stages + 2 + a); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + k2Stages * k2StageBytes + 8 * (2 * k2Stages + 4));
-    uint8_t* epi_stage = smem + k2Stages * k2StageBytes + 256;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kBarOff + 8 * (2 * k2Stages + 4));
+    uint8_t* epi_stage = smem + k2Stages * k2StageBytes;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -609,6 +700,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmB);
+        if (p.tma_store) {
+            ptx::prefetch_tensormap(&tmC);
+            ptx::prefetch_tensormap(&tmAux);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < k2Stages; ++s) {
@@ -812,34 +907,86 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 if (p.epilogue == MMB_EPI_CE_STATS && colw < p.N)
                     ce_stats_warp(p, tmem_base + acc * TN + half * kColsPerWarp + ((uint32_t)(quarter * 32) << 16), row_base, lane, colw);
             }
-            if (aux_pref) {
-                __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(p.C);
+            const uint32_t tacc = tmem_base + acc * TN + half * kColsPerWarp + ((uint32_t)(quarter * 32) << 16);
+            const bool has_aux = p.epilogue == MMB_EPI_GELU_GRAD_BF16 || (p.epilogue == MMB_EPI_GELU_BF16 && p.aux != nullptr);
+            // 8 warps: one output stream (multiply needs its prefetched aux values); 16 warps: no multiply epilogue
+            const bool tma_epi = p.tma_store && !(p.dbg & 48) &&
+                                 (k2EpiWarps == 8 ? (!has_aux && (p.epilogue != MMB_EPI_MUL_AUX_BF16 || aux_pref))
+                                                  : p.epilogue != MMB_EPI_MUL_AUX_BF16);
+            bool done = p.epilogue == MMB_EPI_CE_STATS;
+            if (tma_epi && colw < p.N) {
+                done = true;
+                if constexpr (k2EpiWarps == 8) {
+                    // 128-column strip = two 64-column boxes (plain / ReLU / multiply epilogues; GELU only in A/B runs)
 #pragma unroll
-                for (int ci = 0; ci < kColsPerWarp / 32; ++ci) {
-                    uint32_t raw[32];
-                    const uint32_t taddr = tmem_base + acc * TN + half * kColsPerWarp + ci * 32 + ((uint32_t)(quarter * 32) << 16);
-                    ptx::tmem_ld_32x32(taddr, raw);
-                    ptx::tmem_ld_wait();
-                    float v[32];
+                    for (int g = 0; g < kColsPerWarp / 64; ++g) {     // unrolled: auxr[] stays in registers
+                        const int colg = colw + g * 64;
+                        if (colg >= p.N) break;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint4 q = auxr[4 * ci + j];
-                        const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
-                        v[8 * j + 0] = __uint_as_float(raw[8 * j + 0]) * p.alpha * f0.x;
-                        v[8 * j + 1] = __uint_as_float(raw[8 * j + 1]) * p.alpha * f0.y;
-                        v[8 * j + 2] = __uint_as_float(raw[8 * j + 2]) * p.alpha * f1.x;
-                        v[8 * j + 3] = __uint_as_float(raw[8 * j + 3]) * p.alpha * f1.y;
-                        v[8 * j + 4] = __uint_as_float(raw[8 * j + 4]) * p.alpha * f2.x;
-                        v[8 * j + 5] = __uint_as_float(raw[8 * j + 5]) * p.alpha * f2.y;
-                        v[8 * j + 6] = __uint_as_float(raw[8 * j + 6]) * p.alpha * f3.x;
-                        v[8 * j + 7] = __uint_as_float(raw[8 * j + 7]) * p.alpha * f3.y;
+                        for (int h = 0; h < 2; ++h) {
+                            const int col0 = colg + 32 * h;
+                            uint32_t raw[32];
+                            ptx::tmem_ld_32x32(tacc + g * 64 + h * 32, raw);
+                            ptx::tmem_ld_wait();
+                            float v[32], w[32];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                            if (p.alpha != 1.0f) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+                            }
+                            if (p.epilogue == MMB_EPI_MUL_AUX_BF16) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const uint4 q = auxr[8 * g + 4 * h + j];
+                                    const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
+                                    v[8 * j + 0] *= f0.x;
+                                    v[8 * j + 1] *= f0.y;
+                                    v[8 * j + 2] *= f1.x;
+                                    v[8 * j + 3] *= f1.y;
+                                    v[8 * j + 4] *= f2.x;
+                                    v[8 * j + 5] *= f2.y;
+                                    v[8 * j + 6] *= f3.x;
+                                    v[8 * j + 7] *= f3.y;
+                                }
+                            } else {
+                                bias_add_chunk(p, v, col0);
+                                activate_chunk(p.epilogue, false, v, w);
+                            }
+                            if (h == 0) stage_acquire(lane);
+                            stage_row128(stage_buf, v, lane, h);
+                        }
+                        stage_release(&tmC, stage_buf, nullptr, 0, colg, row_base, lane);
                     }
-                    stage_row(stage_buf, v, lane);
-                    flush_stage(stage_buf, Cb, p.ldc, row_base, p.M, colw + ci * 32, p.N, lane);
+                } else {
+                    // 64-column strip = two 32-column boxes per stream (GELU epilogues: C and, in training, the aux stream)
+#pragma unroll 1
+                    for (int c = 0; c < kColsPerWarp; c += 32) {
+                        const int col0 = colw + c;
+                        if (col0 >= p.N) break;
+                        uint32_t raw[32];
+                        ptx::tmem_ld_32x32(tacc + c, raw);
+                        ptx::tmem_ld_wait();
+                        float v[32], w[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                        if (p.alpha != 1.0f) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+                        }
+                        bias_add_chunk(p, v, col0);
+                        activate_chunk(p.epilogue, has_aux, v, w);
+                        stage_acquire(lane);
+                        stage_row(stage_buf, v, lane);
+                        if (has_aux) stage_row(stage_buf + 2048, w, lane);
+                        stage_release(&tmC, stage_buf, has_aux ? &tmAux : nullptr, stage_buf + 2048, col0, row_base, lane);
+                    }
                 }
+            } else if (p.tma_store) {
+                stage_acquire(lane);       // the st.global paths below reuse the staging tile
             }
 #pragma unroll 1
-            for (int c = (aux_pref || p.epilogue == MMB_EPI_CE_STATS) ? kColsPerWarp : 0; c < kColsPerWarp; c += 32) {
+            for (int c = done ? kColsPerWarp : 0; c < kColsPerWarp; c += 32) {
                 const int col0 = n_blk * TN + half * kColsPerWarp + c;
                 if (col0 >= p.N) break;
                 if (p.dbg & 32) continue;
@@ -868,6 +1015,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
 
     // teardown: nobody may exit while the peer can still touch its shared memory / barriers / TMEM
+    if (warp >= kEpiWarp0 && lane == 0 && p.tma_store) ptx::bulk_wait_read<0>();   // staging tiles outlive their last store
     __syncwarp();
     ptx::tc_fence_before();
     ptx::cluster_sync();
@@ -898,7 +1046,7 @@ static PFN_encodeTiled get_encode_fn() {
 struct TmapKey {
     const void* ptr;
     uint64_t d0, d1, ld;
-    uint32_t b0, b1;
+    uint32_t b0, b1;   // b1 carries the swizzle mode in its top bit (box rows are <= 256)
     bool operator==(const TmapKey& o) const {
         return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && ld == o.ld && b0 == o.b0 && b1 == o.b1;
     }
@@ -915,10 +1063,17 @@ struct TmapKeyHash {
 
 // bf16 2-D tensor map, SWIZZLE_128B: dims {d0 (contiguous), d1 (rows)}, row stride ld elements, box {b0, b1}.
 // Cached: the encode is pure host work but the engine issues ~150 GEMMs per step over a fixed buffer set.
+static int make_tmap_bf16_sw(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0, uint32_t b1,
+                             bool sw64);
 int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0, uint32_t b1) {
+    return make_tmap_bf16_sw(out, ptr, d0, d1, ld, b0, b1, false);
+}
+// sw64: SWIZZLE_64B (64-byte box rows: the 16-warp epilogue's store tiles) instead of SWIZZLE_128B
+static int make_tmap_bf16_sw(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0, uint32_t b1,
+                             bool sw64) {
     static std::mutex mu;
     static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
-    TmapKey key{ptr, d0, d1, ld, b0, b1};
+    TmapKey key{ptr, d0, d1, ld, b0, b1 | (sw64 ? 0x80000000u : 0u)};
     {
         std::lock_guard<std::mutex> g(mu);
         auto it = cache.find(key);
@@ -937,8 +1092,8 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, 
     cuuint32_t box[2] = {b0, b1};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled failed (%d) ptr=%p dims=(%llu,%llu) ld=%llu box=(%u,%u)", (int)r, ptr,
                        (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)ld, b0, b1);
@@ -972,6 +1127,7 @@ static void fill_common(GemmParams& p, const mmb_gemm_args* a, int tile_m, int t
     p.n_tiles = (a->N + tile_n - 1) / tile_n;
     p.total_tiles = p.m_tiles * p.n_tiles * p.split_k;
     p.alpha = a->alpha;
+    p.tma_store = 0;
     p.dbg = a->dbg_flags;
     static const int lane_issue = [] {                       // MMB_GEMM_ISSUE=lane: single-lane MMA issue (A/B runs)
         const char* e = getenv("MMB_GEMM_ISSUE");
@@ -1063,10 +1219,29 @@ static int launch_gemm_2cta(const mmb_gemm_args* a, cudaStream_t stream) {
     // GELU epilogues are long latency chains: 16 epilogue warps; everything else: 8 (dbg bit 6 flips the choice, for A/B runs)
     bool wide = a->epilogue == MMB_EPI_GELU_BF16 || a->epilogue == MMB_EPI_GELU_GRAD_BF16;
     if (a->dbg_flags & 64) wide = !wide;
+    // bf16 outputs leave through TMA stores (dbg bit 8 / MMB_GEMM_STORE=stg keeps the st.global epilogue, for A/B runs)
+    static const bool stg_env = [] {
+        const char* e = getenv("MMB_GEMM_STORE");
+        return e != nullptr && e[0] == 's';
+    }();
+    const bool bf16_out = a->epilogue == MMB_EPI_STORE_BF16 || a->epilogue == MMB_EPI_GELU_BF16 ||
+                          a->epilogue == MMB_EPI_RELU_BF16 || a->epilogue == MMB_EPI_GELU_GRAD_BF16 ||
+                          a->epilogue == MMB_EPI_MUL_AUX_BF16;
+    p.tma_store = (bf16_out && !stg_env && !(a->dbg_flags & 256)) ? 1 : 0;
+    CUtensorMap tmC = tmA, tmAux = tmA;      // placeholders when unused (never dereferenced)
+    if (p.tma_store) {
+        const bool aux_out = a->epilogue == MMB_EPI_GELU_GRAD_BF16 || (a->epilogue == MMB_EPI_GELU_BF16 && a->aux != nullptr);
+        rc = make_tmap_bf16_sw(&tmC, a->C, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldc, wide ? 32 : 64, 32, wide);
+        if (rc == MMB_OK && aux_out) {
+            MMB_REQUIRE(((uintptr_t)a->aux % 16) == 0, "mmb_gemm: aux must be 16-byte aligned");
+            rc = make_tmap_bf16_sw(&tmAux, a->aux, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldaux, wide ? 32 : 64, 32, wide);
+        }
+        if (rc != MMB_OK) return rc;
+    }
     if (wide)
-        gemm_tcgen05_2cta_kernel<16><<<2 * clusters, Cfg2<16>::kThreads, Cfg2<16>::kSmemBytes, stream>>>(tmA, tmB, p);
+        gemm_tcgen05_2cta_kernel<16><<<2 * clusters, Cfg2<16>::kThreads, Cfg2<16>::kSmemBytes, stream>>>(tmA, tmB, tmC, tmAux, p);
     else
-        gemm_tcgen05_2cta_kernel<8><<<2 * clusters, Cfg2<8>::kThreads, Cfg2<8>::kSmemBytes, stream>>>(tmA, tmB, p);
+        gemm_tcgen05_2cta_kernel<8><<<2 * clusters, Cfg2<8>::kThreads, Cfg2<8>::kSmemBytes, stream>>>(tmA, tmB, tmC, tmAux, p);
     return check_launch("gemm_tcgen05_2cta_kernel");
 }
 

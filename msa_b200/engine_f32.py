@@ -63,6 +63,9 @@ class PlanF32:
     convert_inputs = Plan.convert_inputs
     bind_tensors = Plan.bind_tensors
     set_loss_weights = Plan.set_loss_weights
+
+    def set_seed(self, seed):         # dropout-free path
+        pass
     run = staticmethod(Plan.run)
 
     def _linear(self, seq, X, W, bias, Y, M, N, K, act=capi.ACT_NONE):

@@ -182,8 +182,13 @@ def heads(sd, cfg, x0, ap_v, ap_s, sentiment, dtype=torch.float64):
 
 
 def forward(sd, cfg, input_ids, token_type_ids, attention_mask, masked_labels, ap_label, sentiment,
-            alpha=1.0, beta=1.0, dtype=torch.float64, dropout=None):
-    """MMBertForPretraining.forward -> ((13-tuple), logits), same structure as the reference."""
+            alpha=1.0, beta=1.0, dtype=torch.float64, dropout=None, cls_values=None):
+    """MMBertForPretraining.forward -> ((13-tuple), logits), same structure as the reference.
+    ``cls_values`` ([3B, H], test aid): the heads are EVALUATED at these [CLS] rows (a candidate's own encoder output)
+    while their gradient still flows into this restatement's encoder (straight-through).  The fusion head's
+    relu(attn(.)) gates (MMBertForPretraining.py:407-409) then take the candidate's side of every near-zero
+    pre-activation, so that a gate flipped by bf16 rounding — a discontinuity of the model, not an error of the
+    candidate — does not show up as a gradient difference in every encoder parameter."""
     sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
     ids_t, vis, aud, ids_v, ids_s = input_ids
     m_t, (m_tv, m_v), (m_ts, m_s) = attention_mask
@@ -199,6 +204,8 @@ def forward(sd, cfg, input_ids, token_type_ids, attention_mask, masked_labels, a
            + _cross_entropy(pred_v.reshape(-1, V), lab_v.reshape(-1))
            + _cross_entropy(pred_s.reshape(-1, V), lab_s.reshape(-1))) / 3.0
     x0 = torch.cat((seq_t[:, 0], seq_v[:, 0], seq_s[:, 0]), dim=0)
+    if cls_values is not None:
+        x0 = x0 + (cls_values.to(dtype) - x0).detach()
     ap, label, nce, out_logits, rel_t, al_v, al_s = heads(sd, cfg, x0, ap_v, ap_s, sentiment, dtype=dtype)
     joint = alpha * mlm + ap + label - beta * nce
     return (joint, None, None, None, ap, label, nce, pred_t, rel_t, pred_v, al_v, pred_s, al_s), out_logits
@@ -233,7 +240,7 @@ TIED = {"cls.predictions.decoder.weight": "bert.embeddings.word_embeddings.weigh
         "cls.predictions.decoder.bias": "cls.predictions.bias"}
 
 
-def forward_backward(sd, cfg, batch, alpha=1.0, beta=1.0, dtype=torch.float64, dropout=None):
+def forward_backward(sd, cfg, batch, alpha=1.0, beta=1.0, dtype=torch.float64, dropout=None, cls_values=None):
     """Runs forward + ``joint_loss.backward()`` on leaf copies of ``sd``.
     Returns (outputs, logits, grads) where grads maps canonical parameter names to gradients
     (None for parameters the path does not touch)."""
@@ -245,7 +252,7 @@ def forward_backward(sd, cfg, batch, alpha=1.0, beta=1.0, dtype=torch.float64, d
     full = dict(leaves)
     for alias, canon in TIED.items():
         full[alias] = leaves[canon]
-    out, logits = forward(full, cfg, alpha=alpha, beta=beta, dtype=dtype, dropout=dropout, **batch)
+    out, logits = forward(full, cfg, alpha=alpha, beta=beta, dtype=dtype, dropout=dropout, cls_values=cls_values, **batch)
     out[0].backward()
     grads = {k: (v.grad if v.grad is not None else None) for k, v in leaves.items()}
     return out, logits, grads

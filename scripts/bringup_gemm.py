@@ -54,6 +54,33 @@ CASES = {
     "x_ffn1_nold": (16000, 3072, 768, 0, 0, "gelu", 1, 32),
     "x_ffn2_nold": (16000, 768, 3072, 0, 0, "bias", 1, 32),
     "x_big_nold": (16384, 4096, 4096, 0, 0, "store", 1, 32),
+    # round 2: the MOSEI-shape epilogue-bound GEMMs, dissected the same way
+    "z_ffn1_gg": (73600, 3072, 768, 0, 0, "gelu_grad", 1, 0),
+    "z_ffn1_gg_nostore": (73600, 3072, 768, 0, 0, "gelu_grad", 1, 16),
+    "z_ffn1_gg_nold": (73600, 3072, 768, 0, 0, "gelu_grad", 1, 32),
+    "z_ffn2d_mul": (73600, 3072, 768, 0, 1, "mul_aux", 1, 0),
+    "z_ffn2d_mul_nostore": (73600, 3072, 768, 0, 1, "mul_aux", 1, 16),
+    "z_ffn2d_mul_nold": (73600, 3072, 768, 0, 1, "mul_aux", 1, 32),
+    "z_qkv": (73600, 2304, 768, 0, 0, "bias", 1, 0),
+    "z_qkv_nostore": (73600, 2304, 768, 0, 0, "bias", 1, 16),
+    "z_qkv_nold": (73600, 2304, 768, 0, 0, "bias", 1, 32),
+    "z_ffn1_plain": (73600, 3072, 768, 0, 0, "bias", 1, 0),
+    "z_ffn2": (73600, 768, 3072, 0, 0, "bias", 1, 0),
+    "z_ffn2_nold": (73600, 768, 3072, 0, 0, "bias", 1, 32),
+    "z_wo": (73600, 768, 768, 0, 0, "bias", 1, 0),
+    "z_wo_nold": (73600, 768, 768, 0, 0, "bias", 1, 32),
+    # dbg bit 8 (256): st.global epilogue instead of the TMA stores
+    "s_ffn1_gg": (73600, 3072, 768, 0, 0, "gelu_grad", 1, 256),
+    "s_ffn2d_mul": (73600, 3072, 768, 0, 1, "mul_aux", 1, 256),
+    "s_qkv": (73600, 2304, 768, 0, 0, "bias", 1, 256),
+    "s_wo": (73600, 768, 768, 0, 0, "bias", 1, 256),
+    "s_ffn2": (73600, 768, 3072, 0, 0, "bias", 1, 256),
+    "z_c2_qkv": (16000, 2304, 768, 0, 0, "bias", 1, 0), "s_c2_qkv": (16000, 2304, 768, 0, 0, "bias", 1, 256),
+    "z_c2_ffn1_gg": (16000, 3072, 768, 0, 0, "gelu_grad", 1, 0), "s_c2_ffn1_gg": (16000, 3072, 768, 0, 0, "gelu_grad", 1, 256),
+    "z_ragged_gg": (1000, 1000, 136, 0, 0, "gelu_grad", 1, 0),
+    "z_ragged_bias": (1000, 1000, 136, 0, 0, "bias", 1, 0),
+    "z_ragged_mul": (1000, 1024, 136, 0, 1, "mul_aux", 1, 0),
+    "z_vocab": (2048, 30522, 768, 0, 0, "bias", 1, 0),
 }
 
 
@@ -97,6 +124,14 @@ def run_case(name):
         e = capi.EPI_GELU_BF16; kw["bias"] = bias
         pre = (ref + bias).to(torch.bfloat16).float()
         ref = torch.nn.functional.gelu(pre)
+    elif epi == "gelu_grad":
+        e = capi.EPI_GELU_GRAD_BF16; kw["bias"] = bias
+        aux = torch.zeros(M, ldc, device=dev, dtype=torch.bfloat16)[:, :N]
+        ref = torch.nn.functional.gelu(ref + bias)
+    elif epi == "mul_aux":
+        e = capi.EPI_MUL_AUX_BF16
+        aux = torch.randn(M, ldc, device=dev).to(torch.bfloat16)[:, :N]
+        ref = ref * aux.float()
     elif epi == "dgelu":
         e = capi.EPI_DGELU_BF16
         aux = torch.randn(M, ldc, device=dev).to(torch.bfloat16)[:, :N]
@@ -119,6 +154,10 @@ def run_case(name):
     res = {"case": name, "max_abs_err": err, "ref_max": scale, "rel": err / max(scale, 1e-9)}
     if epi == "gelu":
         res["aux_err"] = (aux.float() - pre).abs().max().item()
+    if epi == "gelu_grad":
+        u = (A.float() @ B.float().t() + bias).requires_grad_(True)
+        torch.nn.functional.gelu(u).sum().backward()
+        res["aux_err"] = (aux.float() - u.grad).abs().max().item()
     if True:
         for _ in range(3):
             launch()
