@@ -122,6 +122,8 @@ def profile_gemm(model, plan):
                 # algorithmic HBM bytes of the launch: both operands once, the output once (f32 for the wgrad epilogues),
                 # plus the auxiliary stream of the GELU / multiply epilogues
                 out_b = 4 if a.epilogue in (capi.EPI_STORE_F32, capi.EPI_ATOMIC_ADD_F32) else 2
+                if a.epilogue == capi.EPI_CE_STATS:
+                    out_b = 0               # fused cross entropy: only the labelled rows (~1 %) are written
                 aux_b = 2 if (a.aux and a.epilogue in (capi.EPI_GELU_BF16, capi.EPI_DGELU_BF16, capi.EPI_GELU_GRAD_BF16,
                                                        capi.EPI_MUL_AUX_BF16)) else 0
                 abytes += 2.0 * a.K * (a.M + a.N) + float(a.M) * a.N * (out_b + aux_b)
@@ -143,6 +145,37 @@ def measured_traffic(workload_name):
         except (OSError, ValueError, KeyError):
             continue
     return None
+
+
+def executed_train_gflop_per_sample(shape, workload, batches):
+    """The dense-faithful figure of SURVEY.md §8d counts every attention score of the S x S square.  The kernels skip
+    what is exactly zero: key tiles behind the last unmasked key (forward and backward) and, in the backward, the query
+    rows behind it (their upstream gradient is exactly zero).  This returns the train GFLOP per sample with the attention
+    term counted as EXECUTED (forward 4 S e H, backward 8 e^2 H per sequence with e = 1 + last unmasked key), averaged over
+    the given host batches — reported next to the dense-faithful number so that neither hides the other."""
+    H, N = shape.hidden_size, shape.num_hidden_layers
+    dense = train_gflop_per_sample(shape, workload)
+    T = workload.T
+    d_attn = e_attn = 0.0
+    nsamp = 0
+    for b in batches:
+        m_t, (m_tv, m_v), (m_ts, m_s) = b["attention_mask"]
+
+        def eff(mask):                   # [B, S] -> 1 + index of the last unmasked key (S when none is: processed in full)
+            S = mask.shape[1]
+            idx = torch.arange(1, S + 1)[None, :] * (mask != 0)
+            e = idx.max(dim=1).values
+            return torch.where(e > 0, e, torch.full_like(e, S)).double()
+
+        fv = m_v[:, :, 0] if m_v.dim() == 3 else m_v
+        fs = m_s[:, :, 0] if m_s.dim() == 3 else m_s
+        for mask in (m_t, torch.cat((m_tv.double(), fv.double()), 1), torch.cat((m_ts.double(), fs.double()), 1)):
+            S = float(mask.shape[1])
+            e = eff(mask)
+            d_attn += float(N * 12.0 * S * S * H * mask.shape[0])
+            e_attn += float(N * H * (4.0 * S * e + 8.0 * e * e).sum())
+        nsamp += m_t.shape[0]
+    return dense + (e_attn - d_attn) / nsamp / 1e9
 
 
 def config_dict(workload, shape, world):
@@ -547,6 +580,7 @@ def main():
         opt.zero_grad()
         achieved = flops / (gemm_ms / 1e3) / 1e12
         gf = train_gflop_per_sample(shape, workload)
+        gf_exec = executed_train_gflop_per_sample(shape, workload, host)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -578,7 +612,10 @@ def main():
                          "step_achieved": value / world * gf / 1e3,
                          "step_frac": value / world * gf / 1e3 / peaks["tflops"],
                          "step_frac_burst": value / world * gf / 1e3 / peaks["burst"],
-                         "peak_burst": peaks["burst"], "train_gflop_per_sample": gf},
+                         "peak_burst": peaks["burst"], "train_gflop_per_sample": gf,
+                         # attention counted as executed (exact-zero key tiles / query rows skipped), everything else dense
+                         "train_gflop_per_sample_executed": gf_exec,
+                         "step_frac_executed": value / world * gf_exec / 1e3 / peaks["tflops"]},
             "model_flops": {"train_gflop_per_sample": gf, "achieved_tflops_per_gpu": value / world * gf / 1e3,
                             "frac_of_peak": value / world * gf / 1e3 / peaks["tflops"]},
             "dp": dp,

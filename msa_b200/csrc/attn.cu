@@ -91,9 +91,11 @@ attn_schedule_kernel(const int* __restrict__ cu, const int* __restrict__ kv_end,
     // zero-gradient query tail (header): holds iff no row at or behind its sequence's kv_end carries a label
     int labelled_tail = row_label == nullptr ? 1 : 0;
     if (row_label != nullptr) {
-        for (int i = 0; i < nseq; ++i) {
+        // one warp per sequence (the tails are short and the loads independent: 32 sequences in flight)
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int i = warp; i < nseq; i += kSchedThreads / 32) {
             const int r1 = cu[i + 1];
-            for (int r = cu[i] + eff[i] + tid; r < r1; r += kSchedThreads) labelled_tail |= row_label[r] != -100 ? 1 : 0;
+            for (int r = cu[i] + eff[i] + lane; r < r1; r += 32) labelled_tail |= __ldg(row_label + r) != -100 ? 1 : 0;
         }
     }
     const bool qskip = __syncthreads_or(labelled_tail) == 0;

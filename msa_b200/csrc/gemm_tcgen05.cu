@@ -893,13 +893,24 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             // accumulator, so the global-load latency hides under the tile's MMAs instead of stalling every chunk
             const int colw = n_blk * TN + half * kColsPerWarp;
             const bool aux_pref = p.epilogue == MMB_EPI_MUL_AUX_BF16 && colw + kColsPerWarp <= p.N && !(p.dbg & 48);
-            uint4 auxr[kColsPerWarp / 8];
+            // (32-byte loads: a lane walks along ITS row, so a 16-byte load would use half of every sector it touches — ncu
+            // had the L1 at 78 % throughput with 16-byte loads, the busiest unit of this GEMM)
+            uint32_t auxr[kColsPerWarp / 16][8];
             if (aux_pref) {
                 const int row = row_base + lane;
-                const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) +
-                                                                  (size_t)(row < p.M ? row : 0) * p.ldaux + colw);
+                const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)(row < p.M ? row : 0) * p.ldaux + colw;
+                if ((reinterpret_cast<uintptr_t>(src) & 31) == 0) {
 #pragma unroll
-                for (int j = 0; j < kColsPerWarp / 8; ++j) auxr[j] = __ldg(src + j);
+                    for (int j = 0; j < kColsPerWarp / 16; ++j) ptx::ldg256_nc(src + 16 * j, auxr[j]);
+                } else {                                   // ldaux / base not 32-byte aligned: two 16-byte loads
+#pragma unroll
+                    for (int j = 0; j < kColsPerWarp / 16; ++j) {
+                        const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(src + 16 * j));
+                        const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(src + 16 * j + 8));
+                        auxr[j][0] = q0.x; auxr[j][1] = q0.y; auxr[j][2] = q0.z; auxr[j][3] = q0.w;
+                        auxr[j][4] = q1.x; auxr[j][5] = q1.y; auxr[j][6] = q1.z; auxr[j][7] = q1.w;
+                    }
+                }
             }
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
@@ -937,17 +948,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             }
                             if (p.epilogue == MMB_EPI_MUL_AUX_BF16) {
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const uint4 q = auxr[8 * g + 4 * h + j];
-                                    const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
-                                    v[8 * j + 0] *= f0.x;
-                                    v[8 * j + 1] *= f0.y;
-                                    v[8 * j + 2] *= f1.x;
-                                    v[8 * j + 3] *= f1.y;
-                                    v[8 * j + 4] *= f2.x;
-                                    v[8 * j + 5] *= f2.y;
-                                    v[8 * j + 6] *= f3.x;
-                                    v[8 * j + 7] *= f3.y;
+                                for (int j = 0; j < 16; ++j) {      // 32 columns = two 32-byte vectors of 8 bf16 pairs
+                                    const float2 f = unpack_bf16x2(auxr[4 * g + 2 * h + (j >> 3)][j & 7]);
+                                    v[2 * j] *= f.x;
+                                    v[2 * j + 1] *= f.y;
                                 }
                             } else {
                                 bias_add_chunk(p, v, col0);

@@ -71,23 +71,31 @@ __device__ __forceinline__ void smem_accumulate(float* __restrict__ acc, const R
     }
 }
 
+// Backward.  All element-wise arithmetic runs on PAIRS of adjacent columns with the packed fp32x2 forms (FFMA2 / FADD2 /
+// FMUL2, sm_100): the scalar version issued ~1 180 instructions per row and was bound by issue slots at 61-70 % of the
+// copy bandwidth; the keep decisions become a float2 multiplier (keep ? 1 / (1 - p) : 0) built once per pair and used for
+// both the recomputed LayerNorm input and the outgoing gradient.
+// 2 CTAs x 6 warps per SM: 12 resident warps leave ~170 registers per thread — with 16 (128 registers) the 18 row vectors in
+// flight plus the two 24-value arrays kept across the warp reduction spilled ~360 bytes per thread and row
+constexpr int kLnBwdWarps = 6;
 template <int NCH>
-__global__ void __launch_bounds__(kLnWarps * 32, 2)
+__global__ void __launch_bounds__(kLnBwdWarps * 32, 2)
 drln_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ g2,
                 const __nv_bfloat16* __restrict__ y, const float* __restrict__ res,
                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
                 __nv_bfloat16* __restrict__ d_y, float* __restrict__ d_res, float* __restrict__ dgamma,
                 float* __restrict__ dbeta, float* __restrict__ dbias, const __nv_bfloat16* __restrict__ gelu_aux, int M,
                 int H, uint32_t thresh, float inv_keep, uint64_t seed, uint32_t stream) {
-    extern __shared__ __align__(16) float smem[];   // [kLnWarps][3][H]
+    extern __shared__ __align__(16) float smem[];   // [kLnBwdWarps][3][H]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nw = gridDim.x * kLnWarps;
+    const int nw = gridDim.x * kLnBwdWarps;
     float* acc_g = smem + (size_t)warp * 3 * H;
     float* acc_b = acc_g + H;
     float* acc_bias = acc_b + H;
     for (int i = lane; i < 3 * H; i += 32) acc_g[i] = 0.f;
     __syncwarp();
-    for (int row = blockIdx.x * kLnWarps + warp; row < M; row += nw) {
+    const bool drop = thresh != 0u;
+    for (int row = blockIdx.x * kLnBwdWarps + warp; row < M; row += nw) {
         // every load of the row goes in flight before the first one is consumed (the kernel is latency-bound otherwise)
         RowRawB<NCH> y_raw, g1_raw;
         RowRawF<NCH> res_raw, g2_raw;
@@ -95,79 +103,115 @@ drln_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ 
         if (res != nullptr) row_fetch_f32(res_raw, res + (size_t)row * H, H, lane);
         row_fetch_bf16(g1_raw, g1 + (size_t)row * H, H, lane);
         if (g2 != nullptr) row_fetch_f32(g2_raw, g2 + (size_t)row * H, H, lane);
-        const uint32_t mask = row_dropout_mask<NCH>(H, lane, seed, stream, (uint64_t)row, thresh);   // hashed under the loads
-        // recompute the LayerNorm input exactly as the forward did: z = dropout(y) + res
-        RowF<NCH> z;
-        row_unpack_bf16(z, y_raw);
-        row_apply_mask(z, mask, inv_keep);
-        if (res != nullptr) row_add_f32(z, res_raw);
-        RowF<NCH> g;
-        row_unpack_bf16(g, g1_raw);
-        if (g2 != nullptr) row_add_f32(g, g2_raw);
         const float mean = mean_in[row], rstd = rstd_in[row];
-        // dbeta += dy ; dgamma += dy * xhat ; dz = (dy*gamma - mean(dy*gamma) - xhat * mean(dy*gamma*xhat)) * rstd
-        float s1 = 0.f, s2 = 0.f;
+        const uint32_t key = drop ? rng_row_key(seed, stream, (uint32_t)row) : 0u;     // hashed under the loads
+        const float2 rstd2 = make_float2(rstd, rstd), nmr2 = make_float2(-mean * rstd, -mean * rstd);
+        float2 xh[NCH][4], dg[NCH][4];
+        uint32_t keep = 0u;          // one bit per element of this lane (bit c * 8 + 2 i + {0, 1})
+        float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int e = (c * 32 + lane) * 8;
             if (e < H) {
-                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + e));
-                const float4 g1v = __ldg(reinterpret_cast<const float4*>(gamma + e + 4));
-                const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1v.x, g1v.y, g1v.z, g1v.w};
+                const uint32_t yw[4] = {y_raw.q[c].x, y_raw.q[c].y, y_raw.q[c].z, y_raw.q[c].w};
+                const uint32_t gw[4] = {g1_raw.q[c].x, g1_raw.q[c].y, g1_raw.q[c].z, g1_raw.q[c].w};
+                const float2 rs[4] = {make_float2(res_raw.a[c].x, res_raw.a[c].y), make_float2(res_raw.a[c].z, res_raw.a[c].w),
+                                      make_float2(res_raw.b[c].x, res_raw.b[c].y), make_float2(res_raw.b[c].z, res_raw.b[c].w)};
+                const float2 gs[4] = {make_float2(g2_raw.a[c].x, g2_raw.a[c].y), make_float2(g2_raw.a[c].z, g2_raw.a[c].w),
+                                      make_float2(g2_raw.b[c].x, g2_raw.b[c].y), make_float2(g2_raw.b[c].z, g2_raw.b[c].w)};
+                const float4 gm0 = __ldg(reinterpret_cast<const float4*>(gamma + e));
+                const float4 gm1 = __ldg(reinterpret_cast<const float4*>(gamma + e + 4));
+                const float2 gm[4] = {make_float2(gm0.x, gm0.y), make_float2(gm0.z, gm0.w), make_float2(gm1.x, gm1.y),
+                                      make_float2(gm1.z, gm1.w)};
                 float4* pg = reinterpret_cast<float4*>(acc_g + e);
                 float4* pb = reinterpret_cast<float4*>(acc_b + e);
                 const float4 ag0 = pg[0], ag1 = pg[1], ab0 = pb[0], ab1 = pb[1];
-                float ag[8] = {ag0.x, ag0.y, ag0.z, ag0.w, ag1.x, ag1.y, ag1.z, ag1.w};
-                float ab[8] = {ab0.x, ab0.y, ab0.z, ab0.w, ab1.x, ab1.y, ab1.z, ab1.w};
+                float2 ag[4] = {make_float2(ag0.x, ag0.y), make_float2(ag0.z, ag0.w), make_float2(ag1.x, ag1.y), make_float2(ag1.z, ag1.w)};
+                float2 ab[4] = {make_float2(ab0.x, ab0.y), make_float2(ab0.z, ab0.w), make_float2(ab1.x, ab1.y), make_float2(ab1.z, ab1.w)};
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float xhat = (z.v[c][i] - mean) * rstd;
-                    z.v[c][i] = xhat;
-                    const float dy = g.v[c][i];
-                    ag[i] = fmaf(dy, xhat, ag[i]);
-                    ab[i] += dy;
-                    const float dg = dy * gm[i];
-                    g.v[c][i] = dg;
-                    s1 += dg;
-                    s2 = fmaf(dg, xhat, s2);
+                for (int i = 0; i < 4; ++i) {
+                    // recompute the LayerNorm input exactly as the forward did: z = dropout(y) + res
+                    float2 z = unpack_bf16x2(yw[i]);
+                    if (drop) {
+                        const uint32_t bits = rng_pair(key, (uint32_t)(e >> 1) + i);
+                        const bool k0 = rng_keep_lo(bits, thresh), k1 = rng_keep_hi(bits, thresh);
+                        keep |= ((k0 ? 1u : 0u) | (k1 ? 2u : 0u)) << (c * 8 + 2 * i);
+                        z = mul2(z, make_float2(k0 ? inv_keep : 0.f, k1 ? inv_keep : 0.f));
+                    }
+                    if (res != nullptr) z = add2(z, rs[i]);
+                    float2 dy = unpack_bf16x2(gw[i]);
+                    if (g2 != nullptr) dy = add2(dy, gs[i]);
+                    // dbeta += dy ; dgamma += dy * xhat ; dz = (dy*gamma - mean(dy*gamma) - xhat * mean(dy*gamma*xhat)) * rstd
+                    const float2 x = fma2(z, rstd2, nmr2);
+                    xh[c][i] = x;
+                    ag[i] = fma2(dy, x, ag[i]);
+                    ab[i] = add2(ab[i], dy);
+                    const float2 d = mul2(dy, gm[i]);
+                    dg[c][i] = d;
+                    s1 = add2(s1, d);
+                    s2 = fma2(d, x, s2);
                 }
-                pg[0] = make_float4(ag[0], ag[1], ag[2], ag[3]);
-                pg[1] = make_float4(ag[4], ag[5], ag[6], ag[7]);
-                pb[0] = make_float4(ab[0], ab[1], ab[2], ab[3]);
-                pb[1] = make_float4(ab[4], ab[5], ab[6], ab[7]);
+                pg[0] = make_float4(ag[0].x, ag[0].y, ag[1].x, ag[1].y);
+                pg[1] = make_float4(ag[2].x, ag[2].y, ag[3].x, ag[3].y);
+                pb[0] = make_float4(ab[0].x, ab[0].y, ab[1].x, ab[1].y);
+                pb[1] = make_float4(ab[2].x, ab[2].y, ab[3].x, ab[3].y);
             }
         }
-        s1 = warp_sum(s1) / (float)H;
-        s2 = warp_sum(s2) / (float)H;
+        const float m1 = warp_sum(s1.x + s1.y) / (float)H;
+        const float m2 = warp_sum(s2.x + s2.y) / (float)H;
+        const float2 c1 = make_float2(-m1 * rstd, -m1 * rstd), c2 = make_float2(-m2 * rstd, -m2 * rstd);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int e = (c * 32 + lane) * 8;
             if (e < H) {
+                float2 dz[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) g.v[c][i] = (g.v[c][i] - s1 - z.v[c][i] * s2) * rstd;
+                for (int i = 0; i < 4; ++i) dz[i] = fma2(xh[c][i], c2, fma2(dg[c][i], rstd2, c1));    // (dg - m1 - xhat m2) rstd
+                // dz: gradient of the residual branch
+                if (d_res != nullptr) {
+                    *reinterpret_cast<float4*>(d_res + (size_t)row * H + e) = make_float4(dz[0].x, dz[0].y, dz[1].x, dz[1].y);
+                    *reinterpret_cast<float4*>(d_res + (size_t)row * H + e + 4) = make_float4(dz[2].x, dz[2].y, dz[3].x, dz[3].y);
+                }
+                // gradient of the dense output (pre-dropout): dz * mask / keep — same mask, same scaling
+                if (drop) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        dz[i] = mul2(dz[i], make_float2(((keep >> (c * 8 + 2 * i)) & 1u) ? inv_keep : 0.f,
+                                                        ((keep >> (c * 8 + 2 * i + 1)) & 1u) ? inv_keep : 0.f));
+                }
+                if (gelu_aux != nullptr) {  // y = gelu(aux): chain through the activation (LM-head transform, :482-484)
+                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(gelu_aux + (size_t)row * H + e));
+                    const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 uv = unpack_bf16x2(uw[i]);
+                        dz[i].x *= gelu_erf_grad(uv.x);
+                        dz[i].y *= gelu_erf_grad(uv.y);
+                    }
+                }
+                uint4 q;
+                q.x = pack_bf16x2(dz[0].x, dz[0].y);
+                q.y = pack_bf16x2(dz[1].x, dz[1].y);
+                q.z = pack_bf16x2(dz[2].x, dz[2].y);
+                q.w = pack_bf16x2(dz[3].x, dz[3].y);
+                *reinterpret_cast<uint4*>(d_y + (size_t)row * H + e) = q;
+                if (dbias != nullptr) {     // the bias gradient sums exactly what the wgrad GEMM will read (bf16-rounded)
+                    const float2 r0 = unpack_bf16x2(q.x), r1 = unpack_bf16x2(q.y), r2 = unpack_bf16x2(q.z), r3 = unpack_bf16x2(q.w);
+                    float4* pz = reinterpret_cast<float4*>(acc_bias + e);
+                    float4 a = pz[0], b = pz[1];
+                    const float2 a0 = add2(make_float2(a.x, a.y), r0), a1 = add2(make_float2(a.z, a.w), r1);
+                    const float2 b0 = add2(make_float2(b.x, b.y), r2), b1 = add2(make_float2(b.z, b.w), r3);
+                    pz[0] = make_float4(a0.x, a0.y, a1.x, a1.y);
+                    pz[1] = make_float4(b0.x, b0.y, b1.x, b1.y);
+                }
             }
         }
-        // g now holds dz: gradient of the residual branch
-        if (d_res != nullptr) row_store_f32(g, d_res + (size_t)row * H, H, lane);
-        // gradient of the dense output (pre-dropout): dz * mask / keep
-        row_apply_mask(g, mask, inv_keep);   // same mask, same scaling
-        if (gelu_aux != nullptr) {  // y = gelu(aux): chain through the activation (LM-head transform, :482-484)
-            RowF<NCH> u;
-            row_load_bf16(u, gelu_aux + (size_t)row * H, H, lane);
-#pragma unroll
-            for (int c = 0; c < NCH; ++c)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) g.v[c][i] *= gelu_erf_grad(u.v[c][i]);
-        }
-        row_round_bf16(g);  // the bias gradient sums exactly what the wgrad GEMM will read
-        row_store_bf16(g, d_y + (size_t)row * H, H, lane);
-        if (dbias != nullptr) smem_accumulate(acc_bias, g, H, lane);
     }
     __syncthreads();
-    for (int col = threadIdx.x; col < H; col += kLnWarps * 32) {
+    for (int col = threadIdx.x; col < H; col += kLnBwdWarps * 32) {
         float sg = 0.f, sb = 0.f, sbias = 0.f;
 #pragma unroll
-        for (int w = 0; w < kLnWarps; ++w) {
+        for (int w = 0; w < kLnBwdWarps; ++w) {
             const float* a = smem + (size_t)w * 3 * H;
             sg += a[col];
             sb += a[H + col];
@@ -252,12 +296,12 @@ extern "C" int mmb_dropout_residual_ln_bwd(const mmb_drln_bwd_args* a, void* str
     MMB_REQUIRE(a->M > 0 && a->H > 0 && a->H % 8 == 0 && a->H <= 1024, "drln_bwd: bad shape M=%d H=%d", a->M, a->H);
     const uint32_t thresh = dropout_threshold(a->p_drop);
     const float inv_keep = dropout_inv_keep(a->p_drop);
-    const int grid = min((a->M + kLnWarps - 1) / kLnWarps, num_sms() * 2);
-    const size_t smem = (size_t)kLnWarps * 3 * a->H * sizeof(float);
+    const int grid = min((a->M + kLnBwdWarps - 1) / kLnBwdWarps, num_sms() * 2);
+    const size_t smem = (size_t)kLnBwdWarps * 3 * a->H * sizeof(float);
     MMB_DISPATCH_NCH(a->H, {
         MMB_ENSURE_SMEM(100 * 1024, drln_bwd_kernel<NCH>);
     });
-    MMB_DISPATCH_NCH(a->H, (drln_bwd_kernel<NCH><<<grid, kLnWarps * 32, smem, (cudaStream_t)stream>>>(
+    MMB_DISPATCH_NCH(a->H, (drln_bwd_kernel<NCH><<<grid, kLnBwdWarps * 32, smem, (cudaStream_t)stream>>>(
                                (const __nv_bfloat16*)a->g1, a->g2, (const __nv_bfloat16*)a->y,
                                a->res, a->mean, a->rstd, a->gamma, (__nv_bfloat16*)a->d_y,
                                a->d_res, a->dgamma, a->dbeta, a->dbias,
