@@ -436,6 +436,9 @@ def main():
     ap.add_argument("--materialize-logits", type=int, default=0, help="infer-sweep: keep the [rows, V] decoder output")
     ap.add_argument("--no-cuda-graph", action="store_true", help="infer-sweep: launch the plan kernel by kernel")
     ap.add_argument("--lr", type=float, default=1e-5)
+    ap.add_argument("--dp-mode", default=None, choices=["deferred", "overlap"],
+                    help="N>1: gradient all-reduce schedule (msa_b200.ddp.GradReducer; default deferred)")
+    ap.add_argument("--dp-compress", default=None, choices=["bf16"], help="N>1: all-reduce a bf16 copy of the gradient")
     ap.add_argument("--reserve-sms", type=int, default=None,
                     help="N>1: SMs the persistent kernels leave to NCCL (default 4; MMB_RESERVE_SMS overrides)")
     ap.add_argument("--nccl-ctas", type=int, default=None, help="N>1: NCCL_MAX_CTAS (default 4; 0 = NCCL's own choice)")
@@ -455,15 +458,18 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    dp = {"reserved_sms": 0, "nccl_max_ctas": None}
+    dp_mode = args.dp_mode or os.environ.get("MMB_DP_MODE", "deferred")
+    dp = {"mode": dp_mode, "compress": args.dp_compress, "reserved_sms": 0, "nccl_max_ctas": None}
     if world > 1:
-        # One gradient all-reduce per layer runs under the backward sweep.  Its bandwidth need is small (460 MB per step),
-        # but the persistent GEMM / attention kernels own every SM: an NCCL kernel then waits for a kernel boundary and the
-        # next persistent wave runs short of the SMs NCCL took.  So NCCL is capped to a few CTAs and the persistent kernels
-        # leave that many SMs free.
-        ctas = 4 if args.nccl_ctas is None else args.nccl_ctas
-        if ctas > 0:
-            os.environ.setdefault("NCCL_MAX_CTAS", str(ctas))
+        # deferred (default): one all-reduce after the backward sweep, every SM free for NCCL.  overlap: one all-reduce per
+        # layer under the backward sweep — the persistent GEMM / attention kernels own every SM, so NCCL is capped to a few
+        # CTAs and the persistent kernels leave that many SMs free.
+        if dp_mode == "overlap":
+            ctas = 4 if args.nccl_ctas is None else args.nccl_ctas
+            if ctas > 0:
+                os.environ.setdefault("NCCL_MAX_CTAS", str(ctas))
+        elif args.nccl_ctas:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_ctas))
         dp["nccl_max_ctas"] = os.environ.get("NCCL_MAX_CTAS")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
@@ -471,7 +477,7 @@ def main():
     if world > 1:
         reserve = args.reserve_sms
         if reserve is None:
-            reserve = int(os.environ.get("MMB_RESERVE_SMS", "4"))
+            reserve = int(os.environ.get("MMB_RESERVE_SMS", "4" if dp_mode == "overlap" else "0"))
         capi.check(capi.lib().mmb_set_reserved_sms(int(reserve)), "mmb_set_reserved_sms")
         dp["reserved_sms"] = int(reserve)
     peaks = load_peaks()
@@ -483,7 +489,8 @@ def main():
     broadcast_parameters(model)
     opt = FusedAdamW(model, lr=args.lr)
     opt.grad_scale = 1.0 / world
-    reducer = GradReducer(model._store, shape.num_hidden_layers).attach(model) if world > 1 else None
+    reducer = (GradReducer(model._store, shape.num_hidden_layers, mode=dp_mode, compress=args.dp_compress).attach(model)
+               if world > 1 else None)
 
     B = workload.batch
     nb = 4  # distinct synthetic batches, cycled

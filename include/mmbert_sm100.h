@@ -27,9 +27,10 @@
 extern "C" {
 #endif
 
-#define MMB_VERSION 202 /* round 2; 200: mmb_pack_args.mask_frame_stride; 201: MMB_EPI_CE_STATS, mmb_gemm_args.aux2,
+#define MMB_VERSION 203 /* round 2; 200: mmb_pack_args.mask_frame_stride; 201: MMB_EPI_CE_STATS, mmb_gemm_args.aux2,
                            mmb_pack_args.row_label / vocab, mmb_ce_sparse_*, mmb_embed_args.err_count;
-                           202: mmb_attn_schedule_args.row_label (zero-gradient query tail skipped by the backward) */
+                           202: mmb_attn_schedule_args.row_label (zero-gradient query tail skipped by the backward);
+                           203: mmb_gemm_args.colsum */
 
 enum mmb_status {
     MMB_OK = 0,
@@ -101,6 +102,10 @@ typedef struct mmb_gemm_args {
     float alpha;
     /* debug overrides for bring-up (0 = use built-in values) */
     int32_t dbg_flags;
+    float* colsum; /* NULL, or [N] f32: colsum[n] += sum over rows of the bf16-ROUNDED C[:, n] (the bias gradient of the
+                      Linear whose output gradient C is: exactly what its wgrad GEMM reads).  bf16-output epilogues
+                      only; taken from the epilogue's staging tiles of the CTA-pair kernel, else by a mmb_colsum_bf16
+                      launch behind the GEMM */
 } mmb_gemm_args;
 
 int mmb_gemm(const mmb_gemm_args* a, void* stream);

@@ -55,6 +55,8 @@ struct GemmParams {
     uint32_t a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step;
     int dbg;  // bring-up only: bit 4 = epilogue skips global stores, bit 5 = epilogue skips the TMEM loads too
     int tma_store;  // CTA-pair kernel: bf16 outputs leave through cp.async.bulk.tensor stores (tmC / tmAux)
+    int stages;     // CTA-pair kernel: depth of the operand ring (6, or 5 to make room for the column-sum array)
+    float* colsum;  // CTA-pair kernel, 8 epilogue warps: [N] column sums of the bf16-rounded output, or null
 };
 
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], int ncols_valid) {
@@ -95,6 +97,11 @@ __device__ __forceinline__ uint32_t stage_off(int r, int j) { return (uint32_t)(
 // explicit shared-space accesses (the staging pointer is a 32-bit shared address: guarantees STS/LDS, no generic LD/ST)
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
 }
 __device__ __forceinline__ void lds128(uint32_t addr, uint32_t& x, uint32_t& y, uint32_t& z, uint32_t& w) {
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(addr) : "memory");
@@ -662,9 +669,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // are long latency chains (tcgen05.ld -> bias -> erf math -> two staged output streams): with 8 warps the issue slots
 // were ~30 % busy and the epilogue, not the MMA, bounded FFN1 (39 % tensor-pipe active).
 template <int kEpiWarps> struct Cfg2 {
-    static constexpr int kStages = kEpiWarps == 16 ? 5 : 6;
     static constexpr int kThreads = (4 + kEpiWarps) * 32;
-    static constexpr int kSmemBytes = kStages * (2 * 128 * BK * 2) + 256 + kEpiWarps * 4096 + 1024;
+    static constexpr int kMaxSmem = 227 * 1024;
+    // [operand ring: stages x 32 KB][epilogue staging: kEpiWarps x 4 KB][barriers: 256 B][column sums: colsum_floats x 4]
+    static int stages(bool colsum) { return (kEpiWarps == 16 || colsum) ? 5 : 6; }
+    static int smem_bytes(int stages, int colsum_floats) {
+        return stages * (2 * 128 * BK * 2) + kEpiWarps * 4096 + 256 + colsum_floats * 4 + 1024;
+    }
 };
 constexpr int k2ABytes = 128 * BK * 2;           // this CTA's half of the 256-row A tile
 constexpr int k2BBytes = 128 * BK * 2;           // this CTA's half of the 256-column B tile
@@ -676,12 +687,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg2<k2EpiWarps>::kT
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
                          const GemmParams p) {
-    constexpr int k2Stages = Cfg2<k2EpiWarps>::kStages;
+    const int k2Stages = p.stages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t smem_base = ptx::smem_u32(smem);
     // [operand ring][epilogue staging: k2EpiWarps x 4 KB, 1024-byte aligned (swizzled TMA-store boxes)][barriers]
-    constexpr int kBarOff = k2Stages * k2StageBytes + k2EpiWarps * kStageBytesPerWarp;
+    const int kBarOff = k2Stages * k2StageBytes + k2EpiWarps * kStageBytesPerWarp;
     const uint32_t bar_base = smem_base + kBarOff;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (k2Stages + s); };
@@ -689,6 +700,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * k2Stages + 2 + a); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kBarOff + 8 * (2 * k2Stages + 4));
     uint8_t* epi_stage = smem + k2Stages * k2StageBytes;
+    float* colacc = reinterpret_cast<float*>(smem + kBarOff + 256);   // [N] per-CTA column sums (p.colsum != null)
+    if (p.colsum != nullptr)
+        for (int i = threadIdx.x; i < p.N; i += Cfg2<k2EpiWarps>::kThreads) colacc[i] = 0.f;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -960,6 +974,29 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             if (h == 0) stage_acquire(lane);
                             stage_row128(stage_buf, v, lane, h);
                         }
+                        if (p.colsum != nullptr) {
+                            // column sums of the staged (bf16-rounded) tile: lane l owns columns 2l, 2l+1 of the 64; rows
+                            // beyond M hold padding (bias-only values) and are left out
+                            __syncwarp();
+                            const int nrow = min(32, p.M - row_base);
+                            float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+                            const uint32_t wb = stage_buf + (uint32_t)((lane & 3) * 4);
+                            if (nrow == 32) {
+#pragma unroll
+                                for (int r = 0; r < 32; r += 4) {
+                                    a0 = add2(a0, unpack_bf16x2(lds32(wb + stage_off128(r, lane >> 2))));
+                                    a1 = add2(a1, unpack_bf16x2(lds32(wb + stage_off128(r + 1, lane >> 2))));
+                                    a2 = add2(a2, unpack_bf16x2(lds32(wb + stage_off128(r + 2, lane >> 2))));
+                                    a3 = add2(a3, unpack_bf16x2(lds32(wb + stage_off128(r + 3, lane >> 2))));
+                                }
+                            } else {
+                                for (int r = 0; r < nrow; ++r) a0 = add2(a0, unpack_bf16x2(lds32(wb + stage_off128(r, lane >> 2))));
+                            }
+                            const float2 t = add2(add2(a0, a1), add2(a2, a3));
+                            const int c = colg + 2 * lane;
+                            if (c < p.N) atomicAdd(colacc + c, t.x);
+                            if (c + 1 < p.N) atomicAdd(colacc + c + 1, t.y);
+                        }
                         stage_release(&tmC, stage_buf, nullptr, 0, colg, row_base, lane);
                     }
                 } else {
@@ -1027,6 +1064,11 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         ptx::tc_fence_after();
         ptx::tmem_dealloc_2cta<512>(tmem_base);
     }
+    if (p.colsum != nullptr)        // every epilogue warp's shared-memory reductions are behind the cluster barrier
+        for (int i = threadIdx.x; i < p.N; i += Cfg2<k2EpiWarps>::kThreads) {
+            const float v = colacc[i];
+            if (v != 0.f) atomicAdd(p.colsum + i, v);
+        }
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -1132,6 +1174,8 @@ static void fill_common(GemmParams& p, const mmb_gemm_args* a, int tile_m, int t
     p.total_tiles = p.m_tiles * p.n_tiles * p.split_k;
     p.alpha = a->alpha;
     p.tma_store = 0;
+    p.stages = 0;
+    p.colsum = nullptr;
     p.dbg = a->dbg_flags;
     static const int lane_issue = [] {                       // MMB_GEMM_ISSUE=lane: single-lane MMA issue (A/B runs)
         const char* e = getenv("MMB_GEMM_ISSUE");
@@ -1200,6 +1244,18 @@ int make_tmap_rec16(CUtensorMap* out, const void* ptr, uint64_t records, uint64_
     return MMB_OK;
 }
 
+// mmb_gemm_args.colsum where the epilogue cannot take it: a mmb_colsum_bf16 launch over the finished C
+static int gemm_colsum_fallback(const mmb_gemm_args* a, cudaStream_t stream) {
+    MMB_REQUIRE(a->N % 8 == 0 && a->ldc % 8 == 0, "mmb_gemm: colsum needs N %% 8 == 0 on this path (N=%d)", a->N);
+    mmb_colsum_args c;
+    c.X = a->C;
+    c.out = a->colsum;
+    c.ld = a->ldc;
+    c.M = a->M;
+    c.N = a->N;
+    return mmb_colsum_bf16(&c, stream);
+}
+
 // CTA-pair kernel: 256 x 256 tiles, one cluster of 2 per SM pair.
 static int launch_gemm_2cta(const mmb_gemm_args* a, cudaStream_t stream) {
     CUtensorMap tmA, tmB;
@@ -1216,8 +1272,8 @@ static int launch_gemm_2cta(const mmb_gemm_args* a, cudaStream_t stream) {
     if (rc != MMB_OK) return rc;
     GemmParams p;
     fill_common(p, a, 256, 256);
-    MMB_ENSURE_SMEM(Cfg2<8>::kSmemBytes, gemm_tcgen05_2cta_kernel<8>);
-    MMB_ENSURE_SMEM(Cfg2<16>::kSmemBytes, gemm_tcgen05_2cta_kernel<16>);
+    MMB_ENSURE_SMEM(Cfg2<8>::kMaxSmem, gemm_tcgen05_2cta_kernel<8>);
+    MMB_ENSURE_SMEM(Cfg2<16>::kMaxSmem, gemm_tcgen05_2cta_kernel<16>);
     const int pairs = persistent_sms() / 2;
     const int clusters = p.total_tiles < pairs ? p.total_tiles : pairs;
     // GELU epilogues are long latency chains: 16 epilogue warps; everything else: 8 (dbg bit 6 flips the choice, for A/B runs)
@@ -1242,10 +1298,29 @@ static int launch_gemm_2cta(const mmb_gemm_args* a, cudaStream_t stream) {
         }
         if (rc != MMB_OK) return rc;
     }
-    if (wide)
-        gemm_tcgen05_2cta_kernel<16><<<2 * clusters, Cfg2<16>::kThreads, Cfg2<16>::kSmemBytes, stream>>>(tmA, tmB, tmC, tmAux, p);
-    else
-        gemm_tcgen05_2cta_kernel<8><<<2 * clusters, Cfg2<8>::kThreads, Cfg2<8>::kSmemBytes, stream>>>(tmA, tmB, tmC, tmAux, p);
+    // column sums ride on the 8-warp TMA-store epilogue (one output stream); everything else: mmb_gemm adds a launch
+    static const int stages_env = [] {
+        const char* e = getenv("MMB_GEMM_STAGES");
+        return e != nullptr ? atoi(e) : 0;
+    }();
+    // (the multiply epilogue leaves the TMA-store path on a ragged last column strip: N must be a multiple of 128 there)
+    const bool fused_colsum = a->colsum != nullptr && p.tma_store && !wide && (size_t)a->N * 4 <= 28 * 1024 &&
+                              (a->epilogue != MMB_EPI_MUL_AUX_BF16 || a->N % 128 == 0) && !(a->dbg_flags & 48);
+    p.colsum = fused_colsum ? a->colsum : nullptr;
+    if (wide) {
+        p.stages = Cfg2<16>::stages(false);
+        gemm_tcgen05_2cta_kernel<16><<<2 * clusters, Cfg2<16>::kThreads, Cfg2<16>::smem_bytes(p.stages, 0), stream>>>(tmA, tmB, tmC, tmAux, p);
+    } else {
+        p.stages = Cfg2<8>::stages(fused_colsum);
+        if (!fused_colsum && (stages_env == 5 || stages_env == 6)) p.stages = stages_env;      // A/B runs
+        gemm_tcgen05_2cta_kernel<8><<<2 * clusters, Cfg2<8>::kThreads, Cfg2<8>::smem_bytes(p.stages, fused_colsum ? a->N : 0), stream>>>(
+            tmA, tmB, tmC, tmAux, p);
+    }
+    if (a->colsum != nullptr && !fused_colsum) {
+        int rc2 = check_launch("gemm_tcgen05_2cta_kernel");
+        if (rc2 != MMB_OK) return rc2;
+        return gemm_colsum_fallback(a, stream);
+    }
     return check_launch("gemm_tcgen05_2cta_kernel");
 }
 
@@ -1285,9 +1360,15 @@ extern "C" int mmb_gemm(const mmb_gemm_args* a, void* stream) {
     // Dispatch: the CTA-pair kernel (256 x 256 tiles) whenever the problem has more than one 128-row tile and
     // more than 128 columns; otherwise the single-CTA kernel (128 x 256, or 128 x 128 for N <= 128).
     // dbg_flags: bit 0 forces the 128 x 128 tile, bit 3 forces the single-CTA 128 x 256 kernel.
-    if (a->dbg_flags & 1) return launch_gemm<128>(a, (cudaStream_t)stream);
-    if (a->dbg_flags & 8) return launch_gemm<256>(a, (cudaStream_t)stream);
-    if (a->N <= 128) return launch_gemm<128>(a, (cudaStream_t)stream);
-    if (a->M > 128) return launch_gemm_2cta(a, (cudaStream_t)stream);
-    return launch_gemm<256>(a, (cudaStream_t)stream);
+    if (a->colsum != nullptr)
+        MMB_REQUIRE(a->epilogue == MMB_EPI_STORE_BF16 || a->epilogue == MMB_EPI_RELU_BF16 || a->epilogue == MMB_EPI_MUL_AUX_BF16 ||
+                        a->epilogue == MMB_EPI_GELU_BF16 || a->epilogue == MMB_EPI_DGELU_BF16,
+                    "mmb_gemm: colsum needs a single bf16 output (epilogue %d)", a->epilogue);
+    const bool one_cta = (a->dbg_flags & (1 | 8)) || a->N <= 128 || a->M <= 128;
+    if (!one_cta) return launch_gemm_2cta(a, (cudaStream_t)stream);
+    int rc;
+    if ((a->dbg_flags & 1) || (a->N <= 128 && !(a->dbg_flags & 8))) rc = launch_gemm<128>(a, (cudaStream_t)stream);
+    else rc = launch_gemm<256>(a, (cudaStream_t)stream);
+    if (rc == MMB_OK && a->colsum != nullptr) rc = gemm_colsum_fallback(a, (cudaStream_t)stream);
+    return rc;
 }

@@ -5,15 +5,25 @@ The reference has no distributed code.  Semantics are PyTorch-DDP semantics: eve
 on its own micro-batch (per-rank CE means, per-rank in-batch CPC negatives) and the parameter gradients are
 averaged; the 1/world factor is folded into the fused AdamW (``FusedAdamW.grad_scale``).
 
-Why the overlap is simple here: the three reference passes are packed into ONE backward sweep, so layer l's
-weight gradients are final the moment its last wgrad GEMM is enqueued — that launch index triggers the
-bucket's all-reduce on NCCL's stream while the compute stream continues with layer l-1.  The wgrad epilogues
-accumulate straight into the flat gradient buffer (msa_b200.store.FlatStore), so a bucket is a contiguous
-slice of that buffer: nothing is copied or re-packed before the collective.
+Two schedules (``mode``):
+
+* ``"deferred"`` (default): ONE all-reduce of the whole flat gradient buffer right after the backward sweep.  Every
+  compute kernel of this path is persistent — one CTA (or CTA pair) per SM with the whole register file and ~220 KB of
+  shared memory, its tiles divided statically over the grid — so an NCCL kernel running under the backward cannot
+  share an SM with them: it either waits for a kernel boundary or takes SMs away from the next persistent grid, whose
+  late CTAs then stretch that kernel.  Measured at 2 GPUs (MOSEI shape): overlapped buckets cost +2.5 ms per 59.5 ms
+  step (with or without SMs reserved for NCCL), while 460 MB over NVLink 5 with every SM free for NCCL is well under
+  that.  ``compress="bf16"`` sends a bf16 copy (half the bytes; gradients are summed in bf16 by NCCL).
+* ``"overlap"``: bucketed all-reduces issued from inside the backward launch loop.  The three reference passes are
+  packed into ONE backward sweep, so layer l's weight gradients are final the moment its last wgrad GEMM is enqueued —
+  that launch index triggers the bucket's all-reduce on NCCL's stream while the compute stream continues with layer
+  l-1.  The wgrad epilogues accumulate straight into the flat gradient buffer (msa_b200.store.FlatStore), so a bucket
+  is a contiguous slice of that buffer: nothing is copied or re-packed before the collective.
 
 Params without gradient (W_cv, W_cs, cls.seq_relationship) live outside [0, trainable_end) and are never sent.
 """
 import contextlib
+import os
 
 import torch
 import torch.distributed as dist
@@ -50,9 +60,14 @@ def check_partition(sched, trainable_end):
 class GradReducer:
     """Issues the bucketed all-reduces.  ``attach(model)`` wires it into MMBertForPretraining's backward."""
 
-    def __init__(self, store, num_layers, process_group=None):
+    def __init__(self, store, num_layers, process_group=None, mode=None, compress=None):
         self.store = store
         self.group = process_group
+        self.mode = mode or os.environ.get("MMB_DP_MODE", "deferred")
+        self.compress = compress if compress is not None else (os.environ.get("MMB_DP_COMPRESS") or None)
+        if self.mode not in ("deferred", "overlap") or self.compress not in (None, "bf16"):
+            raise ValueError(f"GradReducer: mode={self.mode!r} compress={self.compress!r}")
+        self._cbuf = None
         self.sched = bucket_schedule(store, num_layers)
         assert check_partition(self.sched, store.trainable_end)
         self.pending = []
@@ -73,21 +88,34 @@ class GradReducer:
             self.sync = old
 
     def reduce_bucket(self, ranges):
-        if self.world == 1 or not self.sync:
+        if self.world == 1 or not self.sync or self.mode != "overlap":
             return
         for a, b in ranges:
             self.pending.append(dist.all_reduce(self.store.grad[a:b], op=dist.ReduceOp.SUM, group=self.group,
                                                 async_op=True))
 
     def finish(self):
-        """Makes the current stream wait for every outstanding collective (no host synchronisation on NCCL)."""
+        """End of the backward sweep.  deferred: the one all-reduce of the step; both modes: the current stream then
+        waits for every outstanding collective (no host synchronisation on NCCL)."""
+        if self.mode == "deferred" and self.world > 1 and self.sync:
+            g = self.store.grad[:self.store.trainable_end]
+            if self.compress == "bf16":
+                from . import capi
+                if self._cbuf is None:
+                    self._cbuf = torch.empty(g.numel(), device=g.device, dtype=torch.bfloat16)
+                capi.cast_bf16(g, self._cbuf)
+                dist.all_reduce(self._cbuf, op=dist.ReduceOp.SUM, group=self.group, async_op=True).wait()
+                g.copy_(self._cbuf)
+            else:
+                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True).wait()
         for w in self.pending:
             w.wait()
         self.pending = []
 
     def hooks_for(self, plan):
         """launch index in plan.bwd -> callable.  Triggers: the heads_bwd launch, each layer's last wgrad launch."""
-        import ctypes
+        if self.mode == "deferred":
+            return None
         hooks = {}
         lib_heads = plan._fn("heads_bwd")
         gemm = plan._fn("gemm")

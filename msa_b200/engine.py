@@ -294,6 +294,7 @@ class Plan:
         MN, K_ = capi.MAJOR_MN, capi.MAJOR_K
         ATOM = capi.EPI_ATOMIC_ADD_F32
         word_bf = self._w("bert.embeddings.word_embeddings.weight")
+        fuse_colsum = os.environ.get("MMB_GEMM_COLSUM", "1") != "0"      # A/B runs: 0 = separate mmb_colsum_bf16 launches
         b.append((self._fn("ce_bwd" if self.materialize_logits else "ce_sparse_bwd"), self.ce_args))
         # tied decoder: d_tln = dlogits · Wword ; g_word += dlogits^T · t_ln ; g_dec_bias += colsum(dlogits)
         self._gemm(b, self.dlogits, word_bf, self.GT, M, H, V, b_major=MN)
@@ -325,11 +326,14 @@ class Plan:
             self._seeded.append(a)
             b.append((self._fn("dropout_residual_ln_bwd"), a))
             # FFN2: du = (dY2 · W2) ∘ gelu'(u) ; gW2 += dY2^T · hg     (L["u"] holds gelu'(u), see the forward)
+            # (the epilogue also takes the column sums of du = the FFN1 bias gradient, from its staging tiles)
             self._gemm(b, self.GC, self._w(pre + "output.dense.weight"), self.du, M, I, H, b_major=MN,
-                       epilogue=capi.EPI_MUL_AUX_BF16, aux=L["u"])
+                       epilogue=capi.EPI_MUL_AUX_BF16, aux=L["u"],
+                       colsum=self._g(pre + "intermediate.dense.bias") if fuse_colsum else None)
             self._gemm(b, self.GC, L["hg"], self._g(pre + "output.dense.weight"), H, I, M, a_major=MN, b_major=MN,
                        epilogue=ATOM, split_k=_split_k(H, I, M))
-            b.append((self._fn("colsum_bf16"), capi.colsum_args(self.du, self._g(pre + "intermediate.dense.bias"))))
+            if not fuse_colsum:
+                b.append((self._fn("colsum_bf16"), capi.colsum_args(self.du, self._g(pre + "intermediate.dense.bias"))))
             # FFN1: dA = du · W1 ; gW1 += du^T · a
             self._gemm(b, self.du, self._w(pre + "intermediate.dense.weight"), self.GA, M, H, I, b_major=MN)
             self._gemm(b, self.du, L["a"], self._g(pre + "intermediate.dense.weight"), I, H, M, a_major=MN, b_major=MN,

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     assert len(capi.DECLARED_FUNCTIONS) >= 20
     for name in capi.DECLARED_FUNCTIONS:
         assert hasattr(L, name), name
-    assert L.mmb_version() == 202
+    assert L.mmb_version() == 203
     assert capi.launch_count() >= 0
 
 
@@ -175,7 +175,7 @@ def test_root_level_drop_in_modules_import():
     assert out.strip().endswith("ok")
 
 
-def _ddp_worker(rank, world, port, q):
+def _ddp_worker(rank, world, port, q, mode="overlap"):
     import torch.distributed as dist
     from msa_b200.ddp import GradReducer
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -184,8 +184,8 @@ def _ddp_worker(rank, world, port, q):
     st = FlatStore(shape, "mosi")
     st.grad = torch.full((st.total,), float(rank + 1))
     st.grad[st.trainable_end:] = -7.0                      # never-touched parameters must not be communicated
-    red = GradReducer(st, shape.num_hidden_layers)
-    for _, ranges in red.sched:                            # same order on every rank
+    red = GradReducer(st, shape.num_hidden_layers, mode=mode)
+    for _, ranges in red.sched:                            # same order on every rank (no-ops in deferred mode)
         red.reduce_bucket(ranges)
     red.finish()
     ok = bool((st.grad[:st.trainable_end] == sum(range(1, world + 1))).all()) and bool((st.grad[st.trainable_end:] == -7.0).all())
@@ -209,12 +209,15 @@ def _ddp_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_gradient_reducer_two_ranks_gloo():
+@pytest.mark.parametrize("mode", ["deferred", "overlap"])
+def test_gradient_reducer_two_ranks_gloo(mode):
+    """Both schedules of msa_b200.ddp.GradReducer (one all-reduce after the backward sweep / per-layer buckets under it)
+    sum the trainable range exactly once per stepping backward and leave the never-touched tail alone."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() + (7 if mode == "overlap" else 0)) % 2000
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q, mode)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]

@@ -67,6 +67,27 @@ def test_gemm_epilogues():
     assert _rel(acc, 1 + 0.5 * (A.float() @ B.float().t())) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(520, 3072, 768), (1000, 1000, 136), (100, 512, 200), (300, 120, 264)])
+def test_gemm_fused_column_sums(M, N, K):
+    """mmb_gemm_args.colsum: the bias gradient (column sums of the bf16-ROUNDED output, accumulated) taken in the epilogue
+    of the CTA-pair kernel — ragged edges, the multiply and plain epilogues — and by the follow-up launch on the shapes
+    the single-CTA kernels serve.  Must equal the column sums of the C the same call wrote."""
+    from msa_b200 import capi
+    torch.manual_seed(5)
+    A, B = _bf(torch.randn(M, K, device="cuda") * 0.3), _bf(torch.randn(N, K, device="cuda") * 0.3)
+    bias = torch.randn(N, device="cuda")
+    aux = _bf(torch.randn(M, N, device="cuda"))
+    C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    for epi, kw in ((capi.EPI_MUL_AUX_BF16, dict(aux=aux)), (capi.EPI_STORE_BF16, dict(bias=bias))):
+        cs = torch.full((N,), 3.0, device="cuda")
+        capi.gemm(A, B, C, M, N, K, epilogue=epi, colsum=cs, **kw)
+        ref = (A.float() @ B.float().t())
+        ref = ref * aux.float() if epi == capi.EPI_MUL_AUX_BF16 else ref + bias
+        assert _rel(C.float(), ref) < 2 * BF16_EPS
+        want = 3.0 + C.float().sum(0)
+        assert _rel(cs, want) < 1e-5, epi
+
+
 @pytest.mark.parametrize("H", [128, 768, 1024])
 @pytest.mark.parametrize("with_res", [True, False])
 def test_dropout_residual_ln_p0(H, with_res):
