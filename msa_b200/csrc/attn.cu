@@ -57,11 +57,15 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dctx, const __nv_bfloat16
     if (!live) return;
     const uint32_t prob = (uint32_t)head * (uint32_t)total_rows + (uint32_t)row;
     const int64_t o = (int64_t)head * total_rows + row;
+    // lane 0 writes the row record, lane 1 the column record; both hash in ONE instruction stream (two divergent branches
+    // would run the ~25-instruction hash twice per warp — the kernel was issue-bound at 66 %, DRAM 49 %)
+    uint32_t key = 1u;
+    if (drop && sub < 2)
+        key = rng_row_key(sub == 0 ? seed : (seed ^ 0x9E3779B97F4A7C15ull), sub == 0 ? rng_stream : (rng_stream ^ 0x5bd1e995u), prob) | 1u;
     if (sub == 0) {
-        ws[o] = make_uint4(__float_as_uint(-lse[o]), __float_as_uint(-s), drop ? attn_drop_qkey(seed, rng_stream, prob) : 1u, 0u);
+        ws[o] = make_uint4(__float_as_uint(-lse[o]), __float_as_uint(-s), key, 0u);
     } else if (sub == 1) {
-        ws[(int64_t)nheads * total_rows + o] =
-            make_uint4(__float_as_uint(keybias[row] * kLog2e), drop ? attn_drop_kkey(seed, rng_stream, prob) : 1u, 0u, 0u);
+        ws[(int64_t)nheads * total_rows + o] = make_uint4(__float_as_uint(keybias[row] * kLog2e), key, 0u, 0u);
     }
 }
 
