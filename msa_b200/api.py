@@ -243,6 +243,11 @@ class MMBertForPretraining(_Node):
         if self.precision not in ("bf16", "fp32"):
             raise capi.MMBError(f"precision must be 'bf16' or 'fp32', not {self.precision!r}")
         fp32 = self.precision == "fp32"
+        if not self.dense_mlm:
+            # mmb_ce_bwd's dense = 0 leaves the unlabelled rows of dlogits untouched while the decoder dgrad / wgrad GEMMs
+            # read every row; the fused default already restricts the element-wise work to the labelled rows
+            raise capi.MMBError("dense_mlm = False is not supported (the decoder GEMMs read every dlogits row); the default "
+                                "fused cross entropy already touches only the labelled rows")
         # everything that is baked into a plan when it is built is part of its key
         p_joint = float(self.bert.jointEmbeddings.dropout.p)
         key = (B, T, Lv, La, bool(needs_grad), bool(self.training), fp32, p_joint, bool(self.dense_mlm),

@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmmbert_sm100.so")
+LIB_PATH = os.environ.get("MMB_LIB") or os.path.join(_HERE, "lib", "libmmbert_sm100.so")     # MMB_LIB: A/B builds only
 
 MMB_OK, MMB_EINVAL, MMB_EARCH, MMB_ECUDA = 0, -1, -2, -3
 MAJOR_K, MAJOR_MN = 0, 1
