@@ -29,12 +29,12 @@ drln_fwd_kernel(const void* __restrict__ y_, const float* __restrict__ res,
     const int nw = gridDim.x * kLnWarps;
     for (int row = blockIdx.x * kLnWarps + warp; row < M; row += nw) {
         RowF<NCH> z;
-        if (kYF32) row_load_f32(z, reinterpret_cast<const float*>(y_) + (size_t)row * H, H, lane);
+        if (kYF32) row_load_f32<NCH, true>(z, reinterpret_cast<const float*>(y_) + (size_t)row * H, H, lane);
         else row_load_bf16(z, reinterpret_cast<const __nv_bfloat16*>(y_) + (size_t)row * H, H, lane);
         row_dropout(z, H, lane, seed, stream, (uint64_t)row, thresh, inv_keep);
         if (res != nullptr) {
             RowF<NCH> r;
-            row_load_f32(r, res + (size_t)row * H, H, lane);
+            row_load_f32<NCH, true>(r, res + (size_t)row * H, H, lane);
 #pragma unroll
             for (int c = 0; c < NCH; ++c)
 #pragma unroll
@@ -168,10 +168,9 @@ drln_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ 
 #pragma unroll
                 for (int i = 0; i < 4; ++i) dz[i] = fma2(xh[c][i], c2, fma2(dg[c][i], rstd2, c1));    // (dg - m1 - xhat m2) rstd
                 // dz: gradient of the residual branch
-                if (d_res != nullptr) {
-                    *reinterpret_cast<float4*>(d_res + (size_t)row * H + e) = make_float4(dz[0].x, dz[0].y, dz[1].x, dz[1].y);
-                    *reinterpret_cast<float4*>(d_res + (size_t)row * H + e + 4) = make_float4(dz[2].x, dz[2].y, dz[3].x, dz[3].y);
-                }
+                if (d_res != nullptr)
+                    stg256_f32(d_res + (size_t)row * H + e, make_float4(dz[0].x, dz[0].y, dz[1].x, dz[1].y),
+                               make_float4(dz[2].x, dz[2].y, dz[3].x, dz[3].y));
                 // gradient of the dense output (pre-dropout): dz * mask / keep — same mask, same scaling
                 if (drop) {
 #pragma unroll

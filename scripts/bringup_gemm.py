@@ -81,6 +81,8 @@ CASES = {
     "z_ragged_bias": (1000, 1000, 136, 0, 0, "bias", 1, 0),
     "z_ragged_mul": (1000, 1024, 136, 0, 1, "mul_aux", 1, 0),
     "z_vocab": (2048, 30522, 768, 0, 0, "bias", 1, 0),
+    "y_ffn1_gelu_1stream": (73600, 3072, 768, 0, 0, "gelu_noaux", 1, 0),
+    "y_ffn1_gg_8warps": (73600, 3072, 768, 0, 0, "gelu_grad", 1, 64),
 }
 
 
