@@ -148,9 +148,10 @@ __device__ __forceinline__ void row_store_f32(const RowF<NCH>& r, float* __restr
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
         const int e = (c * 32 + lane) * 8;
-        if (e < H)
+        if (e < H) {
             stg256_f32(p + e, make_float4(r.v[c][0], r.v[c][1], r.v[c][2], r.v[c][3]),
                        make_float4(r.v[c][4], r.v[c][5], r.v[c][6], r.v[c][7]));
+        }
     }
 }
 template <int NCH>
