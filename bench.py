@@ -439,6 +439,8 @@ def main():
     ap.add_argument("--dp-mode", default=None, choices=["deferred", "overlap"],
                     help="N>1: gradient all-reduce schedule (msa_b200.ddp.GradReducer; default deferred)")
     ap.add_argument("--dp-compress", default=None, choices=["bf16"], help="N>1: all-reduce a bf16 copy of the gradient")
+    ap.add_argument("--dp-chunks", type=int, default=4,
+                    help="N>1, deferred: pieces of the all-reduce the fused AdamW consumes one by one (1 = wait for all of it)")
     ap.add_argument("--reserve-sms", type=int, default=None,
                     help="N>1: SMs the persistent kernels leave to NCCL (default 4; MMB_RESERVE_SMS overrides)")
     ap.add_argument("--nccl-ctas", type=int, default=None, help="N>1: NCCL_MAX_CTAS (default 4; 0 = NCCL's own choice)")
@@ -491,6 +493,9 @@ def main():
     opt.grad_scale = 1.0 / world
     reducer = (GradReducer(model._store, shape.num_hidden_layers, mode=dp_mode, compress=args.dp_compress).attach(model)
                if world > 1 else None)
+    if reducer is not None and dp_mode == "deferred" and args.dp_compress is None and args.dp_chunks > 1:
+        reducer.pipeline_optimizer(opt, chunks=args.dp_chunks)     # AdamW of piece k under the exchange of pieces k+1..
+        dp["chunks"] = args.dp_chunks
 
     B = workload.batch
     nb = 4  # distinct synthetic batches, cycled

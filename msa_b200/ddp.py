@@ -68,6 +68,11 @@ class GradReducer:
         if self.mode not in ("deferred", "overlap") or self.compress not in (None, "bf16"):
             raise ValueError(f"GradReducer: mode={self.mode!r} compress={self.compress!r}")
         self._cbuf = None
+        # deferred mode, optional: the all-reduce goes out in ``chunks`` pieces that nobody waits for at the end of the
+        # backward; the fused AdamW then waits for piece k and updates that slice while pieces k+1.. are still in flight
+        # (pipeline_optimizer).  Until optimizer.step() — or wait_all() — the gradient buffer is NOT reduced.
+        self.chunks = 1
+        self.inflight = []
         self.sched = bucket_schedule(store, num_layers)
         assert check_partition(self.sched, store.trainable_end)
         self.pending = []
@@ -94,9 +99,33 @@ class GradReducer:
             self.pending.append(dist.all_reduce(self.store.grad[a:b], op=dist.ReduceOp.SUM, group=self.group,
                                                 async_op=True))
 
+    def pipeline_optimizer(self, optimizer, chunks=4):
+        """Lets ``optimizer`` (msa_b200.optim.FusedAdamW) consume the deferred all-reduce piece by piece: its step() waits
+        for one piece at a time, so the parameter update runs under the rest of the exchange.  Anything else that reads
+        gradients between backward and step must call ``wait_all()`` first."""
+        if self.mode != "deferred" or self.compress is not None:
+            raise ValueError("pipeline_optimizer needs mode='deferred' without compression")
+        self.chunks = max(1, int(chunks))
+        optimizer._reducer = self
+        return self
+
+    def wait_all(self):
+        for _, _, w in self.inflight:
+            w.wait()
+        self.inflight = []
+
     def finish(self):
         """End of the backward sweep.  deferred: the one all-reduce of the step; both modes: the current stream then
         waits for every outstanding collective (no host synchronisation on NCCL)."""
+        if self.mode == "deferred" and self.world > 1 and self.sync and self.chunks > 1:
+            n = self.store.trainable_end
+            step = ((n + self.chunks - 1) // self.chunks + 63) // 64 * 64      # 256-byte aligned slices
+            self.wait_all()
+            for a in range(0, n, step):
+                b = min(n, a + step)
+                self.inflight.append((a, b, dist.all_reduce(self.store.grad[a:b], op=dist.ReduceOp.SUM, group=self.group,
+                                                            async_op=True)))
+            return
         if self.mode == "deferred" and self.world > 1 and self.sync:
             g = self.store.grad[:self.store.trainable_end]
             if self.compress == "bf16":

@@ -30,6 +30,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self._step = 0
         self._flat_ptr = st.flat.data_ptr()     # the buffers the moments belong to (checked on every step)
         self.grad_scale = 1.0      # 1/world_size after a SUM all-reduce
+        self._reducer = None       # msa_b200.ddp.GradReducer.pipeline_optimizer: pieces of the all-reduce still in flight
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -38,13 +39,27 @@ class FusedAdamW(torch.optim.Optimizer):
             raise capi.MMBError("model storage was re-materialised after the optimizer was built (build FusedAdamW "
                                 "after .cuda() / set_joint_embeddings)")
         self._step += 1
-        for (a, b), group in zip(self._ranges, self.param_groups):
-            args = capi.fill(capi.AdamwArgs(), p=st.flat[a:b], g=st.grad[a:b], m=self._m[a:b], v=self._v[a:b],
-                             p_bf16=st.bf16[a:b], n=b - a, lr=group["lr"], beta1=group["betas"][0],
-                             beta2=group["betas"][1], eps=group["eps"], weight_decay=group["weight_decay"],
-                             grad_scale=self.grad_scale, step=self._step, correct_bias=int(group["correct_bias"]))
-            capi.call("adamw", args)
-        self.model.launches += 2
+        # slices to update, in order: the whole buffer, or the pieces of a pipelined all-reduce (each waited for right
+        # before its update, so the update of piece k runs while pieces k+1.. are still being exchanged)
+        red = self._reducer
+        pieces = [(0, st.trainable_end, None)]
+        if red is not None and red.inflight:
+            pieces, red.inflight = red.inflight, []
+        launches = 0
+        for lo, hi, work in pieces:
+            if work is not None:
+                work.wait()
+            for (a, b), group in zip(self._ranges, self.param_groups):
+                a, b = max(a, lo), min(b, hi)
+                if a >= b:
+                    continue
+                args = capi.fill(capi.AdamwArgs(), p=st.flat[a:b], g=st.grad[a:b], m=self._m[a:b], v=self._v[a:b],
+                                 p_bf16=st.bf16[a:b], n=b - a, lr=group["lr"], beta1=group["betas"][0],
+                                 beta2=group["betas"][1], eps=group["eps"], weight_decay=group["weight_decay"],
+                                 grad_scale=self.grad_scale, step=self._step, correct_bias=int(group["correct_bias"]))
+                capi.call("adamw", args)
+                launches += 1
+        self.model.launches += launches
         # the kernel wrote parameters through raw pointers: version counters did not move, the mirror is fresh.
         # the frame-projection transposes are rebuilt by the next forward:
         for plan in self.model._plans.values():
@@ -71,6 +86,8 @@ class FusedAdamW(torch.optim.Optimizer):
     def zero_grad(self, set_to_none=False):
         """Zeroes the flat gradient buffer with one memset and keeps the ``.grad`` views attached."""
         st = self.model._store
+        if self._reducer is not None:
+            self._reducer.wait_all()        # pieces of a pipelined all-reduce nobody consumed
         st.grad[:st.trainable_end].zero_()
         if set_to_none:
             for p in self.model._trainable:

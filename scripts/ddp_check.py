@@ -56,5 +56,27 @@ none_ok = all(p.grad is None for n, p in m.named_parameters() if "W_cv" in n or 
 print(f"rank {rank}: max rel diff DP vs mean-of-local grads = {err:.3e}; untouched params stay None: {none_ok}", flush=True)
 # fp32 atomics make each local gradient run-to-run nondeterministic at the 1e-6 level
 assert err < 1e-3 and none_ok
+# pipelined optimizer: the all-reduce in 4 pieces, FusedAdamW waiting for one piece at a time — same parameters afterwards
+from msa_b200.optim import FusedAdamW
+after = []
+for chunks in (1, 4):
+    mm = build()
+    mm._ensure_store(dev)
+    broadcast_parameters(mm)
+    opt = FusedAdamW(mm, lr=1e-3)
+    opt.grad_scale = 1.0 / world
+    red = GradReducer(mm._store, shape.num_hidden_layers, mode="deferred").attach(mm)
+    if chunks > 1:
+        red.pipeline_optimizer(opt, chunks=chunks)
+    for _ in range(2):
+        o, _ = mm(**batches[rank])
+        o[0].backward()
+        opt.step()
+        opt.zero_grad()
+    torch.cuda.synchronize()
+    after.append(mm._store.flat[:mm._store.trainable_end].clone())
+perr = float((after[0] - after[1]).abs().max() / after[0].abs().max())
+print(f"rank {rank}: pipelined vs plain deferred optimizer, max rel parameter diff after 2 steps = {perr:.3e}", flush=True)
+assert perr < 1e-4
 dist.barrier()
 dist.destroy_process_group()

@@ -21,9 +21,10 @@ timeout 300 python bench.py --steps 12 --warmup 4 --no-cpu-baseline --no-gpu-tor
 python -c "
 import json; d=json.load(open('gpurun_out/${tag}_n1.json')); print('n1', round(d['value'],1), round(d['ms_per_step'],2))"
 run deferred
+run deferred_nopipe --dp-chunks 1
 run deferred_bf16 --dp-compress bf16
 run overlap --dp-mode overlap
 run deferred_again
 MMB_DP_MODE=deferred timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 scripts/ddp_check.py > gpurun_out/${tag}_ddp_check.txt 2>&1
-grep "max rel" gpurun_out/${tag}_ddp_check.txt | cut -c1-200
+grep -E "max rel|Error|error" gpurun_out/${tag}_ddp_check.txt | cut -c1-200
 tail -3 gpurun_out/${tag}_deferred.err

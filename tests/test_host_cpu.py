@@ -205,6 +205,17 @@ def _ddp_worker(rank, world, port, q, mode="overlap"):
     red.finish()
     want = sum((r + 1) + 10.0 * (r + 1) for r in range(world))                       # sum over ranks of (g1 + g2)
     ok = ok and bool((st.grad[:st.trainable_end] == want).all())
+    if mode == "deferred":
+        # pipelined form: finish() only ISSUES the pieces; they tile the trainable range and wait_all() completes them
+        red.chunks = 3
+        st.grad[:st.trainable_end] = float(rank + 1)
+        red.finish()
+        pieces = [(a, b) for a, b, _ in red.inflight]
+        ok = ok and len(pieces) == 3 and pieces[0][0] == 0 and pieces[-1][1] == st.trainable_end
+        ok = ok and all(pieces[i][1] == pieces[i + 1][0] for i in range(2))
+        red.wait_all()
+        ok = ok and not red.inflight and bool((st.grad[:st.trainable_end] == sum(range(1, world + 1))).all())
+        ok = ok and bool((st.grad[st.trainable_end:] == 0.0).all())                  # (zeroed above) still not communicated
     q.put((rank, ok, red.bytes_per_step))
     dist.destroy_process_group()
 
