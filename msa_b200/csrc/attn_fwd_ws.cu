@@ -70,6 +70,12 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+// three-input maximum (FMNMX3, sm_100)
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -383,15 +389,15 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
                     const float2 x1 = fma2(make_float2(__uint_as_float(s_raw[4 * i + 2]), __uint_as_float(s_raw[4 * i + 3])), sc2,
                                            make_float2(b.z, b.w));
                     x[4 * i] = x0.x; x[4 * i + 1] = x0.y; x[4 * i + 2] = x1.x; x[4 * i + 3] = x1.y;
-                    m_part = fmaxf(m_part, fmaxf(fmaxf(x0.x, x0.y), fmaxf(x1.x, x1.y)));
+                    m_part = max3(max3(m_part, x0.x, x0.y), x1.x, x1.y);
                 }
                 // row maximum across the four warps of this lane quarter
                 const uint32_t mx = smax + (uint32_t)((g & 1) * 4 * kRows) * 4;
                 sts32(mx + (uint32_t)(cq * kRows + r) * 4, __float_as_uint(m_part));
                 quarter_sync();
-                const float m_tile = fmaxf(fmaxf(__uint_as_float(lds32(mx + (uint32_t)r * 4)), __uint_as_float(lds32(mx + (uint32_t)(kRows + r) * 4))),
-                                           fmaxf(__uint_as_float(lds32(mx + (uint32_t)(2 * kRows + r) * 4)),
-                                                 __uint_as_float(lds32(mx + (uint32_t)(3 * kRows + r) * 4))));
+                const float m_tile = max3(fmaxf(__uint_as_float(lds32(mx + (uint32_t)r * 4)), __uint_as_float(lds32(mx + (uint32_t)(kRows + r) * 4))),
+                                          __uint_as_float(lds32(mx + (uint32_t)(2 * kRows + r) * 4)),
+                                          __uint_as_float(lds32(mx + (uint32_t)(3 * kRows + r) * 4)));
                 // lazy reference maximum: move it (and rescale O and the partial sum) only when exceeded by more than 2^8
                 const bool need = m_tile > m_ref + 8.f;     // identical for the four threads of a row
                 if (__any_sync(0xffffffffu, need)) {
@@ -419,15 +425,22 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
                 const float2 nm2 = make_float2(-m_ref, -m_ref);
                 uint32_t pk[8];
                 float2 lacc = make_float2(0.f, 0.f);
+                uint32_t kk[16];       // this thread's 16 column dropout keys: four 16-byte shared loads
+                if (kDrop) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint4 q = lds_u4(cv + kStep * 4 + i * 16);
+                        kk[4 * i] = q.x; kk[4 * i + 1] = q.y; kk[4 * i + 2] = q.z; kk[4 * i + 3] = q.w;
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float2 xs = add2(make_float2(x[2 * i], x[2 * i + 1]), nm2);
                     float2 pr = make_float2(ex2_approx(xs.x), ex2_approx(xs.y));
                     lacc = add2(lacc, pr);
                     if (kDrop) {       // dropped entries become 0; the 1/(1-p) rescale is applied once in the epilogue
-                        const uint32_t k0 = lds32(cv + kStep * 4 + (2 * i) * 4), k1 = lds32(cv + kStep * 4 + (2 * i + 1) * 4);
-                        pr.x = attn_keep(qkey, k0, p.thresh32) ? pr.x : 0.f;
-                        pr.y = attn_keep(qkey, k1, p.thresh32) ? pr.y : 0.f;
+                        pr.x = attn_keep(qkey, kk[2 * i], p.thresh32) ? pr.x : 0.f;
+                        pr.y = attn_keep(qkey, kk[2 * i + 1], p.thresh32) ? pr.y : 0.f;
                     }
                     pk[i] = pack_bf16x2(pr.x, pr.y);
                 }

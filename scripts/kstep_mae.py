@@ -18,8 +18,12 @@ ap.add_argument("--B", type=int, default=8)
 ap.add_argument("--T", type=int, default=20)
 ap.add_argument("--lr", type=float, default=5e-4)
 ap.add_argument("--dataset", default="mosi")
+ap.add_argument("--dropout", type=int, default=1, help="0: dropout off on both sides (deterministic comparison, one seed)")
 a = ap.parse_args()
 t0 = time.time()
-r = kstep.run(O.Cfg(num_hidden_layers=a.layers), a.dataset, K=a.K, B=a.B, T=a.T, L=a.T, seeds=a.seeds, lr=a.lr)
+if a.dropout:
+    r = kstep.run(O.Cfg(num_hidden_layers=a.layers), a.dataset, K=a.K, B=a.B, T=a.T, L=a.T, seeds=a.seeds, lr=a.lr)
+else:
+    r = kstep.run(O.Cfg(num_hidden_layers=a.layers), a.dataset, K=a.K, B=a.B, T=a.T, L=a.T, seeds=1, lr=a.lr, p=(0.0, 0.0, 0.0))
 r["seconds"] = time.time() - t0
 print(json.dumps(r))
