@@ -10,7 +10,7 @@ from msa_b200.params import BertShape, seeded_state_dict
 from oracle import mmbert_oracle as O
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 12
-P = (0.1, 0.1, 0.5)
+P = tuple(float(v) for v in sys.argv[2].split(",")) if len(sys.argv) > 2 else (0.1, 0.1, 0.5)     # hidden, attention, joint
 ocfg = O.Cfg(num_hidden_layers=2)
 sd = seeded_state_dict(ocfg, "mosi", seed=31, std=0.02)
 batch = synth.make_batch(6, 16, 16, 16, 47, 74, vocab_size=ocfg.vocab_size, seed=500, min_len=5)
@@ -46,6 +46,7 @@ for s in range(n):
     res["oracle"]["loss"].append(float(o[0]))
     for k in names:
         res["oracle"][k].append(float(grads[k].double().norm()))
+print(f"# dropout (hidden, attention, joint) = {P}, {n} seeds")
 for key in ("loss",) + names:
     mc, sc = stats(res["cuda"][key])
     mo, so = stats(res["oracle"][key])
