@@ -1016,10 +1016,30 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
                         }
                         bias_add_chunk(p, v, col0);
-                        activate_chunk(p.epilogue, has_aux, v, w);
                         stage_acquire(lane);
-                        stage_row(stage_buf, v, lane);
-                        if (has_aux) stage_row(stage_buf + 2048, w, lane);
+                        if (p.epilogue == MMB_EPI_GELU_GRAD_BF16 || p.epilogue == MMB_EPI_GELU_BF16) {
+                            // 8 columns at a time -> one 16-byte segment of each staging row: only 4 pairs of results are live
+                            // (this kernel has 96 registers per thread; 32 + 32 fp32 results at once left the erf math no ILP)
+                            const bool grad = p.epilogue == MMB_EPI_GELU_GRAD_BF16;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint32_t pg[4], pd[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float2 x = make_float2(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+                                    float2 g, dg;
+                                    gelu_fast2(x, g, dg);
+                                    pg[i] = pack_bf16x2(g.x, g.y);
+                                    pd[i] = grad ? pack_bf16x2(dg.x, dg.y) : pack_bf16x2(x.x, x.y);     // gelu' | pre-activation
+                                }
+                                sts128(stage_buf + stage_off(lane, j), pg[0], pg[1], pg[2], pg[3]);
+                                if (has_aux) sts128(stage_buf + 2048 + stage_off(lane, j), pd[0], pd[1], pd[2], pd[3]);
+                            }
+                        } else {
+                            activate_chunk(p.epilogue, has_aux, v, w);
+                            stage_row(stage_buf, v, lane);
+                            if (has_aux) stage_row(stage_buf + 2048, w, lane);
+                        }
                         stage_release(&tmC, stage_buf, has_aux ? &tmAux : nullptr, stage_buf + 2048, col0, row_base, lane);
                     }
                 }
