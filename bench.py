@@ -151,8 +151,11 @@ def executed_train_gflop_per_sample(shape, workload, batches):
     """The dense-faithful figure of SURVEY.md §8d counts every attention score of the S x S square.  The kernels skip
     what is exactly zero: key tiles behind the last unmasked key (forward and backward) and, in the backward, the query
     rows behind it (their upstream gradient is exactly zero).  This returns the train GFLOP per sample with the attention
-    term counted as EXECUTED (forward 4 S e H, backward 8 e^2 H per sequence with e = 1 + last unmasked key), averaged over
-    the given host batches — reported next to the dense-faithful number so that neither hides the other."""
+    term counted as EXECUTED (forward 4 q e H with q = the query rows of the 128-row tiles that start before e — the
+    training forward leaves the tiles entirely behind e alone, mmb_attn_args.flags bit 3 —, backward 8 e^2 H per sequence
+    with e = 1 + last unmasked key), averaged over the given host batches — reported next to the dense-faithful number so
+    that neither hides the other."""
+    fwd_skip = os.environ.get("MMB_ATTN_QSKIP", "1") != "0" and os.environ.get("MMB_ATTN_FWD_QSKIP", "1") != "0"
     H, N = shape.hidden_size, shape.num_hidden_layers
     dense = train_gflop_per_sample(shape, workload)
     T = workload.T
@@ -173,7 +176,8 @@ def executed_train_gflop_per_sample(shape, workload, batches):
             S = float(mask.shape[1])
             e = eff(mask)
             d_attn += float(N * 12.0 * S * S * H * mask.shape[0])
-            e_attn += float(N * H * (4.0 * S * e + 8.0 * e * e).sum())
+            q = torch.clamp(torch.ceil(e / 128.0) * 128.0, max=S) if fwd_skip else torch.full_like(e, S)
+            e_attn += float(N * H * (4.0 * q * e + 8.0 * e * e).sum())
         nsamp += m_t.shape[0]
     return dense + (e_attn - d_attn) / nsamp / 1e9
 
@@ -625,7 +629,7 @@ def main():
                          "step_frac": value / world * gf / 1e3 / peaks["tflops"],
                          "step_frac_burst": value / world * gf / 1e3 / peaks["burst"],
                          "peak_burst": peaks["burst"], "train_gflop_per_sample": gf,
-                         # attention counted as executed (exact-zero key tiles / query rows skipped), everything else dense
+                         # attention counted as executed (exact-zero key tiles / padded query rows skipped), everything else dense
                          "train_gflop_per_sample_executed": gf_exec,
                          "step_frac_executed": value / world * gf_exec / 1e3 / peaks["tflops"]},
             "model_flops": {"train_gflop_per_sample": gf, "achieved_tflops_per_gpu": value / world * gf / 1e3,

@@ -205,7 +205,14 @@ typedef struct mmb_attn_args {
     float p_drop;
     uint64_t seed;
     uint32_t rng_stream;
-    uint32_t flags; /* 0 = default; bring-up: bit 1 forces the persistent warp-specialised forward kernel, bit 2 the other one */
+    uint32_t flags; /* 0 = default; bring-up: bit 1 forces the persistent warp-specialised forward kernel, bit 2 the other one.
+                       bit 3 (value 8), forward with work lists only: if mmb_attn_schedule set the zero-gradient-tail bit
+                       (no row at or behind kv_end carries a label), the 128-query tiles that lie ENTIRELY behind kv_end
+                       are not computed and their ctx / lse rows keep their previous contents.  Those rows are padding:
+                       masked keys for every query of every layer and never read by a loss, so every value the model
+                       returns (and every gradient) is unchanged bit for bit — callers that read the hidden states or the
+                       vocabulary logits of padded positions (materialised pred_t / pred_v / pred_s) must leave it clear.
+                       ctx must hold finite values (e.g. zero-initialised once): the next GEMM still reads those rows. */
     const void* work;       /* NULL, or the work lists written by mmb_attn_schedule for the same cu_seqlens / kv_end /
                                nheads / max_seqlen: the persistent kernels then take their (sequence, head, tile) items
                                longest first instead of in index order (same results bit for bit; evens out the CTAs) */
@@ -231,7 +238,8 @@ int mmb_attn_bwd(const mmb_attn_args* a, void* stream);
  * device (every row_label at or behind kv_end is -100) and, if it holds, sets bit 30 of the header's cap field and
  * orders the dK/dV list by effective key count; mmb_attn_bwd then runs the dK/dV pass over ceil(kv_end / 64) query steps
  * instead of ceil(length / 64), and the dQ pass over the dK/dV list (query tiles behind kv_end only store zeros).
- * Same results bit for bit as the full sweep; the forward is unaffected (those rows' outputs are defined). */
+ * Same results bit for bit as the full sweep; the forward is unaffected (those rows' outputs are defined) unless the
+ * caller sets mmb_attn_args.flags bit 3. */
 typedef struct mmb_attn_schedule_args {
     const int32_t* cu_seqlens; /* [nseq + 1] */
     const int32_t* kv_end;     /* [nseq] or NULL */

@@ -36,6 +36,8 @@ __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dctx, const __nv_bfloat16* __restrict__ ctx,
                      const float* __restrict__ lse, const float* __restrict__ keybias, uint4* __restrict__ ws,
                      int total_rows, int H, int nheads, int drop, uint64_t seed, uint32_t rng_stream) {
+    pdl_trigger();
+    pdl_wait();
     // one 8-lane group per (row, head): 8 lanes x 8 bf16 = 64
     const int gidx = (blockIdx.x * 256 + threadIdx.x) >> 3;
     const int sub = threadIdx.x & 7;
@@ -77,6 +79,8 @@ constexpr int kSchedMaxSeqs = 8192;
 __global__ void __launch_bounds__(kSchedThreads)
 attn_schedule_kernel(const int* __restrict__ cu, const int* __restrict__ kv_end, const int* __restrict__ row_label,
                      int4* __restrict__ work, int nseq, int nheads, int cap) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ int sm[];
     int* len = sm;                 // sequence length
     int* eff = sm + nseq;          // keys before the all-masked tail
@@ -182,8 +186,8 @@ extern "C" int mmb_attn_schedule(const mmb_attn_schedule_args* a, void* stream) 
     const int smem = 6 * a->nseq * (int)sizeof(int);
     if (smem > 48 * 1024)
         MMB_CUDA(cudaFuncSetAttribute(attn_schedule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attn_schedule_kernel<<<1, kSchedThreads, smem, (cudaStream_t)stream>>>(a->cu_seqlens, a->kv_end, a->row_label,
-                                                                           (int4*)a->work, a->nseq, a->nheads, (int)cap);
+    launch_pdl(attn_schedule_kernel, dim3(1), dim3(kSchedThreads), (size_t)smem, (cudaStream_t)stream, a->cu_seqlens, a->kv_end,
+               a->row_label, (int4*)a->work, a->nseq, a->nheads, (int)cap);
     return check_launch("attn_schedule_kernel");
 }
 
@@ -207,9 +211,9 @@ extern "C" int mmb_attn_bwd(const mmb_attn_args* a, void* stream) {
     MMB_REQUIRE(a->ctx && a->lse && a->dctx && a->dqkv && a->bwd_ws, "attn_bwd: null pointer");
     MMB_REQUIRE(((uintptr_t)a->bwd_ws % 16) == 0, "attn_bwd: workspace must be 16-byte aligned");
     const long long groups = (long long)a->total_rows * a->nheads;
-    attn_bwd_prep_kernel<<<(unsigned)((groups * 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)a->dctx, (const __nv_bfloat16*)a->ctx, a->lse, a->keybias, (uint4*)a->bwd_ws, a->total_rows,
-        a->H, a->nheads, a->p_drop > 0.f ? 1 : 0, a->seed, a->rng_stream);
+    launch_pdl(attn_bwd_prep_kernel, dim3((unsigned)((groups * 8 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
+               (const __nv_bfloat16*)a->dctx, (const __nv_bfloat16*)a->ctx, a->lse, a->keybias, (uint4*)a->bwd_ws, a->total_rows,
+               a->H, a->nheads, a->p_drop > 0.f ? 1 : 0, a->seed, a->rng_stream);
     rc = check_launch("attn_bwd_prep_kernel");
     if (rc != MMB_OK) return rc;
     return launch_attn_bwd_tc(a, (cudaStream_t)stream);

@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(kWsThreads, 1)
 attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_constant__ CUtensorMap tm_qkv64,
                    const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_aux128,
                    const __grid_constant__ CUtensorMap tm_aux64, const BwdTcParams p) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = sbase + off_bars<kIsDq>();
@@ -274,6 +275,8 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
         }
         ptx::fence_barrier_init();
     }
+    if (warp == kScoreWarp) ptx::tmem_alloc<512>(tmem_slot);
+    pdl_wait();        // barriers and tensor memory are set up; everything below reads what earlier kernels wrote
     // sequence metadata -> shared memory (items are decoded from it by every role; an item whose tile lies beyond its
     // sequence is skipped for the price of two shared loads instead of a global round trip)
     extern __shared__ uint8_t smem_generic[];
@@ -286,7 +289,6 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
     }
     const int* m_cu = meta_in_smem ? meta : p.cu_seqlens;
     const int* m_kv = p.kv_end == nullptr ? nullptr : (meta_in_smem ? meta + kMetaSeqs + 2 : p.kv_end);
-    if (warp == kScoreWarp) ptx::tmem_alloc<512>(tmem_slot);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -584,7 +586,8 @@ int launch_pass(const CUtensorMap& q128, const CUtensorMap& q64, const CUtensorM
     MMB_ENSURE_SMEM(smem_bytes<kIsDq>(), attn_bwd_ws_kernel<kIsDq, kDrop>);
     const int items = p.tiles * p.nheads * p.nseq;
     const int grid = items < persistent_sms() ? items : persistent_sms();
-    attn_bwd_ws_kernel<kIsDq, kDrop><<<grid, kWsThreads, smem_bytes<kIsDq>(), stream>>>(q128, q64, dmap, aux128, aux64, p);
+    launch_pdl(attn_bwd_ws_kernel<kIsDq, kDrop>, dim3(grid), dim3(kWsThreads), smem_bytes<kIsDq>(), stream, q128, q64, dmap, aux128,
+               aux64, p);
     return check_launch(kIsDq ? "attn_bwd_ws_kernel<dQ>" : "attn_bwd_ws_kernel<dKV>");
 }
 

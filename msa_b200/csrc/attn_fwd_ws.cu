@@ -62,6 +62,7 @@ struct FwParams {
     float inv_keep;
     uint64_t seed;
     uint32_t rng_stream;
+    int skip_tail;             // flags bit 3: query tiles entirely behind kv_end may stay unwritten (see mmb_attn_args.flags)
 };
 
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t x) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(x) : "memory"); }
@@ -152,6 +153,7 @@ __device__ __forceinline__ Item make_item(const FwParams& p, const int* cu, cons
 template <bool kDrop>
 __global__ void __launch_bounds__(kFwThreads, 1)
 attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_constant__ CUtensorMap tm_q64, const FwParams p) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sbase - ptx::smem_u32(smem_raw));
@@ -181,6 +183,8 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
         }
         ptx::fence_barrier_init();
     }
+    if (warp == kScoreWarp) ptx::tmem_alloc<256>(tmem_slot);
+    pdl_wait();        // barriers and tensor memory are set up; everything below reads what earlier kernels wrote
     int* meta = reinterpret_cast<int*>(sgen + kOffMeta);
     const bool meta_in_smem = p.nseq <= kMetaSeqs;
     if (meta_in_smem) {
@@ -190,7 +194,6 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
     }
     const int* m_cu = meta_in_smem ? meta : p.cu_seqlens;
     const int* m_kv = p.kv_end == nullptr ? nullptr : (meta_in_smem ? meta + kMetaSeqs + 2 : p.kv_end);
-    if (warp == kScoreWarp) ptx::tmem_alloc<256>(tmem_slot);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -198,8 +201,16 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
     int total_items = p.tiles * p.nheads * p.nseq;
     const int4* wl = nullptr;
     if (p.work != nullptr) {
-        total_items = __ldg(p.work).x;                       // header {items of this list, of the dK/dV list, capacity}
+        const int4 hdr = __ldg(p.work);      // {items of this list, of the dK/dV list, capacity | qskip << 30, unmasked dK/dV items}
+        total_items = hdr.x;
         wl = p.work + 1;
+        if (p.skip_tail && ((hdr.z >> 30) & 1)) {
+            // The schedule verified that no row at or behind kv_end carries a label: those rows are masked keys for every
+            // query and feed no loss, so a 128-query tile that lies entirely behind kv_end is unobservable.  Walk the
+            // unmasked part of the dK/dV list instead: one record per 128-row tile that starts before kv_end.
+            total_items = hdr.w;
+            wl = p.work + 1 + (hdr.z & 0x3fffffff);
+        }
     }
     const int stride = gridDim.x;
     // TMEM columns: score slot s at s * 64, O accumulator a at 128 + a * 64
@@ -477,7 +488,7 @@ int launch(const CUtensorMap& q128, const CUtensorMap& q64, const FwParams& p, c
     MMB_ENSURE_SMEM(kFwSmem, attn_fwd_ws_kernel<kDrop>);
     const int items = p.tiles * p.nheads * p.nseq;
     const int grid = items < persistent_sms() ? items : persistent_sms();
-    attn_fwd_ws_kernel<kDrop><<<grid, kFwThreads, kFwSmem, stream>>>(q128, q64, p);
+    launch_pdl(attn_fwd_ws_kernel<kDrop>, dim3(grid), dim3(kFwThreads), kFwSmem, stream, q128, q64, p);
     return check_launch("attn_fwd_ws_kernel");
 }
 
@@ -506,6 +517,7 @@ int launch_attn_fwd_ws(const mmb_attn_args* a, cudaStream_t stream) {
     p.inv_keep = dropout_inv_keep(a->p_drop);
     p.seed = a->seed;
     p.rng_stream = a->rng_stream;
+    p.skip_tail = (a->flags & 8) ? 1 : 0;
     return p.thresh32 ? launch<true>(q128, q64, p, stream) : launch<false>(q128, q64, p, stream);
 }
 

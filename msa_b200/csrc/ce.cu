@@ -36,6 +36,8 @@ __device__ __forceinline__ void online_merge(float& m, float& s, float m2, float
 
 __global__ void __launch_bounds__(256)
 ce_fwd_kernel(const CeParams p) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const int row = blockIdx.x;
     int pass;
     const long long label = row_label(p, row, pass);
@@ -86,6 +88,8 @@ ce_fwd_kernel(const CeParams p) {
 
 __global__ void __launch_bounds__(256)
 ce_bwd_kernel(const CeParams p) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const int row = blockIdx.x;
     int pass;
     const long long label = row_label(p, row, pass);
@@ -128,6 +132,8 @@ ce_bwd_kernel(const CeParams p) {
 // fp32 validation path: the same statistics on f32 logits (one CTA per labelled row)
 __global__ void __launch_bounds__(256)
 ce_fwd_f32_kernel(const CeParams p) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const int row = blockIdx.x;
     int pass;
     const long long label = row_label(p, row, pass);
@@ -187,6 +193,8 @@ struct CeSparseParams {
 // one warp per row: merges the G group records of a labelled row
 __global__ void __launch_bounds__(256)
 ce_sparse_fwd_kernel(const CeSparseParams p) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= p.rows) return;
     if (p.row_label[row] == -100) return;
@@ -210,6 +218,8 @@ ce_sparse_fwd_kernel(const CeSparseParams p) {
 // in place.  Unlabelled but written in an earlier step: back to zero.  Everything else is already zero.
 __global__ void __launch_bounds__(256)
 ce_sparse_bwd_kernel(const CeSparseParams p) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const int row = blockIdx.x;
     const int label = p.row_label[row];
     float* flag = p.stats + (size_t)(2 * p.G + 1) * p.rows + row;
@@ -257,6 +267,8 @@ ce_sparse_bwd_kernel(const CeSparseParams p) {
 constexpr int kRowSlice = 1024;
 __global__ void __launch_bounds__(256)
 colsum_rows_kernel(const CeSparseParams p) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const int col = (blockIdx.x * 256 + threadIdx.x) * 2;
     const int r0 = blockIdx.y * kRowSlice, r1 = min(p.rows, r0 + kRowSlice);
     __shared__ int s_rows[kRowSlice];
@@ -336,10 +348,10 @@ extern "C" int mmb_ce_fwd(const mmb_ce_args* a, void* stream) {
     MMB_REQUIRE(a->loss_sum != nullptr, "ce_fwd: null loss_sum");
     MMB_CUDA(cudaMemsetAsync(a->loss_sum, 0, 3 * sizeof(float), (cudaStream_t)stream));
     if (a->logits_f32) {
-        ce_fwd_f32_kernel<<<p.pass_base[3], 256, 0, (cudaStream_t)stream>>>(p);
+        launch_pdl(ce_fwd_f32_kernel, dim3(p.pass_base[3]), dim3(256), (size_t)(0), (cudaStream_t)stream, p);
         return check_launch("ce_fwd_f32_kernel");
     }
-    ce_fwd_kernel<<<p.pass_base[3], 256, 0, (cudaStream_t)stream>>>(p);
+    launch_pdl(ce_fwd_kernel, dim3(p.pass_base[3]), dim3(256), (size_t)(0), (cudaStream_t)stream, p);
     return check_launch("ce_fwd_kernel");
 }
 
@@ -349,7 +361,7 @@ extern "C" int mmb_ce_bwd(const mmb_ce_args* a, void* stream) {
     if (rc != MMB_OK) return rc;
     MMB_REQUIRE(a->dlogits != nullptr, "ce_bwd: null dlogits");
     MMB_REQUIRE(!a->logits_f32, "ce_bwd: the fp32 validation path is forward-only");
-    ce_bwd_kernel<<<p.pass_base[3], 256, 0, (cudaStream_t)stream>>>(p);
+    launch_pdl(ce_bwd_kernel, dim3(p.pass_base[3]), dim3(256), (size_t)(0), (cudaStream_t)stream, p);
     return check_launch("ce_bwd_kernel");
 }
 
@@ -359,7 +371,7 @@ extern "C" int mmb_ce_sparse_fwd(const mmb_ce_sparse_args* a, void* stream) {
     if (rc != MMB_OK) return rc;
     MMB_REQUIRE(a->loss_sum != nullptr, "ce_sparse_fwd: null loss_sum");
     MMB_CUDA(cudaMemsetAsync(a->loss_sum, 0, 3 * sizeof(float), (cudaStream_t)stream));
-    ce_sparse_fwd_kernel<<<(p.rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p);
+    launch_pdl(ce_sparse_fwd_kernel, dim3((p.rows + 7) / 8), dim3(256), (size_t)(0), (cudaStream_t)stream, p);
     return check_launch("ce_sparse_fwd_kernel");
 }
 
@@ -368,7 +380,7 @@ extern "C" int mmb_ce_sparse_bwd(const mmb_ce_sparse_args* a, void* stream) {
     int rc = fill_sparse(p, a);
     if (rc != MMB_OK) return rc;
     MMB_REQUIRE(a->dlogits != nullptr, "ce_sparse_bwd: null dlogits");
-    ce_sparse_bwd_kernel<<<p.rows, 256, 0, (cudaStream_t)stream>>>(p);
+    launch_pdl(ce_sparse_bwd_kernel, dim3(p.rows), dim3(256), (size_t)(0), (cudaStream_t)stream, p);
     return check_launch("ce_sparse_bwd_kernel");
 }
 
@@ -378,6 +390,6 @@ extern "C" int mmb_colsum_rows_bf16(const mmb_ce_sparse_args* a, void* stream) {
     if (rc != MMB_OK) return rc;
     MMB_REQUIRE(a->dlogits != nullptr && a->dbias != nullptr, "colsum_rows: null pointer");
     dim3 grid((p.V + 511) / 512, (p.rows + kRowSlice - 1) / kRowSlice);
-    colsum_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    launch_pdl(colsum_rows_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, p);
     return check_launch("colsum_rows_kernel");
 }

@@ -51,8 +51,47 @@ int persistent_sms();   // num_sms() minus the SMs reserved for concurrent colle
         }                                                                                                            \
     } while (0)
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// A training step is ~345 kernels in one stream, most of them persistent grids that fill the chip; between two of them the
+// chip drains, the next grid is scheduled and runs its prologue (barrier init, TMEM allocation, descriptor prefetch) before
+// any useful work starts.  Launched with cudaLaunchAttributeProgrammaticStreamSerialization, kernel N+1's CTAs are placed as
+// soon as every CTA of kernel N has executed griddepcontrol.launch_dependents (pdl_trigger(), first statement of every
+// converted kernel) and an SM has room; they run their prologue and then block in griddepcontrol.wait (pdl_wait()) until
+// kernel N has COMPLETED and its writes are visible.  Rules every converted kernel keeps:
+//   * every thread executes pdl_wait() before its first global-memory access (read OR write) and before any return — a
+//     grid that finished without waiting would let ITS dependent overtake the grid before it;
+//   * only shared-memory / TMEM / barrier set-up and reads of kernel parameters happen before it.
+// Launched without the attribute both instructions are no-ops.  MMB_PDL=1 turns the attribute on (=2: also under stream
+// capture).  DEFAULT OFF: measured on B200 (same-box A/B) it buys nothing here — every heavy kernel is a
+// persistent grid whose CTAs each take a whole SM (~200 KB of shared memory, the full register file), so a dependent CTA
+// can only be placed once its predecessor's CTA on that SM has exited, and the grid still starts when the slowest one ends.
+int pdl_mode();      // 0 = off (default), 1 = on outside stream capture, 2 = always
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    int on = pdl_mode();
+    if (on == 1) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) on = 0;
+    }
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = on ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -65,6 +65,8 @@ struct PrepParams {
 };
 
 __global__ void pack_prepare_kernel(const PrepParams p) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const int rows = p.d.rows();
     int cnt[3] = {0, 0, 0};
     for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += gridDim.x * blockDim.x) {
@@ -181,6 +183,8 @@ __device__ __forceinline__ void text_embed_row(const EmbedParams& p, const RowCo
 template <int NCH>
 __global__ void __launch_bounds__(kEmbWarps * 32)
 embed_text_fwd_kernel(const EmbedParams p) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntext = 3 * p.d.B * p.d.T;
     for (int tr = blockIdx.x * kEmbWarps + warp; tr < ntext; tr += gridDim.x * kEmbWarps) {
@@ -224,6 +228,8 @@ constexpr int kFrameRows = 16;
 template <int NCH>
 __global__ void __launch_bounds__(256)
 embed_frame_fwd_kernel(const EmbedParams p, int mod) {  // mod 0 = visual (pass 1), 1 = speech (pass 2)
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     extern __shared__ float fsm[];
     const int D = p.frame_dim[mod], L = mod == 0 ? p.d.L1 : p.d.L2, pass = mod + 1;
     const int Dp = D + 1;
@@ -322,6 +328,8 @@ __device__ __forceinline__ void row_atomic_add(const RowF<NCH>& g, float* __rest
 template <int NCH>
 __global__ void __launch_bounds__(kEmbWarps * 32)
 embed_text_bwd_kernel(const EmbedParams p) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntext = 3 * p.d.B * p.d.T;
@@ -380,6 +388,8 @@ embed_text_bwd_kernel(const EmbedParams p) {
 template <int NCH>
 __global__ void __launch_bounds__(kEmbWarps * 32)
 embed_frame_bwd_kernel(const EmbedParams p) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nfr = p.d.frame_rows();
@@ -419,6 +429,8 @@ constexpr int kWgRows = 32;
 template <int DI>
 __global__ void __launch_bounds__(256)
 frame_wgrad_kernel(const EmbedParams p, int mod, int rows_per_cta) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     extern __shared__ float wsm[];
     const int D = p.frame_dim[mod], L = mod == 0 ? p.d.L1 : p.d.L2;
     const int Dp = D + 1;
@@ -468,6 +480,8 @@ frame_wgrad_kernel(const EmbedParams p, int mod, int rows_per_cta) {
 
 // g_w[c][k] += pad[c][k]  (k < D; pad has row stride ldf)
 __global__ void add_padded_kernel(float* __restrict__ gw, const float* __restrict__ pad, int H, int D, int ldf) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= H * D) return;
     const int c = i / D, k = i - c * D;
@@ -550,6 +564,7 @@ extern "C" int mmb_pack_prepare(const mmb_pack_args* a, void* stream) {
     if (a->kv_end) MMB_CUDA(cudaMemsetAsync(a->kv_end, 0, 3 * (size_t)a->B * sizeof(int), (cudaStream_t)stream));
     const int rows = p.d.rows();
     const int grid = min((rows + 255) / 256, num_sms() * 2);
+    // first kernel of a step: a plain launch (its inputs arrive through event waits from a copy stream; see common.cuh)
     pack_prepare_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("pack_prepare_kernel");
 }
@@ -564,7 +579,7 @@ extern "C" int mmb_embed_fwd(const mmb_embed_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int ntext = 3 * p.d.B * p.d.T;
     const int grid = min((ntext + kEmbWarps - 1) / kEmbWarps, num_sms() * 4);
-    MMB_DISPATCH_NCH(p.H, (embed_text_fwd_kernel<NCH><<<grid, kEmbWarps * 32, 0, st>>>(p)));
+    MMB_DISPATCH_NCH(p.H, (launch_pdl(embed_text_fwd_kernel<NCH>, dim3(grid), dim3(kEmbWarps * 32), (size_t)(0), st, p)));
     rc = check_launch("embed_text_fwd_kernel");
     if (rc != MMB_OK) return rc;
     for (int mod = 0; mod < 2; ++mod) {
@@ -575,7 +590,7 @@ extern "C" int mmb_embed_fwd(const mmb_embed_args* a, void* stream) {
         const size_t smem = (size_t)kFrameRows * (p.frame_dim[mod] + 1 + p.H) * sizeof(float);
         MMB_DISPATCH_NCH(p.H, {
             MMB_ENSURE_SMEM(160 * 1024, embed_frame_fwd_kernel<NCH>);
-            embed_frame_fwd_kernel<NCH><<<(nrows + kFrameRows - 1) / kFrameRows, 256, smem, st>>>(p, mod);
+            launch_pdl(embed_frame_fwd_kernel<NCH>, dim3((nrows + kFrameRows - 1) / kFrameRows), dim3(256), (size_t)(smem), st, p, mod);
         });
         rc = check_launch("embed_frame_fwd_kernel");
         if (rc != MMB_OK) return rc;
@@ -594,14 +609,14 @@ extern "C" int mmb_embed_bwd(const mmb_embed_args* a, void* stream) {
     const size_t smem = (size_t)kEmbWarps * p.H * sizeof(float);
     const int ntext = 3 * p.d.B * p.d.T;
     int grid = min((ntext + kEmbWarps - 1) / kEmbWarps, num_sms());
-    MMB_DISPATCH_NCH(p.H, (embed_text_bwd_kernel<NCH><<<grid, kEmbWarps * 32, smem, st>>>(p)));
+    MMB_DISPATCH_NCH(p.H, (launch_pdl(embed_text_bwd_kernel<NCH>, dim3(grid), dim3(kEmbWarps * 32), (size_t)(smem), st, p)));
     rc = check_launch("embed_text_bwd_kernel");
     if (rc != MMB_OK) return rc;
     const int nfr = p.d.frame_rows();
     if (nfr > 0) {
         MMB_REQUIRE(p.pframe && p.dpre, "embed_bwd: null frame buffers");
         grid = min((nfr + kEmbWarps - 1) / kEmbWarps, num_sms());
-        MMB_DISPATCH_NCH(p.H, (embed_frame_bwd_kernel<NCH><<<grid, kEmbWarps * 32, smem, st>>>(p)));
+        MMB_DISPATCH_NCH(p.H, (launch_pdl(embed_frame_bwd_kernel<NCH>, dim3(grid), dim3(kEmbWarps * 32), (size_t)(smem), st, p)));
         rc = check_launch("embed_frame_bwd_kernel");
         if (rc != MMB_OK) return rc;
         for (int mod = 0; mod < 2; ++mod) {
@@ -638,7 +653,7 @@ extern "C" int mmb_embed_bwd(const mmb_embed_args* a, void* stream) {
                 ga.split_k = sk < 1 ? 1 : sk;
                 rc = mmb_gemm(&ga, st);
                 if (rc != MMB_OK) return rc;
-                add_padded_kernel<<<(p.H * D + 255) / 256, 256, 0, st>>>(p.g_w[mod], p.gw_pad[mod], p.H, D, ldf);
+                launch_pdl(add_padded_kernel, dim3((p.H * D + 255) / 256), dim3(256), (size_t)(0), st, p.g_w[mod], p.gw_pad[mod], p.H, D, ldf);
                 rc = check_launch("add_padded_kernel");
                 if (rc != MMB_OK) return rc;
                 mmb_colsum_args ca;
@@ -659,10 +674,10 @@ extern "C" int mmb_embed_bwd(const mmb_embed_args* a, void* stream) {
             const size_t wsmem = (size_t)kWgRows * (64 + D + 1) * sizeof(float);
             dim3 g(col_tiles, chunks);
             if (D <= 96) {
-                frame_wgrad_kernel<24><<<g, 256, wsmem, st>>>(p, mod, rows_per_cta);
+                launch_pdl(frame_wgrad_kernel<24>, dim3(g), dim3(256), (size_t)(wsmem), st, p, mod, rows_per_cta);
             } else {
                 MMB_ENSURE_SMEM(96 * 1024, frame_wgrad_kernel<96>);
-                frame_wgrad_kernel<96><<<g, 256, wsmem, st>>>(p, mod, rows_per_cta);
+                launch_pdl(frame_wgrad_kernel<96>, dim3(g), dim3(256), (size_t)(wsmem), st, p, mod, rows_per_cta);
             }
             rc = check_launch("frame_wgrad_kernel");
             if (rc != MMB_OK) return rc;
@@ -685,6 +700,8 @@ struct MlmParams {
 };
 __global__ void __launch_bounds__(256)
 mlm_mask_kernel(const MlmParams p) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= p.B * p.T) return;
     const long long id = p.ids[i];

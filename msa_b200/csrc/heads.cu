@@ -24,6 +24,8 @@ constexpr int kSgT = 32;    // 32 x 32 output tiles: the largest head GEMM (192 
 __global__ void __launch_bounds__(256)
 sgemm64_kernel(const float* __restrict__ A, int sam, int sak, const float* __restrict__ B, int sbk, int sbn,
                float* __restrict__ C, int ldc, const float* __restrict__ bias, int act, int M, int N, int K, int accumulate) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     __shared__ __align__(16) float As[kSgBK][kSgT + 2];
     __shared__ __align__(16) float Bs[kSgBK][kSgT + 2];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -87,6 +89,8 @@ sgemm64_kernel(const float* __restrict__ A, int sam, int sak, const float* __res
 }
 // db[n] += sum_r dY[r][n]
 __global__ void bias_grad_kernel(const float* __restrict__ dY, int ldy, float* __restrict__ db, int R, int N) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     float s = 0.f;
@@ -97,24 +101,32 @@ __global__ void bias_grad_kernel(const float* __restrict__ dY, int ldy, float* _
 // ---------------------------------------------------------------- small fused elementwise kernels
 __global__ void gather_cls_kernel(const __nv_bfloat16* __restrict__ seq, const int* __restrict__ cu, float* __restrict__ X0,
                                   int R, int H) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const int r = blockIdx.x;
     const __nv_bfloat16* src = seq + (size_t)cu[r] * H;
     for (int j = threadIdx.x; j < H; j += blockDim.x) X0[(size_t)r * H + j] = __bfloat162float(src[j]);
 }
 __global__ void gather_cls_f32_kernel(const float* __restrict__ seq, const int* __restrict__ cu, float* __restrict__ X0, int R,
                                       int H) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const int r = blockIdx.x;
     const float* src = seq + (size_t)cu[r] * H;
     for (int j = threadIdx.x; j < H; j += blockDim.x) X0[(size_t)r * H + j] = src[j];
 }
 __global__ void scatter_cls_grad_kernel(const float* __restrict__ dX0, const int* __restrict__ cu, __nv_bfloat16* __restrict__ g,
                                         int R, int H) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const int r = blockIdx.x;
     __nv_bfloat16* dst = g + (size_t)cu[r] * H;
     for (int j = threadIdx.x; j < H; j += blockDim.x)
         dst[j] = __float2bfloat16_rn(__bfloat162float(dst[j]) + dX0[(size_t)r * H + j]);
 }
 __global__ void dup_cols_kernel(const float* __restrict__ P, float* __restrict__ PP, int R, int H) {  // PP = [P, P]
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const int r = blockIdx.x;
     for (int j = threadIdx.x; j < H; j += blockDim.x) {
         const float v = P[(size_t)r * H + j];
@@ -132,6 +144,8 @@ struct VPtrs {  // per-modality score vectors (0 = vt, 1 = vv, 2 = vs) and their
 __global__ void __launch_bounds__(256)
 score_scale_kernel(const float* __restrict__ U, const float* __restrict__ P, const VPtrs vp, float* __restrict__ s,
                    float* __restrict__ PC, int B, int H) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     __shared__ float red[8];
     const int r = blockIdx.x, m = r / B, b = r - m * B;
     const float* v = vp.w[m];
@@ -153,6 +167,8 @@ __global__ void __launch_bounds__(256)
 score_scale_bwd_kernel(const float* __restrict__ dPC, const float* __restrict__ P, const float* __restrict__ U,
                        const float* __restrict__ s, const VPtrs vp, float* __restrict__ dP, float* __restrict__ dA, int B,
                        int H) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     __shared__ float red[8];
     const int r = blockIdx.x, m = r / B, b = r - m * B;
     float acc = 0.f;
@@ -179,6 +195,8 @@ score_scale_bwd_kernel(const float* __restrict__ dPC, const float* __restrict__ 
 // accumulates nce += -(pos_i - neg_i) / B.   Two kernels: normalise, then rows.
 __global__ void __launch_bounds__(256)
 normalize_rows_kernel(const float* __restrict__ X, float* __restrict__ Y, float* __restrict__ norms, int H) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     __shared__ float red[8];
     const int r = blockIdx.x;
     float acc = 0.f;
@@ -200,6 +218,8 @@ normalize_rows_kernel(const float* __restrict__ X, float* __restrict__ Y, float*
 __global__ void __launch_bounds__(256)
 cpc_rows_kernel(const float* __restrict__ xn, const float* __restrict__ an, float* __restrict__ Sm, float* __restrict__ nce,
                 int B, int H) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     extern __shared__ float g[];
     __shared__ float red[8];
     const int i = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -253,6 +273,8 @@ cpc_rows_kernel(const float* __restrict__ xn, const float* __restrict__ an, floa
 }
 // dG_ij = c * (delta_ij - Sm_ij)   (c = beta * gs / B);  in place over Sm
 __global__ void cpc_dg_kernel(float* __restrict__ Sm, const float* __restrict__ gscale, float beta, int B) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * B) return;
     const float c = beta * (gscale ? *gscale : 1.f) / (float)B;
@@ -263,6 +285,8 @@ __global__ void cpc_dg_kernel(float* __restrict__ Sm, const float* __restrict__ 
 __global__ void __launch_bounds__(256)
 normalize_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, const float* __restrict__ norms,
                      float* __restrict__ out, int H, int accumulate) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     __shared__ float red[8];
     const int r = blockIdx.x;
     float acc = 0.f;
@@ -283,6 +307,8 @@ normalize_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, 
 // G-shaped products for CPC backward: out[i][k] = sum_j M[i][j] Y[j][k]  (transpose = 0) or sum_j M[j][i] Y[j][k] (1)
 __global__ void __launch_bounds__(256)
 bb_matmul_kernel(const float* __restrict__ Mx, const float* __restrict__ Y, float* __restrict__ out, int B, int H, int transpose) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const int i = blockIdx.x;
     extern __shared__ float mrow[];              // row (or column) i of Mx: B floats
     for (int j = threadIdx.x; j < B; j += 256) mrow[j] = transpose ? Mx[(size_t)j * B + i] : Mx[(size_t)i * B + j];
@@ -333,6 +359,8 @@ struct LossParams {
 // single CTA: AP cross entropies, MSE, loss combination (MMBertForPretraining.py:386-388, 427-443)
 __global__ void __launch_bounds__(256)
 final_losses_kernel(const LossParams p) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     __shared__ float red[8];
     float ap_acc = 0.f, mse_acc = 0.f;
     for (int i = threadIdx.x; i < 2 * p.B; i += 256) {
@@ -394,6 +422,8 @@ final_losses_kernel(const LossParams p) {
 }
 __global__ void __launch_bounds__(256)
 final_losses_bwd_kernel(const LossParams p) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const float gs = p.gscale ? *p.gscale : 1.f;
     for (int i = threadIdx.x; i < 2 * p.B; i += 256) {
         const int mod = i / p.B, b = i - mod * p.B;
@@ -415,10 +445,14 @@ final_losses_bwd_kernel(const LossParams p) {
     }
 }
 __global__ void tanh_bwd_kernel(float* __restrict__ dP, const float* __restrict__ P, int n) {  // dZ = dP (1 - P^2), in place
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dP[i] *= (1.f - P[i] * P[i]);
 }
 __global__ void fold_dup_grad_kernel(const float* __restrict__ dPP, float* __restrict__ dP, int R, int H) {  // dP += dPP[:, :H] + dPP[:, H:]
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const int r = blockIdx.x;
     for (int j = threadIdx.x; j < H; j += blockDim.x)
         dP[(size_t)r * H + j] += dPP[(size_t)r * 2 * H + j] + dPP[(size_t)r * 2 * H + H + j];
@@ -450,20 +484,20 @@ static HeadsWs heads_ws(int B, int H) {
 static inline void linear(cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy,
                           int R, int N, int K, int act) {
     dim3 g((N + kSgT - 1) / kSgT, (R + kSgT - 1) / kSgT);
-    sgemm64_kernel<<<g, 256, 0, st>>>(X, ldx, 1, W, 1, ldw, Y, ldy, b, act, R, N, K, 0);
+    launch_pdl(sgemm64_kernel, dim3(g), dim3(256), (size_t)(0), st, X, ldx, 1, W, 1, ldw, Y, ldy, b, act, R, N, K, 0);
 }
 // dX[R,K] (+)= dY[R,N] W[N,K]
 static inline void dx(cudaStream_t st, const float* dY, int ldy, const float* W, int ldw, float* dX, int ldx, int R, int N,
                       int K, int accumulate) {
     dim3 g((K + kSgT - 1) / kSgT, (R + kSgT - 1) / kSgT);
-    sgemm64_kernel<<<g, 256, 0, st>>>(dY, ldy, 1, W, ldw, 1, dX, ldx, nullptr, ACT_NONE, R, K, N, accumulate);
+    launch_pdl(sgemm64_kernel, dim3(g), dim3(256), (size_t)(0), st, dY, ldy, 1, W, ldw, 1, dX, ldx, nullptr, ACT_NONE, R, K, N, accumulate);
 }
 // dW[N,K] += dY[R,N]^T X[R,K] ; db[N] += colsum(dY)
 static inline void dw(cudaStream_t st, const float* dY, int ldy, const float* X, int ldx, float* dW, int ldw, float* db, int R,
                       int N, int K) {
     dim3 g((K + kSgT - 1) / kSgT, (N + kSgT - 1) / kSgT);
-    sgemm64_kernel<<<g, 256, 0, st>>>(dY, 1, ldy, X, ldx, 1, dW, ldw, nullptr, ACT_NONE, N, K, R, 1);
-    if (db) bias_grad_kernel<<<(N + 127) / 128, 128, 0, st>>>(dY, ldy, db, R, N);
+    launch_pdl(sgemm64_kernel, dim3(g), dim3(256), (size_t)(0), st, dY, 1, ldy, X, ldx, 1, dW, ldw, nullptr, ACT_NONE, N, K, R, 1);
+    if (db) launch_pdl(bias_grad_kernel, dim3((N + 127) / 128), dim3(128), (size_t)(0), st, dY, ldy, db, R, N);
 }
 
 }  // namespace mmb
@@ -525,14 +559,14 @@ extern "C" int mmb_heads_fwd(const mmb_heads_args* a, void* stream) {
     float* ws = (float*)a->workspace;
     const VPtrs vp = vptrs(a);
 
-    if (a->seq_out_f32) gather_cls_f32_kernel<<<R, 256, 0, st>>>((const float*)a->seq_out, a->cu_seqlens, ws + w.X0, R, H);
-    else gather_cls_kernel<<<R, 256, 0, st>>>((const __nv_bfloat16*)a->seq_out, a->cu_seqlens, ws + w.X0, R, H);
+    if (a->seq_out_f32) launch_pdl(gather_cls_f32_kernel, dim3(R), dim3(256), (size_t)(0), st, (const float*)a->seq_out, a->cu_seqlens, ws + w.X0, R, H);
+    else launch_pdl(gather_cls_kernel, dim3(R), dim3(256), (size_t)(0), st, (const __nv_bfloat16*)a->seq_out, a->cu_seqlens, ws + w.X0, R, H);
     linear(st, ws + w.X0, H, a->w_pooler, H, a->b_pooler, ws + w.P, H, R, H, H, ACT_TANH);
     if (a->w_seqrel && a->b_seqrel) linear(st, ws + w.P, H, a->w_seqrel, H, a->b_seqrel, ws + w.rel, 2, B, 2, H, ACT_NONE);
     linear(st, ws + w.X0 + (size_t)B * H, H, a->w_align, H, a->b_align, ws + w.al, 2, 2 * B, 2, H, ACT_NONE);
-    dup_cols_kernel<<<R, 256, 0, st>>>(ws + w.P, ws + w.PP, R, H);
+    launch_pdl(dup_cols_kernel, dim3(R), dim3(256), (size_t)(0), st, ws + w.P, ws + w.PP, R, H);
     linear(st, ws + w.PP, 2 * H, a->w_attn, 2 * H, a->b_attn, ws + w.U, H, R, H, 2 * H, ACT_RELU);
-    score_scale_kernel<<<R, 256, 0, st>>>(ws + w.U, ws + w.P, vp, ws + w.s, ws + w.PC, B, H);
+    launch_pdl(score_scale_kernel, dim3(R), dim3(256), (size_t)(0), st, ws + w.U, ws + w.P, vp, ws + w.s, ws + w.PC, B, H);
     linear(st, ws + w.PC, 3 * H, a->w_c11, 3 * H, a->b_c11, ws + w.temp, H, B, H, 3 * H, ACT_NONE);
     linear(st, ws + w.temp, H, a->w_c12, H, a->b_c12, ws + w.logit, 1, B, 1, H, ACT_NONE);
     MMB_CUDA(cudaMemsetAsync(ws + w.nce, 0, 4 * sizeof(float), st));
@@ -541,12 +575,12 @@ extern "C" int mmb_heads_fwd(const mmb_heads_args* a, void* stream) {
         float* xn = ws + w.xn + (size_t)m * B * H;
         float* an = ws + w.an + (size_t)m * B * H;
         linear(st, ws + w.temp, H, a->w_cpc[m], H, a->b_cpc[m], XH, H, B, H, H, ACT_NONE);
-        normalize_rows_kernel<<<B, 256, 0, st>>>(XH, an, ws + w.na + (size_t)m * B, H);
-        normalize_rows_kernel<<<B, 256, 0, st>>>(ws + w.P + (size_t)m * B * H, xn, ws + w.nx + (size_t)m * B, H);
-        cpc_rows_kernel<<<B, 256, B * sizeof(float), st>>>(xn, an, ws + w.Sm + (size_t)m * B * B, ws + w.nce, B, H);
+        launch_pdl(normalize_rows_kernel, dim3(B), dim3(256), (size_t)(0), st, XH, an, ws + w.na + (size_t)m * B, H);
+        launch_pdl(normalize_rows_kernel, dim3(B), dim3(256), (size_t)(0), st, ws + w.P + (size_t)m * B * H, xn, ws + w.nx + (size_t)m * B, H);
+        launch_pdl(cpc_rows_kernel, dim3(B), dim3(256), (size_t)(B * sizeof(float)), st, xn, an, ws + w.Sm + (size_t)m * B * B, ws + w.nce, B, H);
     }
     LossParams lp = loss_params(a, ws, w);
-    final_losses_kernel<<<1, 256, 0, st>>>(lp);
+    launch_pdl(final_losses_kernel, dim3(1), dim3(256), (size_t)(0), st, lp);
     // user-visible score outputs
     if (a->rel_out) MMB_CUDA(cudaMemcpyAsync(a->rel_out, ws + w.rel, 2 * B * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (a->align_out) MMB_CUDA(cudaMemcpyAsync(a->align_out, ws + w.al, 4 * B * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -568,7 +602,7 @@ extern "C" int mmb_heads_bwd(const mmb_heads_args* a, void* stream) {
 
     MMB_CUDA(cudaMemsetAsync(ws + w.dP, 0, (size_t)R * H * sizeof(float), st));
     MMB_CUDA(cudaMemsetAsync(ws + w.dX0, 0, (size_t)R * H * sizeof(float), st));
-    final_losses_bwd_kernel<<<1, 256, 0, st>>>(lp);
+    launch_pdl(final_losses_bwd_kernel, dim3(1), dim3(256), (size_t)(0), st, lp);
     // classifier1_2
     dx(st, ws + w.dlogit, 1, a->w_c12, H, ws + w.dtemp, H, B, 1, H, 0);
     dw(st, ws + w.dlogit, 1, ws + w.temp, H, a->g_w_c12, H, a->g_b_c12, B, 1, H);
@@ -578,11 +612,11 @@ extern "C" int mmb_heads_bwd(const mmb_heads_args* a, void* stream) {
         float* Sm = ws + w.Sm + (size_t)m * B * B;
         const float* xn = ws + w.xn + (size_t)m * B * H;
         const float* an = ws + w.an + (size_t)m * B * H;
-        cpc_dg_kernel<<<(B * B + 255) / 256, 256, 0, st>>>(Sm, a->gscale, a->beta, B);          // Sm <- dG
-        bb_matmul_kernel<<<B, 256, B * sizeof(float), st>>>(Sm, an, ws + w.dxn, B, H, 0);                          // dXn = dG An
-        bb_matmul_kernel<<<B, 256, B * sizeof(float), st>>>(Sm, xn, ws + w.dan, B, H, 1);                          // dAn = dG^T Xn
-        normalize_bwd_kernel<<<B, 256, 0, st>>>(xn, ws + w.dxn, ws + w.nx + (size_t)m * B, ws + w.dP + (size_t)m * B * H, H, 1);
-        normalize_bwd_kernel<<<B, 256, 0, st>>>(an, ws + w.dan, ws + w.na + (size_t)m * B, ws + w.dXH, H, 0);
+        launch_pdl(cpc_dg_kernel, dim3((B * B + 255) / 256), dim3(256), (size_t)(0), st, Sm, a->gscale, a->beta, B);          // Sm <- dG
+        launch_pdl(bb_matmul_kernel, dim3(B), dim3(256), (size_t)(B * sizeof(float)), st, Sm, an, ws + w.dxn, B, H, 0);                          // dXn = dG An
+        launch_pdl(bb_matmul_kernel, dim3(B), dim3(256), (size_t)(B * sizeof(float)), st, Sm, xn, ws + w.dan, B, H, 1);                          // dAn = dG^T Xn
+        launch_pdl(normalize_bwd_kernel, dim3(B), dim3(256), (size_t)(0), st, xn, ws + w.dxn, ws + w.nx + (size_t)m * B, ws + w.dP + (size_t)m * B * H, H, 1);
+        launch_pdl(normalize_bwd_kernel, dim3(B), dim3(256), (size_t)(0), st, an, ws + w.dan, ws + w.na + (size_t)m * B, ws + w.dXH, H, 0);
         dx(st, ws + w.dXH, H, a->w_cpc[m], H, ws + w.dtemp, H, B, H, H, 1);
         dw(st, ws + w.dXH, H, ws + w.temp, H, a->g_w_cpc[m], H, a->g_b_cpc[m], B, H, H);
     }
@@ -590,20 +624,20 @@ extern "C" int mmb_heads_bwd(const mmb_heads_args* a, void* stream) {
     dx(st, ws + w.dtemp, H, a->w_c11, 3 * H, ws + w.dPC, 3 * H, B, H, 3 * H, 0);
     dw(st, ws + w.dtemp, H, ws + w.PC, 3 * H, a->g_w_c11, 3 * H, a->g_b_c11, B, H, 3 * H);
     // score scaling, v_m, relu
-    score_scale_bwd_kernel<<<R, 256, 0, st>>>(ws + w.dPC, ws + w.P, ws + w.U, ws + w.s, vp, ws + w.dP, ws + w.dA, B, H);
+    launch_pdl(score_scale_bwd_kernel, dim3(R), dim3(256), (size_t)(0), st, ws + w.dPC, ws + w.P, ws + w.U, ws + w.s, vp, ws + w.dP, ws + w.dA, B, H);
     // attn Linear on [P, P]
     dx(st, ws + w.dA, H, a->w_attn, 2 * H, ws + w.dPP, 2 * H, R, H, 2 * H, 0);
     dw(st, ws + w.dA, H, ws + w.PP, 2 * H, a->g_w_attn, 2 * H, a->g_b_attn, R, H, 2 * H);
-    fold_dup_grad_kernel<<<R, 256, 0, st>>>(ws + w.dPP, ws + w.dP, R, H);
+    launch_pdl(fold_dup_grad_kernel, dim3(R), dim3(256), (size_t)(0), st, ws + w.dPP, ws + w.dP, R, H);
     // pooler: P = tanh(X0 Wp^T + bp)
-    tanh_bwd_kernel<<<(R * H + 255) / 256, 256, 0, st>>>(ws + w.dP, ws + w.P, R * H);
+    launch_pdl(tanh_bwd_kernel, dim3((R * H + 255) / 256), dim3(256), (size_t)(0), st, ws + w.dP, ws + w.P, R * H);
     dx(st, ws + w.dP, H, a->w_pooler, H, ws + w.dX0, H, R, H, H, 1);
     dw(st, ws + w.dP, H, ws + w.X0, H, a->g_w_pooler, H, a->g_b_pooler, R, H, H);
     // align on seq[:,0] of the two joint passes
     dx(st, ws + w.dal, 2, a->w_align, H, ws + w.dX0 + (size_t)B * H, H, 2 * B, 2, H, 1);
     dw(st, ws + w.dal, 2, ws + w.X0 + (size_t)B * H, H, a->g_w_align, H, a->g_b_align, 2 * B, 2, H);
     // add into the gradient of the encoder output at the [CLS] rows
-    scatter_cls_grad_kernel<<<R, 256, 0, st>>>(ws + w.dX0, a->cu_seqlens, (__nv_bfloat16*)a->dseq_out, R, H);
+    launch_pdl(scatter_cls_grad_kernel, dim3(R), dim3(256), (size_t)(0), st, ws + w.dX0, a->cu_seqlens, (__nv_bfloat16*)a->dseq_out, R, H);
     return check_launch("heads_bwd", 36 + 8);
 }
 
@@ -613,7 +647,7 @@ extern "C" int mmb_linear_f32(const mmb_linear_f32_args* a, void* stream) {
     MMB_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->ldx >= a->K && a->ldw >= a->K && a->ldy >= a->N, "linear_f32: bad shape");
     MMB_REQUIRE(a->act >= MMB_ACT_NONE && a->act <= MMB_ACT_GELU, "linear_f32: bad activation %d", a->act);
     dim3 g((a->N + kSgT - 1) / kSgT, (a->M + kSgT - 1) / kSgT);
-    sgemm64_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(a->X, (int)a->ldx, 1, a->W, 1, (int)a->ldw, a->Y, (int)a->ldy, a->bias,
+    launch_pdl(sgemm64_kernel, dim3(g), dim3(256), (size_t)(0), (cudaStream_t)stream, a->X, (int)a->ldx, 1, a->W, 1, (int)a->ldw, a->Y, (int)a->ldy, a->bias,
                                                        a->act, a->M, a->N, a->K, 0);
     return check_launch("sgemm64_kernel");
 }

@@ -28,6 +28,8 @@ drln_fwd_kernel(const void* __restrict__ y_, const float* __restrict__ res,
                 const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                 float* __restrict__ out_f32, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int H, float eps, uint32_t thresh,
                 float inv_keep, uint64_t seed, uint32_t stream) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nw = gridDim.x * kLnWarps;
     for (int row = blockIdx.x * kLnWarps + warp; row < M; row += nw) {
@@ -89,6 +91,8 @@ drln_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ 
                 __nv_bfloat16* __restrict__ d_y, float* __restrict__ d_res, float* __restrict__ dgamma,
                 float* __restrict__ dbeta, float* __restrict__ dbias, const __nv_bfloat16* __restrict__ gelu_aux, int M,
                 int H, uint32_t thresh, float inv_keep, uint64_t seed, uint32_t stream) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     extern __shared__ __align__(16) float smem[];   // [kLnBwdWarps][3][H]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nw = gridDim.x * kLnBwdWarps;
@@ -229,6 +233,8 @@ drln_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ 
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, float* __restrict__ out, int M, int N, int64_t ld,
                    int rows_per_cta) {
+    pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
     __shared__ float red[8][32 * 8 + 1];
     const int cg = threadIdx.x & 31;  // column group within the CTA's 256-column strip
     const int rr = threadIdx.x >> 5;  // row lane 0..7
@@ -280,12 +286,12 @@ extern "C" int mmb_dropout_residual_ln_fwd(const mmb_drln_fwd_args* a, void* str
     const float inv_keep = dropout_inv_keep(a->p_drop);
     const int grid = min((a->M + kLnWarps - 1) / kLnWarps, num_sms() * 4);
     if (a->y_f32) {
-        MMB_DISPATCH_NCH(a->H, (drln_fwd_kernel<NCH, true><<<grid, kLnWarps * 32, 0, (cudaStream_t)stream>>>(
+        MMB_DISPATCH_NCH(a->H, (launch_pdl(drln_fwd_kernel<NCH, true>, dim3(grid), dim3(kLnWarps * 32), (size_t)(0), (cudaStream_t)stream, 
                                    a->y, a->res, a->gamma, a->beta, (__nv_bfloat16*)a->out, a->out_f32, a->mean, a->rstd, a->M,
                                    a->H, a->eps, thresh, inv_keep, a->seed, a->rng_stream)));
         return check_launch("drln_fwd_kernel<f32>");
     }
-    MMB_DISPATCH_NCH(a->H, (drln_fwd_kernel<NCH><<<grid, kLnWarps * 32, 0, (cudaStream_t)stream>>>(
+    MMB_DISPATCH_NCH(a->H, (launch_pdl(drln_fwd_kernel<NCH>, dim3(grid), dim3(kLnWarps * 32), (size_t)(0), (cudaStream_t)stream, 
                                a->y, a->res, a->gamma, a->beta,
                                (__nv_bfloat16*)a->out, a->out_f32, a->mean, a->rstd, a->M, a->H, a->eps, thresh, inv_keep, a->seed,
                                a->rng_stream)));
@@ -303,7 +309,7 @@ extern "C" int mmb_dropout_residual_ln_bwd(const mmb_drln_bwd_args* a, void* str
     MMB_DISPATCH_NCH(a->H, {
         MMB_ENSURE_SMEM(100 * 1024, drln_bwd_kernel<NCH>);
     });
-    MMB_DISPATCH_NCH(a->H, (drln_bwd_kernel<NCH><<<grid, kLnBwdWarps * 32, smem, (cudaStream_t)stream>>>(
+    MMB_DISPATCH_NCH(a->H, (launch_pdl(drln_bwd_kernel<NCH>, dim3(grid), dim3(kLnBwdWarps * 32), (size_t)(smem), (cudaStream_t)stream, 
                                (const __nv_bfloat16*)a->g1, a->g2, (const __nv_bfloat16*)a->y,
                                a->res, a->mean, a->rstd, a->gamma, (__nv_bfloat16*)a->d_y,
                                a->d_res, a->dgamma, a->dbeta, a->dbias,
@@ -321,7 +327,7 @@ extern "C" int mmb_colsum_bf16(const mmb_colsum_args* a, void* stream) {
     if (ysplit < 1) ysplit = 1;
     const int rows_per_cta = (a->M + ysplit - 1) / ysplit;
     dim3 grid(strips, (a->M + rows_per_cta - 1) / rows_per_cta);
-    colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a->X, a->out, a->M, a->N, a->ld,
+    launch_pdl(colsum_bf16_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)a->X, a->out, a->M, a->N, a->ld,
                                                               rows_per_cta);
     return check_launch("colsum_bf16_kernel");
 }

@@ -29,6 +29,15 @@ int check_launch(const char* what, int kernels) {
     return MMB_OK;
 }
 
+int pdl_mode() {
+    static const int mode = [] {
+        const char* e = getenv("MMB_PDL");
+        const int m = e != nullptr ? atoi(e) : 0;      // default off: measured no gain on this path
+        return m < 0 ? 0 : (m > 2 ? 2 : m);
+    }();
+    return mode;
+}
+
 int num_sms() {
     static int n = 0;
     if (n == 0) {

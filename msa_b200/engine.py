@@ -90,9 +90,18 @@ class Plan:
         # fp32 copies of the residual stream (see csrc/ln.cu: precision note); the last layer's is never read
         self.x32 = [buf(M, H, dtype=F32) for _ in range(N if training else 2)]
         self.layers = []
+        # Forward attention skips the query tiles that lie entirely behind kv_end (padding rows nothing observable reads)
+        # once the schedule has verified the zero-gradient-tail premise: training with the fused cross entropy only — with
+        # materialised logits pred_t / pred_v / pred_s expose those positions.  MMB_ATTN_FWD_QSKIP=0 for A/B runs.
+        self.attn_fwd_skip = (training and not self.materialize_logits and self.attn_work is not None and
+                              os.environ.get("MMB_ATTN_QSKIP", "1") != "0" and os.environ.get("MMB_ATTN_FWD_QSKIP", "1") != "0")
+
+        def zbuf(*shape, dtype=BF16):      # rows a skipped tile never writes are still GEMM operands: finite from the start
+            return torch.zeros(*shape, device=dev, dtype=dtype) if self.attn_fwd_skip else buf(*shape, dtype=dtype)
+
         for _ in range(nsets):
             self.layers.append(dict(
-                qkv=buf(M, 3 * H), ctx=buf(M, H), lse=buf(nh, M, dtype=F32), y1=buf(M, H), a=buf(M, H),
+                qkv=buf(M, 3 * H), ctx=zbuf(M, H), lse=zbuf(nh, M, dtype=F32), y1=buf(M, H), a=buf(M, H),
                 a32=buf(M, H, dtype=F32),
                 m1=buf(M, dtype=F32), r1=buf(M, dtype=F32), u=buf(M, I), hg=buf(M, I), y2=buf(M, H),
                 m2=buf(M, dtype=F32), r2=buf(M, dtype=F32)))
@@ -201,7 +210,8 @@ class Plan:
             bqkv = st.span(pre + "attention.self.query.bias", pre + "attention.self.value.bias")
             self._gemm(f, xin, wqkv, L["qkv"], M, 3 * H, H, bias=bqkv)
             a = capi.attn_args(L["qkv"], L["ctx"], L["lse"], self.keybias, self.cu, H, self.nh, self.max_S,
-                               p_drop=self.p_attn, rng_stream=(l << 8) | ST_ATTN, kv_end=self.kv_end, work=self.attn_work)
+                               p_drop=self.p_attn, rng_stream=(l << 8) | ST_ATTN, kv_end=self.kv_end, work=self.attn_work,
+                               flags=8 if self.attn_fwd_skip else 0)
             L["attn_args"] = a
             self._seeded.append(a)
             f.append((self._fn("attn_fwd"), a))

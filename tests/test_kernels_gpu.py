@@ -505,3 +505,63 @@ def test_attention_backward_skips_the_zero_gradient_query_tail_exactly(p_drop):
     assert (int(skip[0, 2]) >> 30) == 0
     dense = _bf(torch.randn(rows, H, device="cuda"))
     assert torch.equal(run(plain, dense), run(skip, dense))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_attention_forward_leaves_only_fully_masked_query_tiles_unwritten(p_drop):
+    """mmb_attn_args.flags bit 3 (include/mmbert_sm100.h): with the zero-gradient-tail bit of the schedule set, the forward
+    skips exactly the 128-query tiles that start at or behind kv_end.  Every row before ceil(kv_end / 128) * 128 must be
+    bit-identical to the full forward (context and LSE), the skipped rows must keep their previous contents, the backward
+    (whose upstream gradient is zero behind kv_end) must be bit-identical, and without the schedule's bit the flag is inert."""
+    from msa_b200 import capi
+    g = torch.Generator().manual_seed(28)
+    nh = 12
+    lens = torch.randint(1, 551, (40,), generator=g).tolist() + [550, 40, 300, 129, 550, 550]
+    valid = [int(torch.randint(1, s + 1, (1,), generator=g)) for s in lens[:-6]] + [131, 0, 300, 128, 64, 1]
+    H, rows = nh * 64, sum(lens)
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    torch.manual_seed(29)
+    qkv = _bf(torch.randn(rows, 3 * H, device="cuda"))
+    keybias = torch.zeros(rows, device="cuda")
+    dctx = _bf(torch.randn(rows, H, device="cuda"))
+    row_label = torch.full((rows,), -100, device="cuda", dtype=torch.int32)
+    written = torch.ones(rows, dtype=torch.bool)
+    for i, (s, v) in enumerate(zip(lens, valid)):
+        keybias[cu[i] + v:cu[i] + s] = -10000.0
+        if v > 0:
+            dctx[cu[i] + v:cu[i] + s] = 0
+            row_label[cu[i] + int(torch.randint(0, v, (1,), generator=g))] = 5
+            written[cu[i] + (v + 127) // 128 * 128:cu[i] + s] = False
+    assert 0.2 < float((~written).float().mean()) < 0.8
+    kv_end = torch.tensor(valid, device="cuda", dtype=torch.int32)
+    cu_t = torch.tensor(cu, device="cuda", dtype=torch.int32)
+    written = written.cuda()
+
+    def run(wl, flags):
+        ctx = torch.full((rows, H), 3.0, device="cuda", dtype=torch.bfloat16)
+        lse = torch.full((nh, rows), 5.0, device="cuda")
+        dqkv = torch.full((rows, 3 * H), 7.0, device="cuda", dtype=torch.bfloat16)
+        bwd_ws = capi.attn_bwd_workspace(rows, nh, "cuda")
+        a = capi.attn_args(qkv, ctx, lse, keybias, cu_t, H, nh, max(lens), dctx=dctx, dqkv=dqkv, bwd_ws=bwd_ws,
+                           kv_end=kv_end, p_drop=p_drop, seed=4, rng_stream=1, work=wl, flags=flags)
+        capi.call("attn_fwd", a)
+        capi.call("attn_bwd", a)
+        return ctx.float(), lse, dqkv.float()
+
+    plain = capi.attn_schedule_buffer(len(lens), nh, max(lens), "cuda")
+    capi.call("attn_schedule", capi.attn_schedule_args(cu_t, kv_end, plain, nh, max(lens)))
+    skip = capi.attn_schedule_buffer(len(lens), nh, max(lens), "cuda")
+    capi.call("attn_schedule", capi.attn_schedule_args(cu_t, kv_end, skip, nh, max(lens), row_label=row_label))
+    assert (int(skip[0, 2]) >> 30) == 1
+    ctx0, lse0, dq0 = run(skip, 0)
+    ctx1, lse1, dq1 = run(skip, 8)
+    assert torch.equal(ctx0[written], ctx1[written]) and torch.equal(lse0[:, written], lse1[:, written])
+    assert bool((ctx1[~written] == 3.0).all()) and bool((lse1[:, ~written] == 5.0).all())
+    assert bool((ctx0[~written] != 3.0).any())
+    assert torch.isfinite(dq1).all() and torch.equal(dq0, dq1)
+    # without the schedule's verdict (no row labels given) the flag changes nothing
+    ctx2, lse2, dq2 = run(plain, 8)
+    assert torch.equal(ctx0, ctx2) and torch.equal(lse0, lse2) and torch.equal(dq0, dq2)

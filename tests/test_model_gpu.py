@@ -294,6 +294,50 @@ def test_fused_cross_entropy_tracks_changing_labels_and_matches_the_materialised
             assert rel_err(p.grad, gm[n].grad, floor=1e-6) < 1e-2, (seed, n)
 
 
+def test_forward_attention_tail_skip_changes_nothing_observable(monkeypatch):
+    """Training with the fused cross entropy skips the forward attention of the 128-query tiles that lie entirely behind
+    kv_end (mmb_attn_args.flags bit 3; padding rows that no loss, no head and no unmasked key ever reads).  Two models on
+    the same weights, one built with MMB_ATTN_FWD_QSKIP=0: over three different batches through the SAME plans (so the
+    skipped rows hold stale values of the previous batch) every returned value and every gradient agrees to the order of
+    the fp32 atomic reductions (loss sums, split-K) — the kernel-level test checks the attention output bit for bit."""
+    ocfg = O.Cfg(hidden_size=128, num_hidden_layers=3, num_attention_heads=2, intermediate_size=256, vocab_size=1000,
+                 max_position_embeddings=64)
+    sd = seeded_state_dict(ocfg, "mosei", seed=5, std=0.05)
+    monkeypatch.setenv("MMB_ATTN_FWD_QSKIP", "0")
+    m_full = _build(ocfg, "mosei", sd, fused=True).train()
+    batches = [synth.tree_to(synth.make_batch(6, 16, 400, 300, 35, 74, vocab_size=1000, seed=s, min_len=4), "cuda") for s in (1, 2, 3)]
+    m_full(**batches[0])
+    monkeypatch.setenv("MMB_ATTN_FWD_QSKIP", "1")
+    m_skip = _build(ocfg, "mosei", sd, fused=True).train()
+    m_skip(**batches[0])
+    plans = [next(iter(m._plans.values())) if hasattr(m, "_plans") else None for m in (m_full, m_skip)]
+    if plans[0] is not None:
+        assert not plans[0].attn_fwd_skip and plans[1].attn_fwd_skip
+    for batch in batches:
+        for m in (m_full, m_skip):
+            for p in m.parameters():
+                p.grad = None
+        o0, l0 = m_full(**batch)
+        o1, l1 = m_skip(**batch)
+        o0[0].backward()
+        o1[0].backward()
+        for a, b in zip(o0, o1):
+            assert (a is None) == (b is None)
+            if a is not None:
+                assert torch.isfinite(b).all() and rel_err(b.detach().float(), a.detach().float(), floor=1e-3) < 1e-5
+        assert rel_err(l1.detach(), l0.detach(), floor=1e-3) < 1e-5
+        g0 = dict(m_full.named_parameters())
+        for n, p in m_skip.named_parameters():
+            if p.grad is None:
+                assert g0[n].grad is None
+                continue
+            assert torch.isfinite(p.grad).all(), n
+            if n.endswith("attention.self.key.bias"):      # identically zero in exact arithmetic
+                assert float((p.grad - g0[n].grad).abs().max()) < 1e-4, n
+                continue
+            assert rel_err(p.grad, g0[n].grad, floor=1e-6) < 1e-4, n
+
+
 def test_out_of_range_label_or_token_id_poisons_the_loss():
     """torch's CrossEntropyLoss / nn.Embedding device-assert on an index outside the vocabulary; this path counts them on
     the device (no host sync), reads nothing out of bounds and returns a NaN joint loss."""
