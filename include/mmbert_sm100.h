@@ -27,10 +27,12 @@
 extern "C" {
 #endif
 
-#define MMB_VERSION 203 /* round 2; 200: mmb_pack_args.mask_frame_stride; 201: MMB_EPI_CE_STATS, mmb_gemm_args.aux2,
+#define MMB_VERSION 204 /* round 2; 200: mmb_pack_args.mask_frame_stride; 201: MMB_EPI_CE_STATS, mmb_gemm_args.aux2,
                            mmb_pack_args.row_label / vocab, mmb_ce_sparse_*, mmb_embed_args.err_count;
                            202: mmb_attn_schedule_args.row_label (zero-gradient query tail skipped by the backward);
-                           203: mmb_gemm_args.colsum */
+                           203: mmb_gemm_args.colsum;
+                           204: mmb_attn_args.flags bit 3, row lists (mmb_attn_schedule_args.row_list and the row_list
+                           members of the row kernels) */
 
 enum mmb_status {
     MMB_OK = 0,
@@ -135,6 +137,8 @@ typedef struct mmb_drln_fwd_args {
     uint64_t seed;
     uint32_t rng_stream;
     int32_t y_f32; /* fp32 validation path: y is [M,H] f32 and out may be NULL (only out_f32 is written) */
+    const int32_t* row_list; /* NULL, or mmb_attn_schedule's row list: only its live rows are computed, every other row of
+                                out / out_f32 / mean / rstd keeps its previous contents (see mmb_attn_schedule_args) */
 } mmb_drln_fwd_args;
 int mmb_dropout_residual_ln_fwd(const mmb_drln_fwd_args* a, void* stream);
 
@@ -162,6 +166,8 @@ typedef struct mmb_drln_bwd_args {
     float p_drop;
     uint64_t seed;
     uint32_t rng_stream;
+    const int32_t* row_list; /* NULL, or mmb_attn_schedule's row list: the live rows are computed, d_y / d_res of every
+                                other row are set to zero without reading anything (their gradient is exactly zero) */
 } mmb_drln_bwd_args;
 int mmb_dropout_residual_ln_bwd(const mmb_drln_bwd_args* a, void* stream);
 
@@ -172,6 +178,7 @@ typedef struct mmb_colsum_args {
     float* out;    /* [N] f32, accumulated */
     int64_t ld;
     int32_t M, N;
+    const int32_t* row_list; /* NULL, or mmb_attn_schedule's row list: only the live rows are summed (the others are zero) */
 } mmb_colsum_args;
 int mmb_colsum_bf16(const mmb_colsum_args* a, void* stream);
 
@@ -216,6 +223,8 @@ typedef struct mmb_attn_args {
     const void* work;       /* NULL, or the work lists written by mmb_attn_schedule for the same cu_seqlens / kv_end /
                                nheads / max_seqlen: the persistent kernels then take their (sequence, head, tile) items
                                longest first instead of in index order (same results bit for bit; evens out the CTAs) */
+    const int32_t* row_list; /* NULL, or mmb_attn_schedule's row list: mmb_attn_bwd prepares its per-row records only for
+                                the rows the backward kernels read (live rows and the rest of their 128-row tile) */
 } mmb_attn_args;
 size_t mmb_attn_bwd_workspace_bytes(int total_rows, int nheads);
 int mmb_attn_fwd(const mmb_attn_args* a, void* stream);
@@ -246,6 +255,16 @@ typedef struct mmb_attn_schedule_args {
     void* work;                /* out: mmb_attn_schedule_bytes(...) bytes, 16-byte aligned */
     int32_t nseq, nheads, max_seqlen;
     const int32_t* row_label;  /* [rows] from mmb_pack_prepare, or NULL (no query-tail skipping) */
+    int32_t* row_list;         /* NULL, or out: int32 [4 + rows] — the packed rows in three groups,
+                                  [0] = n_live  rows before their sequence's kv_end,
+                                  [1] = n_tile  rows at or behind kv_end that share a 128-row attention tile with a live row,
+                                  [2] = rows, [3] = 1 if the zero-gradient-tail premise above holds (else every row is live),
+                                  [4 ..) = the live rows (ascending), then the tile rows, then the rest.
+                                  A row that is not live is padding: a masked key for every query of every layer whose
+                                  value reaches no loss and whose gradient is exactly zero.  The row kernels (LayerNorm
+                                  forward / backward, column sums, the attention backward's preparation) take the list to
+                                  leave those rows alone; nothing the model returns changes.  Buffers whose dead rows are
+                                  read by a GEMM must hold finite values (zero-initialised once). */
 } mmb_attn_schedule_args;
 size_t mmb_attn_schedule_bytes(int nseq, int nheads, int max_seqlen);
 int mmb_attn_schedule(const mmb_attn_schedule_args* a, void* stream);

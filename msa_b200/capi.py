@@ -165,10 +165,10 @@ def gemm(A, B, C, M, N, K, **kw):
     call("gemm", gemm_args(A, B, C, M, N, K, **kw))
 
 
-def drln_fwd_args(y, res, gamma, beta, out, mean, rstd, eps, p_drop=0.0, seed=0, rng_stream=0, out_f32=None):
+def drln_fwd_args(y, res, gamma, beta, out, mean, rstd, eps, p_drop=0.0, seed=0, rng_stream=0, out_f32=None, row_list=None):
     return fill(DrlnFwdArgs(), y=y, res=res, gamma=gamma, beta=beta, out=out, out_f32=out_f32, mean=mean, rstd=rstd,
                 M=y.shape[0],
-                H=y.shape[1], eps=eps, p_drop=p_drop, seed=seed, rng_stream=rng_stream)
+                H=y.shape[1], eps=eps, p_drop=p_drop, seed=seed, rng_stream=rng_stream, row_list=row_list)
 
 
 def drln_fwd(*a, **kw):
@@ -176,18 +176,18 @@ def drln_fwd(*a, **kw):
 
 
 def drln_bwd_args(g1, g2, y, res, mean, rstd, gamma, d_y, d_res, dgamma, dbeta, dbias, p_drop=0.0, seed=0,
-                  rng_stream=0):
+                  rng_stream=0, row_list=None):
     return fill(DrlnBwdArgs(), g1=g1, g2=g2, y=y, res=res, mean=mean, rstd=rstd, gamma=gamma, d_y=d_y, d_res=d_res,
                 dgamma=dgamma, dbeta=dbeta, dbias=dbias, M=y.shape[0], H=y.shape[1], p_drop=p_drop, seed=seed,
-                rng_stream=rng_stream)
+                rng_stream=rng_stream, row_list=row_list)
 
 
 def drln_bwd(*a, **kw):
     call("dropout_residual_ln_bwd", drln_bwd_args(*a, **kw))
 
 
-def colsum_args(X, out):
-    return fill(ColsumArgs(), X=X, out=out, ld=X.stride(0), M=X.shape[0], N=X.shape[1])
+def colsum_args(X, out, row_list=None):
+    return fill(ColsumArgs(), X=X, out=out, ld=X.stride(0), M=X.shape[0], N=X.shape[1], row_list=row_list)
 
 
 def colsum(X, out):
@@ -203,10 +203,11 @@ def attn_bwd_workspace(total_rows, nheads, device):
 
 
 def attn_args(qkv, ctx, lse, keybias, cu_seqlens, H, nheads, max_seqlen, dctx=None, dqkv=None, bwd_ws=None,
-              p_drop=0.0, seed=0, rng_stream=0, flags=0, kv_end=None, work=None):
+              p_drop=0.0, seed=0, rng_stream=0, flags=0, kv_end=None, work=None, row_list=None):
     return fill(AttnArgs(), qkv=qkv, ctx=ctx, lse=lse, keybias=keybias, cu_seqlens=cu_seqlens, dctx=dctx, dqkv=dqkv,
                 bwd_ws=bwd_ws, kv_end=kv_end, H=H, nheads=nheads, nseq=cu_seqlens.numel() - 1, max_seqlen=max_seqlen,
-                total_rows=qkv.shape[0], p_drop=p_drop, seed=seed, rng_stream=rng_stream, flags=flags, work=work)
+                total_rows=qkv.shape[0], p_drop=p_drop, seed=seed, rng_stream=rng_stream, flags=flags, work=work,
+                row_list=row_list)
 
 
 def attn_schedule_buffer(nseq, nheads, max_seqlen, device):
@@ -217,9 +218,9 @@ def attn_schedule_buffer(nseq, nheads, max_seqlen, device):
     return torch.empty(L.mmb_attn_schedule_bytes(nseq, nheads, max_seqlen) // 16, 4, device=device, dtype=torch.int32)
 
 
-def attn_schedule_args(cu_seqlens, kv_end, work, nheads, max_seqlen, row_label=None):
+def attn_schedule_args(cu_seqlens, kv_end, work, nheads, max_seqlen, row_label=None, row_list=None):
     return fill(AttnScheduleArgs(), cu_seqlens=cu_seqlens, kv_end=kv_end, work=work, nseq=cu_seqlens.numel() - 1,
-                nheads=nheads, max_seqlen=max_seqlen, row_label=row_label)
+                nheads=nheads, max_seqlen=max_seqlen, row_label=row_label, row_list=row_list)
 
 
 def cast_bf16(src, dst):

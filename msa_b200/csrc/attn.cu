@@ -35,14 +35,19 @@ int launch_attn_bwd_tc(const mmb_attn_args* a, cudaStream_t stream);          //
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dctx, const __nv_bfloat16* __restrict__ ctx,
                      const float* __restrict__ lse, const float* __restrict__ keybias, uint4* __restrict__ ws,
-                     int total_rows, int H, int nheads, int drop, uint64_t seed, uint32_t rng_stream) {
+                     int total_rows, int H, int nheads, int drop, uint64_t seed, uint32_t rng_stream,
+                     const int* __restrict__ row_list) {
     pdl_trigger();
     pdl_wait();
-    // one 8-lane group per (row, head): 8 lanes x 8 bf16 = 64
+    // one 8-lane group per (row, head): 8 lanes x 8 bf16 = 64; with a row list only the rows the backward kernels read
+    // (live rows and the rest of their 128-row tiles: the first n_live + n_tile entries)
     const int gidx = (blockIdx.x * 256 + threadIdx.x) >> 3;
     const int sub = threadIdx.x & 7;
-    const bool live = gidx < total_rows * nheads;
-    const int row = live ? gidx / nheads : 0, head = live ? gidx - row * nheads : 0;
+    const int nrows = row_list != nullptr ? __ldg(row_list) + __ldg(row_list + 1) : total_rows;
+    if ((blockIdx.x * 256) >> 3 >= nrows * nheads) return;                 // whole CTA beyond the list
+    const bool live = gidx < nrows * nheads;
+    const int li = live ? gidx / nheads : 0, head = live ? gidx - li * nheads : 0;
+    const int row = row_list != nullptr ? __ldg(row_list + 4 + li) : li;
     const int64_t off = (int64_t)row * H + head * kD + sub * 8;
     const uint4 a = *reinterpret_cast<const uint4*>(dctx + off);
     const uint4 b = *reinterpret_cast<const uint4*>(ctx + off);
@@ -78,7 +83,7 @@ constexpr int kSchedThreads = 1024;
 constexpr int kSchedMaxSeqs = 8192;
 __global__ void __launch_bounds__(kSchedThreads)
 attn_schedule_kernel(const int* __restrict__ cu, const int* __restrict__ kv_end, const int* __restrict__ row_label,
-                     int4* __restrict__ work, int nseq, int nheads, int cap) {
+                     int4* __restrict__ work, int nseq, int nheads, int cap, int* __restrict__ row_list) {
     pdl_trigger();
     pdl_wait();
     extern __shared__ int sm[];
@@ -149,6 +154,49 @@ attn_schedule_kernel(const int* __restrict__ cu, const int* __restrict__ kv_end,
         for (int t = 0; t < tkv; ++t) wkv[t] = make_int4(row0, S, e, (h << 16) | t);
         for (int t = tkv; t < tq; ++t) wz[t - tkv] = make_int4(row0, S, e, (h << 16) | t);
     }
+    if (row_list == nullptr) return;
+    // Row list (header: mmb_attn_schedule_args.row_list): live rows | rest of their 128-row tile | dead rows.  Without the
+    // verified premise every row is live.  The offset arrays of the work lists are dead by now and are reused.
+    __syncthreads();
+    int* off_live = ord_q;
+    int* off_tile = ord_kv;
+    int* off_dead = off_q;
+    __shared__ int tot[2];
+    if (tid == 0) {
+        int nl = 0, nt = 0, nd = 0;
+        for (int i = 0; i < nseq; ++i) {
+            const int S = len[i], e = qskip ? eff[i] : S;
+            const int te = min(S, (e + 127) / 128 * 128);
+            off_live[i] = nl;
+            off_tile[i] = nt;
+            off_dead[i] = nd;
+            nl += e;
+            nt += te - e;
+            nd += S - te;
+        }
+        tot[0] = nl;
+        tot[1] = nt;
+        row_list[0] = nl;
+        row_list[1] = nt;
+        row_list[2] = nl + nt + nd;
+        row_list[3] = qskip ? 1 : 0;
+    }
+    __syncthreads();
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        int* live = row_list + 4;
+        int* tile = live + tot[0];
+        int* dead = tile + tot[1];
+        for (int i = warp; i < nseq; i += kSchedThreads / 32) {
+            const int row0 = cu[i], S = len[i], e = qskip ? eff[i] : S;
+            const int te = min(S, (e + 127) / 128 * 128);
+            for (int j = lane; j < S; j += 32) {
+                if (j < e) live[off_live[i] + j] = row0 + j;
+                else if (j < te) tile[off_tile[i] + (j - e)] = row0 + j;
+                else dead[off_dead[i] + (j - te)] = row0 + j;
+            }
+        }
+    }
 }
 
 static int check_args(const mmb_attn_args* a) {
@@ -187,7 +235,7 @@ extern "C" int mmb_attn_schedule(const mmb_attn_schedule_args* a, void* stream) 
     if (smem > 48 * 1024)
         MMB_CUDA(cudaFuncSetAttribute(attn_schedule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     launch_pdl(attn_schedule_kernel, dim3(1), dim3(kSchedThreads), (size_t)smem, (cudaStream_t)stream, a->cu_seqlens, a->kv_end,
-               a->row_label, (int4*)a->work, a->nseq, a->nheads, (int)cap);
+               a->row_label, (int4*)a->work, a->nseq, a->nheads, (int)cap, a->row_list);
     return check_launch("attn_schedule_kernel");
 }
 
@@ -213,7 +261,7 @@ extern "C" int mmb_attn_bwd(const mmb_attn_args* a, void* stream) {
     const long long groups = (long long)a->total_rows * a->nheads;
     launch_pdl(attn_bwd_prep_kernel, dim3((unsigned)((groups * 8 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
                (const __nv_bfloat16*)a->dctx, (const __nv_bfloat16*)a->ctx, a->lse, a->keybias, (uint4*)a->bwd_ws, a->total_rows,
-               a->H, a->nheads, a->p_drop > 0.f ? 1 : 0, a->seed, a->rng_stream);
+               a->H, a->nheads, a->p_drop > 0.f ? 1 : 0, a->seed, a->rng_stream, a->row_list);
     rc = check_launch("attn_bwd_prep_kernel");
     if (rc != MMB_OK) return rc;
     return launch_attn_bwd_tc(a, (cudaStream_t)stream);

@@ -662,6 +662,7 @@ extern "C" int mmb_embed_bwd(const mmb_embed_args* a, void* stream) {
                 ca.ld = p.H;
                 ca.M = nrows;
                 ca.N = p.H;
+                ca.row_list = nullptr;
                 rc = mmb_colsum_bf16(&ca, st);
                 if (rc != MMB_OK) return rc;
                 continue;

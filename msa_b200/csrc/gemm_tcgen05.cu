@@ -57,7 +57,6 @@ struct GemmParams {
     int tma_store;  // CTA-pair kernel: bf16 outputs leave through cp.async.bulk.tensor stores (tmC / tmAux)
     int stages;     // CTA-pair kernel: depth of the operand ring (6, or 5 to make room for the column-sum array)
     float* colsum;  // CTA-pair kernel, 8 epilogue warps: [N] column sums of the bf16-rounded output, or null
-    int stage2;     // CTA-pair kernel, 8 epilogue warps: two staging tiles per warp (a store drains while the next tile is staged)
 };
 
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], int ncols_valid) {
@@ -344,10 +343,8 @@ __device__ __forceinline__ void bias_add_chunk(const GemmParams& p, float (&v)[3
 }
 
 // the staging tile may be rewritten once the TMA unit has read the previous store out of it (lane 0 issued it)
-// (pending = 1 with two staging tiles per warp: only the store issued before the last one must have been read)
-template <int kPending = 0>
 __device__ __forceinline__ void stage_acquire(int lane) {
-    if (lane == 0) ptx::bulk_wait_read<kPending>();
+    if (lane == 0) ptx::bulk_wait_read<0>();
     __syncwarp();
 }
 // 8-warp layout: this lane's 32 values -> columns [32 * half, 32 * half + 32) of its row in the 64-column tile
@@ -678,8 +675,8 @@ template <int kEpiWarps> struct Cfg2 {
     static constexpr int kMaxSmem = 227 * 1024;
     // [operand ring: stages x 32 KB][epilogue staging: kEpiWarps x 4 KB][barriers: 256 B][column sums: colsum_floats x 4]
     static int stages(bool colsum) { return (kEpiWarps == 16 || colsum) ? 5 : 6; }
-    static int smem_bytes(int stages, int colsum_floats, int stage2 = 0) {
-        return stages * (2 * 128 * BK * 2) + kEpiWarps * 4096 * (stage2 ? 2 : 1) + 256 + colsum_floats * 4 + 1024;
+    static int smem_bytes(int stages, int colsum_floats) {
+        return stages * (2 * 128 * BK * 2) + kEpiWarps * 4096 + 256 + colsum_floats * 4 + 1024;
     }
 };
 constexpr int k2ABytes = 128 * BK * 2;           // this CTA's half of the 256-row A tile
@@ -698,8 +695,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t smem_base = ptx::smem_u32(smem);
     // [operand ring][epilogue staging: k2EpiWarps x 4 KB, 1024-byte aligned (swizzled TMA-store boxes)][barriers]
-    const int kStagePerWarp = kStageBytesPerWarp * (p.stage2 ? 2 : 1);
-    const int kBarOff = k2Stages * k2StageBytes + k2EpiWarps * kStagePerWarp;
+    const int kBarOff = k2Stages * k2StageBytes + k2EpiWarps * kStageBytesPerWarp;
     const uint32_t bar_base = smem_base + kBarOff;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (k2Stages + s); };
@@ -901,8 +897,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int ew = warp - kEpiWarp0;
         const int quarter = warp & 3;
         const int half = ew >> 2;          // column group 0..3 of the tile
-        const uint32_t stage_buf = ptx::smem_u32(epi_stage) + ew * kStagePerWarp;
-        uint32_t stage_flip = 0;           // stage2: byte offset of the staging tile the next 64-column group uses (0 / 4096)
+        const uint32_t stage_buf = ptx::smem_u32(epi_stage) + ew * kStageBytesPerWarp;
         constexpr int kColsPerWarp = TN / (k2EpiWarps / 4);
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -980,11 +975,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                                 bias_add_chunk(p, v, col0);
                                 activate_chunk(p.epilogue, false, v, w);
                             }
-                            if (h == 0) {
-                                if (p.stage2) stage_acquire<1>(lane);
-                                else stage_acquire<0>(lane);
-                            }
-                            stage_row128(stage_buf + stage_flip, v, lane, h);
+                            if (h == 0) stage_acquire(lane);
+                            stage_row128(stage_buf, v, lane, h);
                         }
                         if (p.colsum != nullptr) {
                             // column sums of the staged (bf16-rounded) tile: lane l owns columns 2l, 2l+1 of the 64; rows
@@ -992,7 +984,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             __syncwarp();
                             const int nrow = min(32, p.M - row_base);
                             float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-                            const uint32_t wb = stage_buf + stage_flip + (uint32_t)((lane & 3) * 4);
+                            const uint32_t wb = stage_buf + (uint32_t)((lane & 3) * 4);
                             if (nrow == 32) {
 #pragma unroll
                                 for (int r = 0; r < 32; r += 4) {
@@ -1009,8 +1001,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             if (c < p.N) atomicAdd(colacc + c, t.x);
                             if (c + 1 < p.N) atomicAdd(colacc + c + 1, t.y);
                         }
-                        stage_release(&tmC, stage_buf + stage_flip, nullptr, 0, colg, row_base, lane);
-                        if (p.stage2) stage_flip ^= 4096u;
+                        stage_release(&tmC, stage_buf, nullptr, 0, colg, row_base, lane);
                     }
                 } else {
                     // 64-column strip = two 32-column boxes per stream (GELU epilogues: C and, in training, the aux stream)
@@ -1209,7 +1200,6 @@ static void fill_common(GemmParams& p, const mmb_gemm_args* a, int tile_m, int t
     p.tma_store = 0;
     p.stages = 0;
     p.colsum = nullptr;
-    p.stage2 = 0;
     p.dbg = a->dbg_flags;
     static const int lane_issue = [] {                       // MMB_GEMM_ISSUE=lane: single-lane MMA issue (A/B runs)
         const char* e = getenv("MMB_GEMM_ISSUE");
@@ -1287,6 +1277,7 @@ static int gemm_colsum_fallback(const mmb_gemm_args* a, cudaStream_t stream) {
     c.ld = a->ldc;
     c.M = a->M;
     c.N = a->N;
+    c.row_list = nullptr;
     return mmb_colsum_bf16(&c, stream);
 }
 
@@ -1341,13 +1332,6 @@ static int launch_gemm_2cta(const mmb_gemm_args* a, cudaStream_t stream) {
     const bool fused_colsum = a->colsum != nullptr && p.tma_store && !wide && (size_t)a->N * 4 <= 28 * 1024 &&
                               (a->epilogue != MMB_EPI_MUL_AUX_BF16 || a->N % 128 == 0) && !(a->dbg_flags & 48);
     p.colsum = fused_colsum ? a->colsum : nullptr;
-    // two staging tiles per epilogue warp (8-warp TMA-store epilogues): 64 KB instead of 32 KB, one operand stage fewer.
-    // MMB_GEMM_STAGE2=1 turns it on for every such GEMM, =2 only where the reduction is short (K <= 1024), 0 = off.
-    static const int stage2_env = [] {
-        const char* e = getenv("MMB_GEMM_STAGE2");
-        return e != nullptr ? atoi(e) : 0;
-    }();
-    p.stage2 = (!wide && p.tma_store && (stage2_env == 1 || (stage2_env == 2 && a->K <= 1024))) ? 1 : 0;
     if (wide) {
         p.stages = Cfg2<16>::stages(false);
         launch_pdl(gemm_tcgen05_2cta_kernel<16>, dim3(2 * clusters), dim3(Cfg2<16>::kThreads), Cfg2<16>::smem_bytes(p.stages, 0), stream,
@@ -1355,9 +1339,8 @@ static int launch_gemm_2cta(const mmb_gemm_args* a, cudaStream_t stream) {
     } else {
         p.stages = Cfg2<8>::stages(fused_colsum);
         if (!fused_colsum && (stages_env == 5 || stages_env == 6)) p.stages = stages_env;      // A/B runs
-        if (p.stage2) p.stages = fused_colsum ? 4 : 5;
         launch_pdl(gemm_tcgen05_2cta_kernel<8>, dim3(2 * clusters), dim3(Cfg2<8>::kThreads),
-                   Cfg2<8>::smem_bytes(p.stages, fused_colsum ? a->N : 0, p.stage2), stream, tmA, tmB, tmC, tmAux, p);
+                   Cfg2<8>::smem_bytes(p.stages, fused_colsum ? a->N : 0), stream, tmA, tmB, tmC, tmAux, p);
     }
     if (a->colsum != nullptr && !fused_colsum) {
         int rc2 = check_launch("gemm_tcgen05_2cta_kernel");

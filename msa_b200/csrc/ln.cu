@@ -27,12 +27,15 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 drln_fwd_kernel(const void* __restrict__ y_, const float* __restrict__ res,
                 const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                 float* __restrict__ out_f32, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int H, float eps, uint32_t thresh,
-                float inv_keep, uint64_t seed, uint32_t stream) {
+                float inv_keep, uint64_t seed, uint32_t stream, const int* __restrict__ row_list) {
     pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
     pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nw = gridDim.x * kLnWarps;
-    for (int row = blockIdx.x * kLnWarps + warp; row < M; row += nw) {
+    // row list (mmb_attn_schedule): only the live rows are computed; padding rows keep their previous contents
+    const int nrows = row_list != nullptr ? __ldg(row_list) : M;
+    for (int ri = blockIdx.x * kLnWarps + warp; ri < nrows; ri += nw) {
+        const int row = row_list != nullptr ? __ldg(row_list + 4 + ri) : ri;
         RowF<NCH> z;
         if (kYF32) row_load_f32<NCH, kFwdLd256>(z, reinterpret_cast<const float*>(y_) + (size_t)row * H, H, lane);
         else row_load_bf16(z, reinterpret_cast<const __nv_bfloat16*>(y_) + (size_t)row * H, H, lane);
@@ -90,7 +93,7 @@ drln_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ 
                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
                 __nv_bfloat16* __restrict__ d_y, float* __restrict__ d_res, float* __restrict__ dgamma,
                 float* __restrict__ dbeta, float* __restrict__ dbias, const __nv_bfloat16* __restrict__ gelu_aux, int M,
-                int H, uint32_t thresh, float inv_keep, uint64_t seed, uint32_t stream) {
+                int H, uint32_t thresh, float inv_keep, uint64_t seed, uint32_t stream, const int* __restrict__ row_list) {
     pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
     pdl_wait();
     extern __shared__ __align__(16) float smem[];   // [kLnBwdWarps][3][H]
@@ -102,7 +105,27 @@ drln_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ 
     for (int i = lane; i < 3 * H; i += 32) acc_g[i] = 0.f;
     __syncwarp();
     const bool drop = thresh != 0u;
-    for (int row = blockIdx.x * kLnBwdWarps + warp; row < M; row += nw) {
+    // row list (mmb_attn_schedule): the live rows are computed; the gradient of every other row is exactly zero and is
+    // written as such without reading anything (the wgrad / dgrad GEMMs read every row of d_y, the next LayerNorm
+    // backward every live row of d_res)
+    const int nrows = row_list != nullptr ? __ldg(row_list) : M;
+    if (row_list != nullptr) {
+        const int ndead = __ldg(row_list + 2) - nrows;
+        for (int ri = blockIdx.x * kLnBwdWarps + warp; ri < ndead; ri += nw) {
+            const int row = __ldg(row_list + 4 + nrows + ri);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const int e = (c * 32 + lane) * 8;
+                if (e < H) {
+                    *reinterpret_cast<uint4*>(d_y + (size_t)row * H + e) = make_uint4(0u, 0u, 0u, 0u);
+                    if (d_res != nullptr)
+                        stg256_f32(d_res + (size_t)row * H + e, make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f));
+                }
+            }
+        }
+    }
+    for (int ri = blockIdx.x * kLnBwdWarps + warp; ri < nrows; ri += nw) {
+        const int row = row_list != nullptr ? __ldg(row_list + 4 + ri) : ri;
         // every load of the row goes in flight before the first one is consumed (the kernel is latency-bound otherwise)
         RowRawB<NCH> y_raw, g1_raw;
         RowRawF<NCH> res_raw, g2_raw;
@@ -232,13 +255,20 @@ drln_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ 
 // out[n] += sum_m X[m, n]   (X bf16, row stride ld).  Each thread owns 8 adjacent columns.
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, float* __restrict__ out, int M, int N, int64_t ld,
-                   int rows_per_cta) {
+                   int rows_per_cta, const int* __restrict__ row_list) {
     pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
     pdl_wait();
     __shared__ float red[8][32 * 8 + 1];
     const int cg = threadIdx.x & 31;  // column group within the CTA's 256-column strip
     const int rr = threadIdx.x >> 5;  // row lane 0..7
     const int col0 = blockIdx.x * 256 + cg * 8;
+    // row list (mmb_attn_schedule): only the live rows are read (the others hold zeros); the grid was sized for M rows
+    const int* rl = row_list != nullptr ? row_list + 4 : nullptr;
+    if (rl != nullptr) {
+        M = __ldg(row_list);
+        rows_per_cta = ((M + (int)gridDim.y - 1) / (int)gridDim.y + 7) & ~7;
+    }
+    auto row_of = [&](int i) { return rl != nullptr ? __ldg(rl + i) : i; };
     const int r0 = blockIdx.y * rows_per_cta;
     const int r1 = min(M, r0 + rows_per_cta);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -247,7 +277,7 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, float* __restrict__ out,
         for (; r + 24 < r1; r += 32) {   // four independent 16-byte loads in flight per thread
             uint4 q[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(X + (size_t)(r + 8 * u) * ld + col0));
+            for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(X + (size_t)row_of(r + 8 * u) * ld + col0));
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const float2 a = unpack_bf16x2(q[u].x), b = unpack_bf16x2(q[u].y), c = unpack_bf16x2(q[u].z), d = unpack_bf16x2(q[u].w);
@@ -256,7 +286,7 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, float* __restrict__ out,
             }
         }
         for (; r < r1; r += 8) {
-            const uint4 q = __ldg(reinterpret_cast<const uint4*>(X + (size_t)r * ld + col0));
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(X + (size_t)row_of(r) * ld + col0));
             const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
             acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
             acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
@@ -288,13 +318,13 @@ extern "C" int mmb_dropout_residual_ln_fwd(const mmb_drln_fwd_args* a, void* str
     if (a->y_f32) {
         MMB_DISPATCH_NCH(a->H, (launch_pdl(drln_fwd_kernel<NCH, true>, dim3(grid), dim3(kLnWarps * 32), (size_t)(0), (cudaStream_t)stream, 
                                    a->y, a->res, a->gamma, a->beta, (__nv_bfloat16*)a->out, a->out_f32, a->mean, a->rstd, a->M,
-                                   a->H, a->eps, thresh, inv_keep, a->seed, a->rng_stream)));
+                                   a->H, a->eps, thresh, inv_keep, a->seed, a->rng_stream, a->row_list)));
         return check_launch("drln_fwd_kernel<f32>");
     }
     MMB_DISPATCH_NCH(a->H, (launch_pdl(drln_fwd_kernel<NCH>, dim3(grid), dim3(kLnWarps * 32), (size_t)(0), (cudaStream_t)stream, 
                                a->y, a->res, a->gamma, a->beta,
                                (__nv_bfloat16*)a->out, a->out_f32, a->mean, a->rstd, a->M, a->H, a->eps, thresh, inv_keep, a->seed,
-                               a->rng_stream)));
+                               a->rng_stream, a->row_list)));
     return check_launch("drln_fwd_kernel");
 }
 
@@ -313,7 +343,7 @@ extern "C" int mmb_dropout_residual_ln_bwd(const mmb_drln_bwd_args* a, void* str
                                (const __nv_bfloat16*)a->g1, a->g2, (const __nv_bfloat16*)a->y,
                                a->res, a->mean, a->rstd, a->gamma, (__nv_bfloat16*)a->d_y,
                                a->d_res, a->dgamma, a->dbeta, a->dbias,
-                               (const __nv_bfloat16*)a->gelu_aux, a->M, a->H, thresh, inv_keep, a->seed, a->rng_stream)));
+                               (const __nv_bfloat16*)a->gelu_aux, a->M, a->H, thresh, inv_keep, a->seed, a->rng_stream, a->row_list)));
     return check_launch("drln_bwd_kernel");
 }
 
@@ -328,6 +358,6 @@ extern "C" int mmb_colsum_bf16(const mmb_colsum_args* a, void* stream) {
     const int rows_per_cta = (a->M + ysplit - 1) / ysplit;
     dim3 grid(strips, (a->M + rows_per_cta - 1) / rows_per_cta);
     launch_pdl(colsum_bf16_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)a->X, a->out, a->M, a->N, a->ld,
-                                                              rows_per_cta);
+                                                              rows_per_cta, a->row_list);
     return check_launch("colsum_bf16_kernel");
 }

@@ -86,23 +86,31 @@ class Plan:
             self.attn_work = capi.attn_schedule_buffer(3 * B, self.nh, self.max_S, dev)
         # ---- activations (kept for backward when training; one reused set in eval)
         nsets = N if training else 1
-        self.x = [buf(M, H) for _ in range(N + 1)] if training else [buf(M, H), buf(M, H)]
-        # fp32 copies of the residual stream (see csrc/ln.cu: precision note); the last layer's is never read
-        self.x32 = [buf(M, H, dtype=F32) for _ in range(N if training else 2)]
         self.layers = []
         # Forward attention skips the query tiles that lie entirely behind kv_end (padding rows nothing observable reads)
-        # once the schedule has verified the zero-gradient-tail premise: training with the fused cross entropy only — with
-        # materialised logits pred_t / pred_v / pred_s expose those positions.  MMB_ATTN_FWD_QSKIP=0 for A/B runs.
-        self.attn_fwd_skip = (training and not self.materialize_logits and self.attn_work is not None and
+        # once the schedule has verified that no row behind kv_end carries a label: plans with the fused cross entropy only,
+        # training or not — with materialised logits pred_t / pred_v / pred_s expose those positions.
+        # MMB_ATTN_FWD_QSKIP=0 for A/B runs.
+        self.attn_fwd_skip = (not self.materialize_logits and self.attn_work is not None and
                               os.environ.get("MMB_ATTN_QSKIP", "1") != "0" and os.environ.get("MMB_ATTN_FWD_QSKIP", "1") != "0")
+
+        # The row kernels (LayerNorm forward / backward, column sums, the attention backward's preparation) take the
+        # schedule's row list under the same premise and leave padding rows alone (include/mmbert_sm100.h:
+        # mmb_attn_schedule_args.row_list).  MMB_ROW_SKIP=0 for A/B runs.
+        self.row_list = None
+        if self.attn_fwd_skip and os.environ.get("MMB_ROW_SKIP", "1") != "0":
+            self.row_list = torch.zeros(4 + M, device=dev, dtype=I32)
 
         def zbuf(*shape, dtype=BF16):      # rows a skipped tile never writes are still GEMM operands: finite from the start
             return torch.zeros(*shape, device=dev, dtype=dtype) if self.attn_fwd_skip else buf(*shape, dtype=dtype)
 
+        self.x = [zbuf(M, H) for _ in range(N + 1)] if training else [zbuf(M, H), zbuf(M, H)]
+        # fp32 copies of the residual stream (see csrc/ln.cu: precision note); the last layer's is never read
+        self.x32 = [zbuf(M, H, dtype=F32) for _ in range(N if training else 2)]
         for _ in range(nsets):
             self.layers.append(dict(
-                qkv=buf(M, 3 * H), ctx=zbuf(M, H), lse=zbuf(nh, M, dtype=F32), y1=buf(M, H), a=buf(M, H),
-                a32=buf(M, H, dtype=F32),
+                qkv=buf(M, 3 * H), ctx=zbuf(M, H), lse=zbuf(nh, M, dtype=F32), y1=buf(M, H), a=zbuf(M, H),
+                a32=zbuf(M, H, dtype=F32),
                 m1=buf(M, dtype=F32), r1=buf(M, dtype=F32), u=buf(M, I), hg=buf(M, I), y2=buf(M, H),
                 m2=buf(M, dtype=F32), r2=buf(M, dtype=F32)))
         self.e_m1, self.e_r1, self.e_m2, self.e_r2 = (buf(M, dtype=F32) for _ in range(4))
@@ -111,7 +119,7 @@ class Plan:
         ldf = [(d + 7) // 8 * 8 for d in (self.Dv, self.Da)]
         self.frames_bf16 = [buf(max(B * L, 1), l8) for L, l8 in zip((Lv, La), ldf)] if training else [None, None]
         self.gw_pad = [buf(H, l8, dtype=F32) for l8 in ldf] if training else [None, None]
-        self.t_u, self.t_g, self.t_ln = buf(M, H), buf(M, H), buf(M, H)
+        self.t_u, self.t_g, self.t_ln = buf(M, H), buf(M, H), zbuf(M, H)
         self.t_m, self.t_r = buf(M, dtype=F32), buf(M, dtype=F32)
         self.logits = buf(M, self.Vp) if self.materialize_logits else None
         self.ce_stats = None
@@ -171,9 +179,12 @@ class Plan:
         if self.attn_work is not None:
             # row labels: lets the backward skip the query rows behind kv_end once it is verified that none is labelled
             # (their upstream gradient is exactly zero; include/mmbert_sm100.h).  MMB_ATTN_QSKIP=0 for A/B runs.
-            qskip = self.training and os.environ.get("MMB_ATTN_QSKIP", "1") != "0"
+            qskip = (self.training or self.attn_fwd_skip) and os.environ.get("MMB_ATTN_QSKIP", "1") != "0"
             self.sched_args = capi.attn_schedule_args(self.cu, self.kv_end, self.attn_work, self.nh, self.max_S,
-                                                      row_label=self.row_label if qskip else None)
+                                                      row_label=self.row_label if qskip else None,
+                                                      row_list=self.row_list if qskip else None)
+            if not qskip:
+                self.row_list = None
             f.append((self._fn("attn_schedule"), self.sched_args))
         je = "bert.jointEmbeddings."
         self.embed_args = capi.fill(
@@ -211,7 +222,7 @@ class Plan:
             self._gemm(f, xin, wqkv, L["qkv"], M, 3 * H, H, bias=bqkv)
             a = capi.attn_args(L["qkv"], L["ctx"], L["lse"], self.keybias, self.cu, H, self.nh, self.max_S,
                                p_drop=self.p_attn, rng_stream=(l << 8) | ST_ATTN, kv_end=self.kv_end, work=self.attn_work,
-                               flags=8 if self.attn_fwd_skip else 0)
+                               flags=8 if self.attn_fwd_skip else 0, row_list=self.row_list)
             L["attn_args"] = a
             self._seeded.append(a)
             f.append((self._fn("attn_fwd"), a))
@@ -220,7 +231,7 @@ class Plan:
             a = capi.drln_fwd_args(L["y1"], xin32, self._p(pre + "attention.output.LayerNorm.weight"),
                                    self._p(pre + "attention.output.LayerNorm.bias"), L["a"], L["m1"], L["r1"],
                                    c.layer_norm_eps, p_drop=self.p_hidden, rng_stream=(l << 8) | ST_OUT1,
-                                   out_f32=L["a32"])
+                                   out_f32=L["a32"], row_list=self.row_list)
             self._seeded.append(a)
             f.append((self._fn("dropout_residual_ln_fwd"), a))
             # training: the epilogue also saves gelu'(u) (in the "u" buffer) so that the backward is a plain multiply
@@ -232,7 +243,7 @@ class Plan:
             a = capi.drln_fwd_args(L["y2"], L["a32"], self._p(pre + "output.LayerNorm.weight"),
                                    self._p(pre + "output.LayerNorm.bias"), xout, L["m2"], L["r2"],
                                    c.layer_norm_eps, p_drop=self.p_hidden, rng_stream=(l << 8) | ST_OUT2,
-                                   out_f32=xout32)
+                                   out_f32=xout32, row_list=self.row_list)
             self._seeded.append(a)
             f.append((self._fn("dropout_residual_ln_fwd"), a))
         self.seq_out = self.x[N] if self.training else self.x[N % 2]
@@ -242,7 +253,7 @@ class Plan:
                    aux=self.t_u if self.training else None, bias=self._p(tp + "dense.bias"))
         f.append((self._fn("dropout_residual_ln_fwd"),
                   capi.drln_fwd_args(self.t_g, None, self._p(tp + "LayerNorm.weight"), self._p(tp + "LayerNorm.bias"),
-                                     self.t_ln, self.t_m, self.t_r, c.layer_norm_eps)))
+                                     self.t_ln, self.t_m, self.t_r, c.layer_norm_eps, row_list=self.row_list)))
         word_bf = self._w("bert.embeddings.word_embeddings.weight")
         if self.materialize_logits:
             self._gemm(f, self.t_ln, word_bf, self.logits, M, self.V, H, bias=self._p("cls.predictions.bias"))
@@ -320,7 +331,7 @@ class Plan:
                   capi.fill(capi.drln_bwd_args(self.GT, None, self.t_g, None, self.t_m, self.t_r,
                                                self._p(tp + "LayerNorm.weight"), self.GC, None,
                                                self._g(tp + "LayerNorm.weight"), self._g(tp + "LayerNorm.bias"),
-                                               self._g(tp + "dense.bias")), gelu_aux=self.t_u)))
+                                               self._g(tp + "dense.bias"), row_list=self.row_list), gelu_aux=self.t_u)))
         self._gemm(b, self.GC, self._w(tp + "dense.weight"), self.GA, M, H, H, b_major=MN)
         self._gemm(b, self.GC, self.seq_out, self._g(tp + "dense.weight"), H, H, M, a_major=MN, b_major=MN,
                    epilogue=ATOM, split_k=_split_k(H, H, M))
@@ -332,7 +343,7 @@ class Plan:
             a = capi.drln_bwd_args(self.GA, g2, L["y2"], L["a32"], L["m2"], L["r2"], self._p(pre + "output.LayerNorm.weight"),
                                    self.GC, self.GD, self._g(pre + "output.LayerNorm.weight"),
                                    self._g(pre + "output.LayerNorm.bias"), self._g(pre + "output.dense.bias"),
-                                   p_drop=self.p_hidden, rng_stream=(l << 8) | ST_OUT2)
+                                   p_drop=self.p_hidden, rng_stream=(l << 8) | ST_OUT2, row_list=self.row_list)
             self._seeded.append(a)
             b.append((self._fn("dropout_residual_ln_bwd"), a))
             # FFN2: du = (dY2 · W2) ∘ gelu'(u) ; gW2 += dY2^T · hg     (L["u"] holds gelu'(u), see the forward)
@@ -353,7 +364,7 @@ class Plan:
                                    self._g(pre + "attention.output.LayerNorm.weight"),
                                    self._g(pre + "attention.output.LayerNorm.bias"),
                                    self._g(pre + "attention.output.dense.bias"),
-                                   p_drop=self.p_hidden, rng_stream=(l << 8) | ST_OUT1)
+                                   p_drop=self.p_hidden, rng_stream=(l << 8) | ST_OUT1, row_list=self.row_list)
             self._seeded.append(a)
             b.append((self._fn("dropout_residual_ln_bwd"), a))
             # attention output projection: dCtx = dY1 · Wo ; gWo += dY1^T · ctx
@@ -365,7 +376,7 @@ class Plan:
             wqkv = st.span(pre + "attention.self.query.weight", pre + "attention.self.value.weight", st.bf16).view(3 * H, H)
             gwqkv = st.span(pre + "attention.self.query.weight", pre + "attention.self.value.weight", st.grad).view(3 * H, H)
             gbqkv = st.span(pre + "attention.self.query.bias", pre + "attention.self.value.bias", st.grad)
-            b.append((self._fn("colsum_bf16"), capi.colsum_args(self.dqkv, gbqkv)))
+            b.append((self._fn("colsum_bf16"), capi.colsum_args(self.dqkv, gbqkv, row_list=self.row_list)))
             self._gemm(b, self.dqkv, wqkv, self.GA, M, H, 3 * H, b_major=MN)
             self._gemm(b, self.dqkv, self.x[l], gwqkv, 3 * H, H, M, a_major=MN, b_major=MN, epilogue=ATOM,
                        split_k=_split_k(3 * H, H, M))

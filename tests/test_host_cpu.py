@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     assert len(capi.DECLARED_FUNCTIONS) >= 20
     for name in capi.DECLARED_FUNCTIONS:
         assert hasattr(L, name), name
-    assert L.mmb_version() == 203
+    assert L.mmb_version() == 204
     assert capi.launch_count() >= 0
 
 

@@ -565,3 +565,110 @@ def test_attention_forward_leaves_only_fully_masked_query_tiles_unwritten(p_drop
     # without the schedule's verdict (no row labels given) the flag changes nothing
     ctx2, lse2, dq2 = run(plain, 8)
     assert torch.equal(ctx0, ctx2) and torch.equal(lse0, lse2) and torch.equal(dq0, dq2)
+
+
+def _expected_row_list(lens, kv_end, premise):
+    """Restates mmb_attn_schedule_args.row_list (include/mmbert_sm100.h)."""
+    live, tile, dead, row0 = [], [], [], 0
+    for s, e in zip(lens, kv_end):
+        e = (e if 0 < e < s else s) if premise else s
+        te = min(s, (e + 127) // 128 * 128)
+        live += list(range(row0, row0 + e))
+        tile += list(range(row0 + e, row0 + te))
+        dead += list(range(row0 + te, row0 + s))
+        row0 += s
+    return live, tile, dead
+
+
+@pytest.mark.gpu
+def test_schedule_row_list_and_the_row_kernels_that_take_it():
+    """The row list of mmb_attn_schedule (live rows | rest of their attention tile | dead rows) against a Python restatement,
+    with and without the premise; then the row kernels with the list: LayerNorm forward computes exactly the live rows
+    (bit-identical to the full launch) and leaves the others alone, the backward is bit-identical on the live rows and
+    writes zeros elsewhere without reading (NaN-filled inputs there), the column sum only reads live rows."""
+    from msa_b200 import capi
+    g = torch.Generator().manual_seed(31)
+    lens = torch.randint(1, 551, (37,), generator=g).tolist() + [550, 128, 129, 1, 300]
+    kv = [int(torch.randint(1, s + 1, (1,), generator=g)) for s in lens[:-5]] + [70, 128, 0, 1, 129]
+    rows, nh, H = sum(lens), 2, 768
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    cu_t = torch.tensor(cu, device="cuda", dtype=torch.int32)
+    kv_t = torch.tensor(kv, device="cuda", dtype=torch.int32)
+    row_label = torch.full((rows,), -100, device="cuda", dtype=torch.int32)
+    for i, (s, v) in enumerate(zip(lens, kv)):
+        row_label[cu[i] + (int(torch.randint(0, v, (1,), generator=g)) if v > 0 else 0)] = 7
+    work = capi.attn_schedule_buffer(len(lens), nh, max(lens), "cuda")
+    rl = torch.full((4 + rows,), -1, device="cuda", dtype=torch.int32)
+
+    def schedule(labels):
+        rl.fill_(-1)
+        capi.call("attn_schedule", capi.attn_schedule_args(cu_t, kv_t, work, nh, max(lens), row_label=labels, row_list=rl))
+        return rl.cpu().tolist()
+
+    for premise in (True, False):
+        labels = row_label
+        if not premise:
+            labels = row_label.clone()
+            labels[cu[37] + 549] = 3      # a label behind kv_end (sequence 37: 550 rows, kv_end 70)
+        got = schedule(labels)
+        live, tile, dead = _expected_row_list(lens, kv, premise)
+        assert got[:4] == [len(live), len(tile), rows, 1 if premise else 0]
+        assert got[4:4 + len(live)] == live
+        assert got[4 + len(live):4 + len(live) + len(tile)] == tile
+        assert sorted(got[4 + len(live) + len(tile):]) == dead
+    got = schedule(row_label)
+    live, tile, dead = _expected_row_list(lens, kv, True)
+    assert 0.2 < len(live) / rows < 0.8
+    is_live = torch.zeros(rows, dtype=torch.bool, device="cuda")
+    is_live[torch.tensor(live, device="cuda")] = True
+
+    torch.manual_seed(32)
+    y, res = _bf(torch.randn(rows, H, device="cuda")), torch.randn(rows, H, device="cuda")
+    gamma, beta = torch.randn(H, device="cuda"), torch.randn(H, device="cuda")
+
+    def fwd(row_list, p):
+        out = torch.full((rows, H), 3.0, device="cuda", dtype=torch.bfloat16)
+        out32, mean, rstd = torch.full((rows, H), 3.0, device="cuda"), torch.full((rows,), 3.0, device="cuda"), torch.full((rows,), 3.0, device="cuda")
+        capi.drln_fwd(y, res, gamma, beta, out, mean, rstd, 1e-12, p_drop=p, seed=5, rng_stream=2, out_f32=out32, row_list=row_list)
+        return out, out32, mean, rstd
+
+    for p in (0.0, 0.1):
+        full, part = fwd(None, p), fwd(rl, p)
+        for a, b in zip(full, part):
+            assert torch.equal(a[is_live], b[is_live])
+            assert bool((b[~is_live] == 3.0).all())
+        out, out32, mean, rstd = full
+        g1, g2 = _bf(torch.randn(rows, H, device="cuda")), torch.randn(rows, H, device="cuda")
+        g1[~is_live] = 0
+        g2[~is_live] = 0
+
+        def bwd(row_list, poison):
+            g1_, g2_, y_, res_ = (t.clone() for t in (g1, g2, y, res))
+            if poison:          # nothing may be read on the other rows
+                for t in (g1_, g2_, y_, res_):
+                    t[~is_live] = float("nan")
+            d_y = torch.full((rows, H), 5.0, device="cuda", dtype=torch.bfloat16)
+            d_res = torch.full((rows, H), 5.0, device="cuda")
+            dgamma, dbeta, dbias = (torch.zeros(H, device="cuda") for _ in range(3))
+            capi.drln_bwd(g1_, g2_, y_, res_, mean, rstd, gamma, d_y, d_res, dgamma, dbeta, dbias, p_drop=p, seed=5, rng_stream=2,
+                          row_list=row_list)
+            return d_y, d_res, dgamma, dbeta, dbias
+
+        fb, pb = bwd(None, False), bwd(rl, True)
+        assert torch.equal(fb[0][is_live], pb[0][is_live]) and torch.equal(fb[1][is_live], pb[1][is_live])
+        assert bool((pb[0][~is_live] == 0).all()) and bool((pb[1][~is_live] == 0).all())
+        assert bool((fb[0][~is_live] == 0).all())          # the full launch computes the same zeros
+        for a, b in zip(fb[2:], pb[2:]):
+            assert torch.isfinite(b).all() and _rel(b, a) < 1e-5          # fp32 atomics: order only
+
+    X = _bf(torch.randn(rows, 2304, device="cuda"))
+    X[~is_live] = 0
+    ref = torch.zeros(2304, device="cuda")
+    capi.colsum(X, ref)
+    Xp = X.clone()
+    Xp[~is_live] = float("nan")
+    got_sum = torch.zeros(2304, device="cuda")
+    capi.call("colsum_bf16", capi.colsum_args(Xp, got_sum, row_list=rl))
+    assert torch.isfinite(got_sum).all() and _rel(got_sum, ref) < 1e-5

@@ -296,14 +296,16 @@ def test_fused_cross_entropy_tracks_changing_labels_and_matches_the_materialised
 
 def test_forward_attention_tail_skip_changes_nothing_observable(monkeypatch):
     """Training with the fused cross entropy skips the forward attention of the 128-query tiles that lie entirely behind
-    kv_end (mmb_attn_args.flags bit 3; padding rows that no loss, no head and no unmasked key ever reads).  Two models on
+    kv_end (mmb_attn_args.flags bit 3; padding rows that no loss, no head and no unmasked key ever reads), and the row
+    kernels (LayerNorm forward / backward, column sums, attention-backward preparation) leave those rows alone
+    (mmb_attn_schedule_args.row_list).  Two models on
     the same weights, one built with MMB_ATTN_FWD_QSKIP=0: over three different batches through the SAME plans (so the
     skipped rows hold stale values of the previous batch) every returned value and every gradient agrees to the order of
     the fp32 atomic reductions (loss sums, split-K) — the kernel-level test checks the attention output bit for bit."""
     ocfg = O.Cfg(hidden_size=128, num_hidden_layers=3, num_attention_heads=2, intermediate_size=256, vocab_size=1000,
                  max_position_embeddings=64)
     sd = seeded_state_dict(ocfg, "mosei", seed=5, std=0.05)
-    monkeypatch.setenv("MMB_ATTN_FWD_QSKIP", "0")
+    monkeypatch.setenv("MMB_ATTN_FWD_QSKIP", "0")         # (also turns the row lists of the row kernels off)
     m_full = _build(ocfg, "mosei", sd, fused=True).train()
     batches = [synth.tree_to(synth.make_batch(6, 16, 400, 300, 35, 74, vocab_size=1000, seed=s, min_len=4), "cuda") for s in (1, 2, 3)]
     m_full(**batches[0])
@@ -313,6 +315,7 @@ def test_forward_attention_tail_skip_changes_nothing_observable(monkeypatch):
     plans = [next(iter(m._plans.values())) if hasattr(m, "_plans") else None for m in (m_full, m_skip)]
     if plans[0] is not None:
         assert not plans[0].attn_fwd_skip and plans[1].attn_fwd_skip
+        assert plans[0].row_list is None and plans[1].row_list is not None
     for batch in batches:
         for m in (m_full, m_skip):
             for p in m.parameters():
