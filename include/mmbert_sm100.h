@@ -32,7 +32,7 @@ extern "C" {
                            202: mmb_attn_schedule_args.row_label (zero-gradient query tail skipped by the backward);
                            203: mmb_gemm_args.colsum;
                            204: mmb_attn_args.flags bit 3, row lists (mmb_attn_schedule_args.row_list and the row_list
-                           members of the row kernels) */
+                           members of the row kernels), mmb_gemm_args.row_live */
 
 enum mmb_status {
     MMB_OK = 0,
@@ -108,6 +108,11 @@ typedef struct mmb_gemm_args {
                       Linear whose output gradient C is: exactly what its wgrad GEMM reads).  bf16-output epilogues
                       only; taken from the epilogue's staging tiles of the CTA-pair kernel, else by a mmb_colsum_bf16
                       launch behind the GEMM */
+    const int32_t* row_live; /* NULL, or int32 [M]: 0 marks an output row nobody reads (a padding row, see
+                      mmb_attn_schedule_args.row_list: its per-row flags).  A hint the epilogue MAY use, in units of its
+                      32-row slices: MMB_EPI_GELU_BF16 / MMB_EPI_GELU_GRAD_BF16 leave C / aux of an all-dead slice unwritten (no
+                      activation math, no stores), MMB_EPI_MUL_AUX_BF16 writes zeros there without reading aux (its wgrad consumer
+                      reads every row).  The matrix product itself is computed for every tile.  Other epilogues ignore it. */
 } mmb_gemm_args;
 
 int mmb_gemm(const mmb_gemm_args* a, void* stream);
@@ -255,11 +260,13 @@ typedef struct mmb_attn_schedule_args {
     void* work;                /* out: mmb_attn_schedule_bytes(...) bytes, 16-byte aligned */
     int32_t nseq, nheads, max_seqlen;
     const int32_t* row_label;  /* [rows] from mmb_pack_prepare, or NULL (no query-tail skipping) */
-    int32_t* row_list;         /* NULL, or out: int32 [4 + rows] — the packed rows in three groups,
+    int32_t* row_list;         /* NULL, or out: int32 [4 + 2 rows] — the packed rows in three groups,
                                   [0] = n_live  rows before their sequence's kv_end,
                                   [1] = n_tile  rows at or behind kv_end that share a 128-row attention tile with a live row,
                                   [2] = rows, [3] = 1 if the zero-gradient-tail premise above holds (else every row is live),
-                                  [4 ..) = the live rows (ascending), then the tile rows, then the rest.
+                                  [4, 4 + rows) = the live rows (ascending), then the tile rows, then the rest;
+                                  [4 + rows, 4 + 2 rows) = per-row flags, 1 = live (mmb_gemm_args.row_live).
+                                  The buffer holds 4 + 2 rows ints.
                                   A row that is not live is padding: a masked key for every query of every layer whose
                                   value reaches no loss and whose gradient is exactly zero.  The row kernels (LayerNorm
                                   forward / backward, column sums, the attention backward's preparation) take the list to

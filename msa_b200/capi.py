@@ -150,9 +150,10 @@ def fill(struct, **kw):
 
 
 def gemm_args(A, B, C, M, N, K, *, a_major=MAJOR_K, b_major=MAJOR_K, epilogue=EPI_STORE_BF16, bias=None, aux=None,
-              aux2=None, split_k=1, alpha=1.0, lda=None, ldb=None, ldc=None, ldaux=None, dbg_flags=0, colsum=None):
+              aux2=None, split_k=1, alpha=1.0, lda=None, ldb=None, ldc=None, ldaux=None, dbg_flags=0, colsum=None,
+              row_live=None):
     a = GemmArgs()
-    return fill(a, A=A, B=B, C=C, aux=aux, aux2=aux2, bias=bias, colsum=colsum,
+    return fill(a, A=A, B=B, C=C, aux=aux, aux2=aux2, bias=bias, colsum=colsum, row_live=row_live,
                 lda=A.stride(0) if lda is None else lda, ldb=B.stride(0) if ldb is None else ldb,
                 ldc=(C.stride(0) if C is not None else 0) if ldc is None else ldc,
                 ldaux=((aux.stride(0) if aux is not None else 0) if ldaux is None else ldaux),

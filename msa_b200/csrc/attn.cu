@@ -187,10 +187,12 @@ attn_schedule_kernel(const int* __restrict__ cu, const int* __restrict__ kv_end,
         int* live = row_list + 4;
         int* tile = live + tot[0];
         int* dead = tile + tot[1];
+        int* flag = live + cu[nseq];           // per-row flags behind the list (mmb_gemm_args.row_live)
         for (int i = warp; i < nseq; i += kSchedThreads / 32) {
             const int row0 = cu[i], S = len[i], e = qskip ? eff[i] : S;
             const int te = min(S, (e + 127) / 128 * 128);
             for (int j = lane; j < S; j += 32) {
+                flag[row0 + j] = j < e ? 1 : 0;
                 if (j < e) live[off_live[i] + j] = row0 + j;
                 else if (j < te) tile[off_tile[i] + (j - e)] = row0 + j;
                 else dead[off_dead[i] + (j - te)] = row0 + j;

@@ -57,6 +57,7 @@ struct GemmParams {
     int tma_store;  // CTA-pair kernel: bf16 outputs leave through cp.async.bulk.tensor stores (tmC / tmAux)
     int stages;     // CTA-pair kernel: depth of the operand ring (6, or 5 to make room for the column-sum array)
     float* colsum;  // CTA-pair kernel, 8 epilogue warps: [N] column sums of the bf16-rounded output, or null
+    const int* row_live;   // CTA-pair kernel, GELU_GRAD / MUL_AUX TMA-store epilogues: per-row flags (mmb_gemm_args.row_live)
 };
 
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], int ncols_valid) {
@@ -910,11 +911,17 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             // MUL_AUX: this thread's 128 aux values (its row, the warp's column half) are fetched BEFORE waiting for the
             // accumulator, so the global-load latency hides under the tile's MMAs instead of stalling every chunk
             const int colw = n_blk * TN + half * kColsPerWarp;
+            // padding rows (mmb_gemm_args.row_live): a 32-row slice without a live row needs no epilogue work
+            bool slice_live = true;
+            if (p.row_live != nullptr) {
+                const int row = row_base + lane;
+                slice_live = __any_sync(0xffffffffu, row < p.M && __ldg(p.row_live + row) != 0);
+            }
             const bool aux_pref = p.epilogue == MMB_EPI_MUL_AUX_BF16 && colw + kColsPerWarp <= p.N && !(p.dbg & 48);
             // (32-byte loads: a lane walks along ITS row, so a 16-byte load would use half of every sector it touches — ncu
             // had the L1 at 78 % throughput with 16-byte loads, the busiest unit of this GEMM)
             uint32_t auxr[kColsPerWarp / 16][8];
-            if (aux_pref) {
+            if (aux_pref && slice_live) {
                 const int row = row_base + lane;
                 const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)(row < p.M ? row : 0) * p.ldaux + colw;
                 if ((reinterpret_cast<uintptr_t>(src) & 31) == 0) {
@@ -951,6 +958,13 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     for (int g = 0; g < kColsPerWarp / 64; ++g) {     // unrolled: auxr[] stays in registers
                         const int colg = colw + g * 64;
                         if (colg >= p.N) break;
+                        if (!slice_live) {                // an all-padding slice of the multiply epilogue: zeros, nothing read
+                            stage_acquire(lane);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) sts128(stage_buf + stage_off128(lane, j), 0u, 0u, 0u, 0u);
+                            stage_release(&tmC, stage_buf, nullptr, 0, colg, row_base, lane);
+                            continue;
+                        }
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             const int col0 = colg + 32 * h;
@@ -1008,7 +1022,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll 1
                     for (int c = 0; c < kColsPerWarp; c += 32) {
                         const int col0 = colw + c;
-                        if (col0 >= p.N) break;
+                        if (col0 >= p.N || !slice_live) break;     // (an all-padding slice stays unwritten)
                         uint32_t raw[32];
                         ptx::tmem_ld_32x32(tacc + c, raw);
                         ptx::tmem_ld_wait();
@@ -1200,6 +1214,7 @@ static void fill_common(GemmParams& p, const mmb_gemm_args* a, int tile_m, int t
     p.tma_store = 0;
     p.stages = 0;
     p.colsum = nullptr;
+    p.row_live = nullptr;
     p.dbg = a->dbg_flags;
     static const int lane_issue = [] {                       // MMB_GEMM_ISSUE=lane: single-lane MMA issue (A/B runs)
         const char* e = getenv("MMB_GEMM_ISSUE");
@@ -1332,6 +1347,12 @@ static int launch_gemm_2cta(const mmb_gemm_args* a, cudaStream_t stream) {
     const bool fused_colsum = a->colsum != nullptr && p.tma_store && !wide && (size_t)a->N * 4 <= 28 * 1024 &&
                               (a->epilogue != MMB_EPI_MUL_AUX_BF16 || a->N % 128 == 0) && !(a->dbg_flags & 48);
     p.colsum = fused_colsum ? a->colsum : nullptr;
+    // padding-row hint: the GELU epilogues on their 16-warp TMA path (slices stay unwritten), MUL_AUX on the 8-warp TMA path with whole
+    // 128-column strips (slices are zero-filled); every other combination computes all rows
+    if (a->row_live != nullptr && p.tma_store &&
+        ((wide && (a->epilogue == MMB_EPI_GELU_GRAD_BF16 || a->epilogue == MMB_EPI_GELU_BF16)) ||
+         (!wide && a->epilogue == MMB_EPI_MUL_AUX_BF16 && a->N % 128 == 0)))
+        p.row_live = a->row_live;
     if (wide) {
         p.stages = Cfg2<16>::stages(false);
         launch_pdl(gemm_tcgen05_2cta_kernel<16>, dim3(2 * clusters), dim3(Cfg2<16>::kThreads), Cfg2<16>::smem_bytes(p.stages, 0), stream,

@@ -99,7 +99,7 @@ class Plan:
         # mmb_attn_schedule_args.row_list).  MMB_ROW_SKIP=0 for A/B runs.
         self.row_list = None
         if self.attn_fwd_skip and os.environ.get("MMB_ROW_SKIP", "1") != "0":
-            self.row_list = torch.zeros(4 + M, device=dev, dtype=I32)
+            self.row_list = torch.zeros(4 + 2 * M, device=dev, dtype=I32)
 
         def zbuf(*shape, dtype=BF16):      # rows a skipped tile never writes are still GEMM operands: finite from the start
             return torch.zeros(*shape, device=dev, dtype=dtype) if self.attn_fwd_skip else buf(*shape, dtype=dtype)
@@ -111,7 +111,7 @@ class Plan:
             self.layers.append(dict(
                 qkv=buf(M, 3 * H), ctx=zbuf(M, H), lse=zbuf(nh, M, dtype=F32), y1=buf(M, H), a=zbuf(M, H),
                 a32=zbuf(M, H, dtype=F32),
-                m1=buf(M, dtype=F32), r1=buf(M, dtype=F32), u=buf(M, I), hg=buf(M, I), y2=buf(M, H),
+                m1=buf(M, dtype=F32), r1=buf(M, dtype=F32), u=zbuf(M, I), hg=zbuf(M, I), y2=buf(M, H),
                 m2=buf(M, dtype=F32), r2=buf(M, dtype=F32)))
         self.e_m1, self.e_r1, self.e_m2, self.e_r2 = (buf(M, dtype=F32) for _ in range(4))
         self.pframe = buf(max(nfr, 1), H)
@@ -186,6 +186,10 @@ class Plan:
             if not qskip:
                 self.row_list = None
             f.append((self._fn("attn_schedule"), self.sched_args))
+        # per-row live flags behind the list: the GELU / multiply GEMM epilogues skip all-padding 32-row slices
+        self.row_live = None
+        if self.row_list is not None and os.environ.get("MMB_GEMM_ROW_SKIP", "1") != "0":
+            self.row_live = self.row_list[4 + M:]
         je = "bert.jointEmbeddings."
         self.embed_args = capi.fill(
             capi.EmbedArgs(), frame_dim=[self.Dv, self.Da],
@@ -237,7 +241,8 @@ class Plan:
             # training: the epilogue also saves gelu'(u) (in the "u" buffer) so that the backward is a plain multiply
             self._gemm(f, L["a"], self._w(pre + "intermediate.dense.weight"), L["hg"], M, I, H,
                        epilogue=capi.EPI_GELU_GRAD_BF16 if self.training else capi.EPI_GELU_BF16,
-                       aux=L["u"] if self.training else None, bias=self._p(pre + "intermediate.dense.bias"))
+                       aux=L["u"] if self.training else None, bias=self._p(pre + "intermediate.dense.bias"),
+                       row_live=self.row_live)
             self._gemm(f, L["hg"], self._w(pre + "output.dense.weight"), L["y2"], M, H, I,
                        bias=self._p(pre + "output.dense.bias"))
             a = capi.drln_fwd_args(L["y2"], L["a32"], self._p(pre + "output.LayerNorm.weight"),
@@ -250,7 +255,7 @@ class Plan:
         # LM head: decoder(LayerNorm(gelu(dense(seq)))) on ALL positions (MMBertForPretraining.py:293)
         tp = "cls.predictions.transform."
         self._gemm(f, self.seq_out, self._w(tp + "dense.weight"), self.t_g, M, H, H, epilogue=capi.EPI_GELU_BF16,
-                   aux=self.t_u if self.training else None, bias=self._p(tp + "dense.bias"))
+                   aux=self.t_u if self.training else None, bias=self._p(tp + "dense.bias"), row_live=self.row_live)
         f.append((self._fn("dropout_residual_ln_fwd"),
                   capi.drln_fwd_args(self.t_g, None, self._p(tp + "LayerNorm.weight"), self._p(tp + "LayerNorm.bias"),
                                      self.t_ln, self.t_m, self.t_r, c.layer_norm_eps, row_list=self.row_list)))
@@ -350,7 +355,7 @@ class Plan:
             # (the epilogue also takes the column sums of du = the FFN1 bias gradient, from its staging tiles)
             self._gemm(b, self.GC, self._w(pre + "output.dense.weight"), self.du, M, I, H, b_major=MN,
                        epilogue=capi.EPI_MUL_AUX_BF16, aux=L["u"],
-                       colsum=self._g(pre + "intermediate.dense.bias") if fuse_colsum else None)
+                       colsum=self._g(pre + "intermediate.dense.bias") if fuse_colsum else None, row_live=self.row_live)
             self._gemm(b, self.GC, L["hg"], self._g(pre + "output.dense.weight"), H, I, M, a_major=MN, b_major=MN,
                        epilogue=ATOM, split_k=_split_k(H, I, M))
             if not fuse_colsum:

@@ -600,7 +600,7 @@ def test_schedule_row_list_and_the_row_kernels_that_take_it():
     for i, (s, v) in enumerate(zip(lens, kv)):
         row_label[cu[i] + (int(torch.randint(0, v, (1,), generator=g)) if v > 0 else 0)] = 7
     work = capi.attn_schedule_buffer(len(lens), nh, max(lens), "cuda")
-    rl = torch.full((4 + rows,), -1, device="cuda", dtype=torch.int32)
+    rl = torch.full((4 + 2 * rows,), -1, device="cuda", dtype=torch.int32)
 
     def schedule(labels):
         rl.fill_(-1)
@@ -617,7 +617,11 @@ def test_schedule_row_list_and_the_row_kernels_that_take_it():
         assert got[:4] == [len(live), len(tile), rows, 1 if premise else 0]
         assert got[4:4 + len(live)] == live
         assert got[4 + len(live):4 + len(live) + len(tile)] == tile
-        assert sorted(got[4 + len(live) + len(tile):]) == dead
+        assert sorted(got[4 + len(live) + len(tile):4 + rows]) == dead
+        flags = [0] * rows
+        for r in live:
+            flags[r] = 1
+        assert got[4 + rows:] == flags          # per-row live flags (mmb_gemm_args.row_live)
     got = schedule(row_label)
     live, tile, dead = _expected_row_list(lens, kv, True)
     assert 0.2 < len(live) / rows < 0.8
@@ -672,3 +676,49 @@ def test_schedule_row_list_and_the_row_kernels_that_take_it():
     got_sum = torch.zeros(2304, device="cuda")
     capi.call("colsum_bf16", capi.colsum_args(Xp, got_sum, row_list=rl))
     assert torch.isfinite(got_sum).all() and _rel(got_sum, ref) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N", [(1000, 3072), (520, 768)])
+def test_gemm_row_live_hint_skips_only_all_padding_slices(M, N):
+    """mmb_gemm_args.row_live: a 32-row epilogue slice without a live row is left unwritten by the GELU epilogues and
+    zero-filled by the multiply epilogue (whose column sums then only see the written rows); every slice that holds a
+    live row — and every other epilogue — is bit-identical to the call without the hint."""
+    from msa_b200 import capi
+    torch.manual_seed(6)
+    K = 768
+    A, B = _bf(torch.randn(M, K, device="cuda") * 0.3), _bf(torch.randn(N, K, device="cuda") * 0.3)
+    bias = torch.randn(N, device="cuda")
+    live = torch.zeros(M, device="cuda", dtype=torch.int32)
+    live[:70] = 1
+    live[200:300] = 1          # slices 6..9 hold live rows (rows 192..319), the rest of 96..191 and 320.. are dead
+    live[M - 3] = 1            # a live row in the ragged last slice
+    slice_live = live.view(-1)[: M // 32 * 32].view(-1, 32).amax(1).repeat_interleave(32)
+    slice_live = torch.cat((slice_live, live[M // 32 * 32:].amax().expand(M - M // 32 * 32))).bool()
+    assert 0.2 < float(slice_live.float().mean()) < 0.8
+
+    def run(epi, hint, **kw):
+        C = torch.full((M, N), 9.0, device="cuda", dtype=torch.bfloat16)
+        aux_out = torch.full((M, N), 9.0, device="cuda", dtype=torch.bfloat16) if epi != capi.EPI_MUL_AUX_BF16 else None
+        cs = torch.zeros(N, device="cuda")
+        if epi == capi.EPI_MUL_AUX_BF16:
+            capi.gemm(A, B, C, M, N, K, epilogue=epi, colsum=cs, row_live=live if hint else None, **kw)
+        else:
+            capi.gemm(A, B, C, M, N, K, epilogue=epi, bias=bias, aux=aux_out, row_live=live if hint else None)
+        return C, aux_out, cs
+
+    for epi in (capi.EPI_GELU_GRAD_BF16, capi.EPI_GELU_BF16):
+        (c0, a0, _), (c1, a1, _) = run(epi, False), run(epi, True)
+        assert torch.equal(c0[slice_live], c1[slice_live]) and torch.equal(a0[slice_live], a1[slice_live])
+        assert bool((c1[~slice_live] == 9.0).all()) and bool((a1[~slice_live] == 9.0).all())
+    aux = _bf(torch.randn(M, N, device="cuda"))
+    poisoned = aux.clone()
+    poisoned[~slice_live] = float("nan")           # nothing is read there
+    (c0, _, s0), (c1, _, s1) = run(capi.EPI_MUL_AUX_BF16, False, aux=aux), run(capi.EPI_MUL_AUX_BF16, True, aux=poisoned)
+    assert torch.equal(c0[slice_live], c1[slice_live])
+    assert bool((c1[~slice_live] == 0).all())
+    assert torch.isfinite(s1).all() and _rel(s1, c1.float().sum(0)) < 1e-5 and _rel(s0, c0.float().sum(0)) < 1e-5
+    # an epilogue that does not take the hint computes every row
+    c2 = torch.full((M, N), 9.0, device="cuda", dtype=torch.bfloat16)
+    capi.gemm(A, B, c2, M, N, K, epilogue=capi.EPI_STORE_BF16, bias=bias, row_live=live)
+    assert _rel(c2.float(), A.float() @ B.float().t() + bias) < 2 * BF16_EPS
