@@ -113,6 +113,9 @@ typedef struct mmb_gemm_args {
                       32-row slices: MMB_EPI_GELU_BF16 / MMB_EPI_GELU_GRAD_BF16 leave C / aux of an all-dead slice unwritten (no
                       activation math, no stores), MMB_EPI_MUL_AUX_BF16 writes zeros there without reading aux (its wgrad consumer
                       reads every row).  The matrix product itself is computed for every tile.  Other epilogues ignore it. */
+    int32_t dead_rows_zeroed; /* MMB_EPI_MUL_AUX_BF16 with row_live: non-zero = the caller guarantees that the all-dead
+                      slices of C already hold zeros (an earlier launch of this step into the same buffer under the same
+                      flags): they are skipped instead of zero-filled */
 } mmb_gemm_args;
 
 int mmb_gemm(const mmb_gemm_args* a, void* stream);
@@ -173,6 +176,9 @@ typedef struct mmb_drln_bwd_args {
     uint32_t rng_stream;
     const int32_t* row_list; /* NULL, or mmb_attn_schedule's row list: the live rows are computed, d_y / d_res of every
                                 other row are set to zero without reading anything (their gradient is exactly zero) */
+    int32_t dead_rows_zeroed; /* with row_list: non-zero = the caller guarantees that the non-live rows of d_y and d_res
+                                already hold zeros (an earlier launch of this step wrote them into the same buffers under
+                                the same list and nothing else writes there): they are then not written again */
 } mmb_drln_bwd_args;
 int mmb_dropout_residual_ln_bwd(const mmb_drln_bwd_args* a, void* stream);
 
@@ -224,7 +230,11 @@ typedef struct mmb_attn_args {
                        masked keys for every query of every layer and never read by a loss, so every value the model
                        returns (and every gradient) is unchanged bit for bit — callers that read the hidden states or the
                        vocabulary logits of padded positions (materialised pred_t / pred_v / pred_s) must leave it clear.
-                       ctx must hold finite values (e.g. zero-initialised once): the next GEMM still reads those rows. */
+                       ctx must hold finite values (e.g. zero-initialised once): the next GEMM still reads those rows.
+                       bit 4 (value 16), backward with work lists only: the caller guarantees that the dqkv rows of the 128-row
+                       tiles that lie entirely behind kv_end already hold zeros (an earlier mmb_attn_bwd of this step wrote
+                       them into the same buffer for the same batch); with the zero-gradient-tail bit set those tiles are
+                       then not written again. */
     const void* work;       /* NULL, or the work lists written by mmb_attn_schedule for the same cu_seqlens / kv_end /
                                nheads / max_seqlen: the persistent kernels then take their (sequence, head, tile) items
                                longest first instead of in index order (same results bit for bit; evens out the CTAs) */

@@ -151,9 +151,10 @@ def fill(struct, **kw):
 
 def gemm_args(A, B, C, M, N, K, *, a_major=MAJOR_K, b_major=MAJOR_K, epilogue=EPI_STORE_BF16, bias=None, aux=None,
               aux2=None, split_k=1, alpha=1.0, lda=None, ldb=None, ldc=None, ldaux=None, dbg_flags=0, colsum=None,
-              row_live=None):
+              row_live=None, dead_rows_zeroed=0):
     a = GemmArgs()
     return fill(a, A=A, B=B, C=C, aux=aux, aux2=aux2, bias=bias, colsum=colsum, row_live=row_live,
+                dead_rows_zeroed=dead_rows_zeroed,
                 lda=A.stride(0) if lda is None else lda, ldb=B.stride(0) if ldb is None else ldb,
                 ldc=(C.stride(0) if C is not None else 0) if ldc is None else ldc,
                 ldaux=((aux.stride(0) if aux is not None else 0) if ldaux is None else ldaux),
@@ -177,10 +178,10 @@ def drln_fwd(*a, **kw):
 
 
 def drln_bwd_args(g1, g2, y, res, mean, rstd, gamma, d_y, d_res, dgamma, dbeta, dbias, p_drop=0.0, seed=0,
-                  rng_stream=0, row_list=None):
+                  rng_stream=0, row_list=None, dead_rows_zeroed=0):
     return fill(DrlnBwdArgs(), g1=g1, g2=g2, y=y, res=res, mean=mean, rstd=rstd, gamma=gamma, d_y=d_y, d_res=d_res,
                 dgamma=dgamma, dbeta=dbeta, dbias=dbias, M=y.shape[0], H=y.shape[1], p_drop=p_drop, seed=seed,
-                rng_stream=rng_stream, row_list=row_list)
+                rng_stream=rng_stream, row_list=row_list, dead_rows_zeroed=dead_rows_zeroed)
 
 
 def drln_bwd(*a, **kw):

@@ -81,6 +81,7 @@ struct BwdTcParams {
     const int* cu_seqlens;
     const int* kv_end;
     const int4* work;          // mmb_attn_schedule's lists or null (items in index order)
+    int zero_tiles_done;       // flags bit 4: the zero-fill items of the dK/dV list may be left out (see mmb_attn_args.flags)
     int H, nheads, nseq, tiles, total_rows;
     float scale_log2, scale;
     uint32_t thresh32;
@@ -302,6 +303,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_c
         const int cap = hdr.z & 0x3fffffff;
         // with the query tail skipped both passes walk the dK/dV list: live tiles by effective length, zero-fill tiles last
         total_items = (kIsDq && !qskip) ? hdr.x : hdr.y;
+        if (qskip && p.zero_tiles_done) total_items = hdr.w;      // only the tiles that start before kv_end; the rest is zero already
         wl = p.work + 1 + ((kIsDq && !qskip) ? 0 : cap);
     }
     const bool listed = wl != nullptr;
@@ -609,6 +611,7 @@ int launch_attn_bwd_tc(const mmb_attn_args* a, cudaStream_t stream) {
     p.cu_seqlens = a->cu_seqlens;
     p.kv_end = a->kv_end;
     p.work = (const int4*)a->work;
+    p.zero_tiles_done = (a->flags & 16) ? 1 : 0;
     p.H = a->H;
     p.nheads = a->nheads;
     p.nseq = a->nseq;

@@ -58,6 +58,7 @@ struct GemmParams {
     int stages;     // CTA-pair kernel: depth of the operand ring (6, or 5 to make room for the column-sum array)
     float* colsum;  // CTA-pair kernel, 8 epilogue warps: [N] column sums of the bf16-rounded output, or null
     const int* row_live;   // CTA-pair kernel, GELU_GRAD / MUL_AUX TMA-store epilogues: per-row flags (mmb_gemm_args.row_live)
+    int dead_zeroed;       // MUL_AUX with row_live: all-dead slices of C already hold zeros, skip them
 };
 
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], int ncols_valid) {
@@ -959,6 +960,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         const int colg = colw + g * 64;
                         if (colg >= p.N) break;
                         if (!slice_live) {                // an all-padding slice of the multiply epilogue: zeros, nothing read
+                            if (p.dead_zeroed) continue;  // (already zero from an earlier launch of this step)
                             stage_acquire(lane);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) sts128(stage_buf + stage_off128(lane, j), 0u, 0u, 0u, 0u);
@@ -1215,6 +1217,7 @@ static void fill_common(GemmParams& p, const mmb_gemm_args* a, int tile_m, int t
     p.stages = 0;
     p.colsum = nullptr;
     p.row_live = nullptr;
+    p.dead_zeroed = 0;
     p.dbg = a->dbg_flags;
     static const int lane_issue = [] {                       // MMB_GEMM_ISSUE=lane: single-lane MMA issue (A/B runs)
         const char* e = getenv("MMB_GEMM_ISSUE");
@@ -1353,6 +1356,7 @@ static int launch_gemm_2cta(const mmb_gemm_args* a, cudaStream_t stream) {
         ((wide && (a->epilogue == MMB_EPI_GELU_GRAD_BF16 || a->epilogue == MMB_EPI_GELU_BF16)) ||
          (!wide && a->epilogue == MMB_EPI_MUL_AUX_BF16 && a->N % 128 == 0)))
         p.row_live = a->row_live;
+    p.dead_zeroed = (p.row_live != nullptr && a->dead_rows_zeroed) ? 1 : 0;
     if (wide) {
         p.stages = Cfg2<16>::stages(false);
         launch_pdl(gemm_tcgen05_2cta_kernel<16>, dim3(2 * clusters), dim3(Cfg2<16>::kThreads), Cfg2<16>::smem_bytes(p.stages, 0), stream,

@@ -93,7 +93,8 @@ drln_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ 
                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
                 __nv_bfloat16* __restrict__ d_y, float* __restrict__ d_res, float* __restrict__ dgamma,
                 float* __restrict__ dbeta, float* __restrict__ dbias, const __nv_bfloat16* __restrict__ gelu_aux, int M,
-                int H, uint32_t thresh, float inv_keep, uint64_t seed, uint32_t stream, const int* __restrict__ row_list) {
+                int H, uint32_t thresh, float inv_keep, uint64_t seed, uint32_t stream, const int* __restrict__ row_list,
+                int dead_rows_zeroed) {
     pdl_trigger();     // programmatic dependent launch (common.cuh): no global access before the wait
     pdl_wait();
     extern __shared__ __align__(16) float smem[];   // [kLnBwdWarps][3][H]
@@ -109,7 +110,7 @@ drln_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ 
     // written as such without reading anything (the wgrad / dgrad GEMMs read every row of d_y, the next LayerNorm
     // backward every live row of d_res)
     const int nrows = row_list != nullptr ? __ldg(row_list) : M;
-    if (row_list != nullptr) {
+    if (row_list != nullptr && !dead_rows_zeroed) {
         const int ndead = __ldg(row_list + 2) - nrows;
         for (int ri = blockIdx.x * kLnBwdWarps + warp; ri < ndead; ri += nw) {
             const int row = __ldg(row_list + 4 + nrows + ri);
@@ -343,7 +344,8 @@ extern "C" int mmb_dropout_residual_ln_bwd(const mmb_drln_bwd_args* a, void* str
                                (const __nv_bfloat16*)a->g1, a->g2, (const __nv_bfloat16*)a->y,
                                a->res, a->mean, a->rstd, a->gamma, (__nv_bfloat16*)a->d_y,
                                a->d_res, a->dgamma, a->dbeta, a->dbias,
-                               (const __nv_bfloat16*)a->gelu_aux, a->M, a->H, thresh, inv_keep, a->seed, a->rng_stream, a->row_list)));
+                               (const __nv_bfloat16*)a->gelu_aux, a->M, a->H, thresh, inv_keep, a->seed, a->rng_stream, a->row_list,
+                               a->dead_rows_zeroed)));
     return check_launch("drln_bwd_kernel");
 }
 

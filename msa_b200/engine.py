@@ -345,17 +345,22 @@ class Plan:
             L = self.layers[l]
             pre = f"bert.encoder.layer.{l}."
             g2 = None if l == N - 1 else self.GB
+            # padding rows of GC / GD / GB / du are zero-filled by their first writer of the step (the top layer's launches);
+            # only these kernels write those buffers, so every later launch of the sweep leaves the rows alone
+            zeroed = 1 if (l < N - 1 and self.row_list is not None) else 0
             a = capi.drln_bwd_args(self.GA, g2, L["y2"], L["a32"], L["m2"], L["r2"], self._p(pre + "output.LayerNorm.weight"),
                                    self.GC, self.GD, self._g(pre + "output.LayerNorm.weight"),
                                    self._g(pre + "output.LayerNorm.bias"), self._g(pre + "output.dense.bias"),
-                                   p_drop=self.p_hidden, rng_stream=(l << 8) | ST_OUT2, row_list=self.row_list)
+                                   p_drop=self.p_hidden, rng_stream=(l << 8) | ST_OUT2, row_list=self.row_list,
+                                   dead_rows_zeroed=zeroed)
             self._seeded.append(a)
             b.append((self._fn("dropout_residual_ln_bwd"), a))
             # FFN2: du = (dY2 · W2) ∘ gelu'(u) ; gW2 += dY2^T · hg     (L["u"] holds gelu'(u), see the forward)
             # (the epilogue also takes the column sums of du = the FFN1 bias gradient, from its staging tiles)
             self._gemm(b, self.GC, self._w(pre + "output.dense.weight"), self.du, M, I, H, b_major=MN,
                        epilogue=capi.EPI_MUL_AUX_BF16, aux=L["u"],
-                       colsum=self._g(pre + "intermediate.dense.bias") if fuse_colsum else None, row_live=self.row_live)
+                       colsum=self._g(pre + "intermediate.dense.bias") if fuse_colsum else None, row_live=self.row_live,
+                       dead_rows_zeroed=zeroed if self.row_live is not None else 0)
             self._gemm(b, self.GC, L["hg"], self._g(pre + "output.dense.weight"), H, I, M, a_major=MN, b_major=MN,
                        epilogue=ATOM, split_k=_split_k(H, I, M))
             if not fuse_colsum:
@@ -369,7 +374,8 @@ class Plan:
                                    self._g(pre + "attention.output.LayerNorm.weight"),
                                    self._g(pre + "attention.output.LayerNorm.bias"),
                                    self._g(pre + "attention.output.dense.bias"),
-                                   p_drop=self.p_hidden, rng_stream=(l << 8) | ST_OUT1, row_list=self.row_list)
+                                   p_drop=self.p_hidden, rng_stream=(l << 8) | ST_OUT1, row_list=self.row_list,
+                                   dead_rows_zeroed=zeroed)
             self._seeded.append(a)
             b.append((self._fn("dropout_residual_ln_bwd"), a))
             # attention output projection: dCtx = dY1 · Wo ; gWo += dY1^T · ctx
@@ -377,6 +383,8 @@ class Plan:
             self._gemm(b, self.GC, L["ctx"], self._g(pre + "attention.output.dense.weight"), H, H, M, a_major=MN,
                        b_major=MN, epilogue=ATOM, split_k=_split_k(H, H, M))
             capi.fill(L["attn_args"], dctx=self.GT, dqkv=self.dqkv, bwd_ws=self.attn_ws)
+            if zeroed:          # dqkv: the tiles behind kv_end were zero-filled by the top layer's launch
+                L["attn_args"].flags |= 16
             b.append((self._fn("attn_bwd"), L["attn_args"]))
             wqkv = st.span(pre + "attention.self.query.weight", pre + "attention.self.value.weight", st.bf16).view(3 * H, H)
             gwqkv = st.span(pre + "attention.self.query.weight", pre + "attention.self.value.weight", st.grad).view(3 * H, H)

@@ -24,11 +24,12 @@ PY
 }
 S="--steps 12 --warmup 4"
 run c3_off   MMB_ATTN_FWD_QSKIP=0 -- $S
-run c3_rows  MMB_GEMM_ROW_SKIP=0 -- $S
 run c3_all   -- $S
-run c3_rows2 MMB_GEMM_ROW_SKIP=0 -- $S
+run c3_off2  MMB_ATTN_FWD_QSKIP=0 -- $S
 run c3_all2  -- $S
-run c2_rows  MMB_GEMM_ROW_SKIP=0 -- $S --workload mosi_aligned_b64
+run c2_off   MMB_ATTN_FWD_QSKIP=0 -- $S --workload mosi_aligned_b64
 run c2_all   -- $S --workload mosi_aligned_b64
+run c4_off   MMB_ATTN_FWD_QSKIP=0 -- $S --workload ur_funny_b64
+run c4_all   -- $S --workload ur_funny_b64
 timeout 150 python scripts/step_table.py mosei_unaligned_b64 > gpurun_out/${tag}_step_table_mosei_unaligned_b64.txt 2>&1
 head -32 gpurun_out/${tag}_step_table_mosei_unaligned_b64.txt

@@ -562,6 +562,9 @@ def test_attention_forward_leaves_only_fully_masked_query_tiles_unwritten(p_drop
     assert bool((ctx1[~written] == 3.0).all()) and bool((lse1[:, ~written] == 5.0).all())
     assert bool((ctx0[~written] != 3.0).any())
     assert torch.isfinite(dq1).all() and torch.equal(dq0, dq1)
+    # flags bit 4: the caller vouches for zeros in the tiles behind kv_end -> the backward leaves them alone
+    _, _, dq3 = run(skip, 8 | 16)
+    assert torch.equal(dq3[written], dq1[written]) and bool((dq3[~written] == 7.0).all()) and bool((dq1[~written] == 0).all())
     # without the schedule's verdict (no row labels given) the flag changes nothing
     ctx2, lse2, dq2 = run(plain, 8)
     assert torch.equal(ctx0, ctx2) and torch.equal(lse0, lse2) and torch.equal(dq0, dq2)
@@ -648,7 +651,7 @@ def test_schedule_row_list_and_the_row_kernels_that_take_it():
         g1[~is_live] = 0
         g2[~is_live] = 0
 
-        def bwd(row_list, poison):
+        def bwd(row_list, poison, zeroed=0):
             g1_, g2_, y_, res_ = (t.clone() for t in (g1, g2, y, res))
             if poison:          # nothing may be read on the other rows
                 for t in (g1_, g2_, y_, res_):
@@ -657,13 +660,16 @@ def test_schedule_row_list_and_the_row_kernels_that_take_it():
             d_res = torch.full((rows, H), 5.0, device="cuda")
             dgamma, dbeta, dbias = (torch.zeros(H, device="cuda") for _ in range(3))
             capi.drln_bwd(g1_, g2_, y_, res_, mean, rstd, gamma, d_y, d_res, dgamma, dbeta, dbias, p_drop=p, seed=5, rng_stream=2,
-                          row_list=row_list)
+                          row_list=row_list, dead_rows_zeroed=zeroed)
             return d_y, d_res, dgamma, dbeta, dbias
 
         fb, pb = bwd(None, False), bwd(rl, True)
         assert torch.equal(fb[0][is_live], pb[0][is_live]) and torch.equal(fb[1][is_live], pb[1][is_live])
         assert bool((pb[0][~is_live] == 0).all()) and bool((pb[1][~is_live] == 0).all())
         assert bool((fb[0][~is_live] == 0).all())          # the full launch computes the same zeros
+        zb = bwd(rl, True, zeroed=1)                        # caller-guaranteed zeros: the other rows are not written at all
+        assert torch.equal(zb[0][is_live], pb[0][is_live]) and torch.equal(zb[1][is_live], pb[1][is_live])
+        assert bool((zb[0][~is_live] == 5.0).all()) and bool((zb[1][~is_live] == 5.0).all())
         for a, b in zip(fb[2:], pb[2:]):
             assert torch.isfinite(b).all() and _rel(b, a) < 1e-5          # fp32 atomics: order only
 
@@ -718,6 +724,9 @@ def test_gemm_row_live_hint_skips_only_all_padding_slices(M, N):
     assert torch.equal(c0[slice_live], c1[slice_live])
     assert bool((c1[~slice_live] == 0).all())
     assert torch.isfinite(s1).all() and _rel(s1, c1.float().sum(0)) < 1e-5 and _rel(s0, c0.float().sum(0)) < 1e-5
+    c3 = torch.full((M, N), 9.0, device="cuda", dtype=torch.bfloat16)       # dead_rows_zeroed: those slices are not written
+    capi.gemm(A, B, c3, M, N, K, epilogue=capi.EPI_MUL_AUX_BF16, aux=poisoned, row_live=live, dead_rows_zeroed=1)
+    assert torch.equal(c3[slice_live], c1[slice_live]) and bool((c3[~slice_live] == 9.0).all())
     # an epilogue that does not take the hint computes every row
     c2 = torch.full((M, N), 9.0, device="cuda", dtype=torch.bfloat16)
     capi.gemm(A, B, c2, M, N, K, epilogue=capi.EPI_STORE_BF16, bias=bias, row_live=live)
