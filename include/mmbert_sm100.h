@@ -32,7 +32,7 @@ extern "C" {
                            202: mmb_attn_schedule_args.row_label (zero-gradient query tail skipped by the backward);
                            203: mmb_gemm_args.colsum;
                            204: mmb_attn_args.flags bit 3, row lists (mmb_attn_schedule_args.row_list and the row_list
-                           members of the row kernels), mmb_gemm_args.row_live */
+                           members of the row kernels), mmb_gemm_args.row_live / dead_rows_zeroed, mmb_embed_args.row_live */
 
 enum mmb_status {
     MMB_OK = 0,
@@ -366,6 +366,11 @@ typedef struct mmb_embed_args {
     float* gw_pad[2];
     int32_t* err_count; /* or NULL: incremented for every token id outside [0, V) (such an id reads the padding row 0
                            instead of out-of-bounds memory; torch's nn.Embedding device-asserts there) */
+    const int32_t* row_live; /* NULL, or the per-row flags of mmb_attn_schedule's row list (mmb_gemm_args.row_live): the
+                           forward leaves a block of 16 frames alone if none of its packed rows is live (x0, pframe and
+                           frames_bf16 keep their previous contents there), the backward skips dead text rows and writes
+                           dpre = 0 for dead frames without reading anything.  Text rows are always embedded (the id
+                           range check covers every position). */
 } mmb_embed_args;
 int mmb_embed_fwd(const mmb_embed_args* a, void* stream);
 int mmb_embed_bwd(const mmb_embed_args* a, void* stream);

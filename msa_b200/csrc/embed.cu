@@ -139,6 +139,7 @@ struct EmbedParams {
     __nv_bfloat16* frames_bf16[2]; // optional [B*L, ldf] bf16 copy of the frames (ldf = D rounded up to 8)
     float* gw_pad[2];              // optional [H, ldf] scratch of the tensor-core projection wgrad
     int* err_count;                // optional: count of token ids / token types outside their tables (forward only)
+    const int* row_live;           // optional per-row flags (mmb_embed_args.row_live)
 };
 
 constexpr uint32_t kStreamEmb1 = 0x100, kStreamEmb2 = 0x101;
@@ -238,6 +239,14 @@ embed_frame_fwd_kernel(const EmbedParams p, int mod) {  // mod 0 = visual (pass 
     const int nrows = p.d.B * L;
     const int r0 = blockIdx.x * kFrameRows;
     const int tid = threadIdx.x;
+    if (p.row_live != nullptr) {          // a block of padding frames: nothing downstream reads its rows
+        int any = 0;
+        if (tid < kFrameRows && r0 + tid < nrows) {
+            const int fr = r0 + tid, b = fr / L, l = fr - b * L;
+            any = __ldg(p.row_live + frame_packed_row(p.d, pass, b, l));
+        }
+        if (!__syncthreads_or(any)) return;
+    }
     for (int i = tid; i < kFrameRows * D; i += 256) {
         const int r = i / D, k = i - r * D;
         sF[r * Dp + k] = (r0 + r) < nrows ? load_as_float(p.frames[mod], p.frames_dt[mod], (int64_t)(r0 + r) * D + k) : 0.f;
@@ -342,6 +351,7 @@ embed_text_bwd_kernel(const EmbedParams p) {
         c.b = r / p.d.T;
         c.s = r - c.b * p.d.T;
         const int row = p.d.base(c.pass) + c.b * p.d.S(c.pass) + c.s;
+        if (p.row_live != nullptr && __ldg(p.row_live + row) == 0) continue;      // padding row: its gradient is exactly zero
         RowF<NCH> e, g;
         long long id;
         int tt;
@@ -401,6 +411,11 @@ embed_frame_bwd_kernel(const EmbedParams p) {
         else { const int r = fr - p.d.B * p.d.L1; pass = 2; b = r / p.d.L2; l = r - b * p.d.L2; }
         const int row = frame_packed_row(p.d, pass, b, l);
         RowF<NCH> z, g;
+        if (p.row_live != nullptr && __ldg(p.row_live + row) == 0) {      // padding frame: dpre = 0, nothing read
+            row_zero(g);
+            row_store_bf16(g, p.dpre + (int64_t)fr * p.H, p.H, lane);
+            continue;
+        }
         row_load_bf16(z, p.pframe + (int64_t)fr * p.H, p.H, lane);
         row_load_bf16(g, p.dx0 + (int64_t)row * p.H, p.H, lane);
         if (p.dx0b != nullptr) {
@@ -496,6 +511,7 @@ static int fill_embed(EmbedParams& p, const mmb_embed_args* a) {
     p.d.B = a->B; p.d.T = a->T; p.d.L1 = a->L[0]; p.d.L2 = a->L[1];
     p.H = a->H; p.V = a->V; p.max_pos = a->max_pos;
     p.err_count = a->err_count;
+    p.row_live = a->row_live;
     for (int i = 0; i < 3; ++i) p.ids[i] = (const long long*)a->ids[i];
     p.token_type = (const long long*)a->token_type;
     for (int i = 0; i < 2; ++i) {

@@ -34,8 +34,11 @@ drln_fwd_kernel(const void* __restrict__ y_, const float* __restrict__ res,
     const int nw = gridDim.x * kLnWarps;
     // row list (mmb_attn_schedule): only the live rows are computed; padding rows keep their previous contents
     const int nrows = row_list != nullptr ? __ldg(row_list) : M;
-    for (int ri = blockIdx.x * kLnWarps + warp; ri < nrows; ri += nw) {
-        const int row = row_list != nullptr ? __ldg(row_list + 4 + ri) : ri;
+    int ri = blockIdx.x * kLnWarps + warp;
+    int row_next = (row_list != nullptr && ri < nrows) ? __ldg(row_list + 4 + ri) : ri;      // (the index load runs one row ahead)
+    for (; ri < nrows; ri += nw) {
+        const int row = row_next;
+        row_next = (row_list != nullptr && ri + nw < nrows) ? __ldg(row_list + 4 + ri + nw) : ri + nw;
         RowF<NCH> z;
         if (kYF32) row_load_f32<NCH, kFwdLd256>(z, reinterpret_cast<const float*>(y_) + (size_t)row * H, H, lane);
         else row_load_bf16(z, reinterpret_cast<const __nv_bfloat16*>(y_) + (size_t)row * H, H, lane);
@@ -125,8 +128,11 @@ drln_bwd_kernel(const __nv_bfloat16* __restrict__ g1, const float* __restrict__ 
             }
         }
     }
-    for (int ri = blockIdx.x * kLnBwdWarps + warp; ri < nrows; ri += nw) {
-        const int row = row_list != nullptr ? __ldg(row_list + 4 + ri) : ri;
+    int ri = blockIdx.x * kLnBwdWarps + warp;
+    int row_next = (row_list != nullptr && ri < nrows) ? __ldg(row_list + 4 + ri) : ri;      // (the index load runs one row ahead)
+    for (; ri < nrows; ri += nw) {
+        const int row = row_next;
+        row_next = (row_list != nullptr && ri + nw < nrows) ? __ldg(row_list + 4 + ri + nw) : ri + nw;
         // every load of the row goes in flight before the first one is consumed (the kernel is latency-bound otherwise)
         RowRawB<NCH> y_raw, g1_raw;
         RowRawF<NCH> res_raw, g2_raw;

@@ -114,10 +114,10 @@ class Plan:
                 m1=buf(M, dtype=F32), r1=buf(M, dtype=F32), u=zbuf(M, I), hg=zbuf(M, I), y2=buf(M, H),
                 m2=buf(M, dtype=F32), r2=buf(M, dtype=F32)))
         self.e_m1, self.e_r1, self.e_m2, self.e_r2 = (buf(M, dtype=F32) for _ in range(4))
-        self.pframe = buf(max(nfr, 1), H)
+        self.pframe = zbuf(max(nfr, 1), H)
         # training: bf16 copies of the frames + padded scratch, so that the projection wgrad runs on the tensor cores
         ldf = [(d + 7) // 8 * 8 for d in (self.Dv, self.Da)]
-        self.frames_bf16 = [buf(max(B * L, 1), l8) for L, l8 in zip((Lv, La), ldf)] if training else [None, None]
+        self.frames_bf16 = [zbuf(max(B * L, 1), l8) for L, l8 in zip((Lv, La), ldf)] if training else [None, None]
         self.gw_pad = [buf(H, l8, dtype=F32) for l8 in ldf] if training else [None, None]
         self.t_u, self.t_g, self.t_ln = buf(M, H), buf(M, H), zbuf(M, H)
         self.t_m, self.t_r = buf(M, dtype=F32), buf(M, dtype=F32)
@@ -202,7 +202,7 @@ class Plan:
             eps1=c.layer_norm_eps, eps2=1e-5, p_drop1=self.p_hidden, p_drop2=self.p_joint, seed=0,
             x0=self.x[0], x0_f32=self.x32[0], mean1=self.e_m1, rstd1=self.e_r1, mean2=self.e_m2, rstd2=self.e_r2, pframe=self.pframe,
             B=self.B, T=self.T, L=[self.Lv, self.La], H=H, V=self.V, max_pos=c.max_position_embeddings,
-            err_count=self.label_count[3:])
+            err_count=self.label_count[3:], row_live=self.row_live)
         if self.training:
             capi.fill(self.embed_args, dpre=self.dpre, frames_bf16=self.frames_bf16, gw_pad=self.gw_pad,
                       g_word=self._g("bert.embeddings.word_embeddings.weight"),

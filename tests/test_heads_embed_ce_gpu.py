@@ -108,13 +108,18 @@ def test_embeddings_forward_exact_and_backward():
     ref = torch.cat([O.bert_pass(sd64, ocfg, ids_t, m_t, batch["token_type_ids"][0])[0].reshape(-1, 128),
                      O.bert_pass(sd64, ocfg, ids_v, m_tv, None, vis, m_v)[0].reshape(-1, 128),
                      O.bert_pass(sd64, ocfg, ids_s, m_ts, None, aud, m_s)[0].reshape(-1, 128)])
+    # padding rows (behind the last unmasked key of their sequence) may be left alone by the plan: mmb_embed_args.row_live
+    live = torch.ones(plan.M, dtype=torch.bool, device="cuda") if plan.row_live is None else plan.row_live.bool()
+    assert 0.3 < float(live.float().mean()) <= 1.0
     # fp32 residual-stream copy: only the bf16 rounding of the frame projection separates it from the oracle
-    assert rel_err(plan.x32[0], ref.detach()) < 6e-3
-    assert rel_err(plan.x[0].float(), ref.detach()) < 8e-3
+    assert rel_err(plan.x32[0][live], ref.detach()[live.cpu()]) < 6e-3
+    assert rel_err(plan.x[0].float()[live], ref.detach()[live.cpu()]) < 8e-3
     # ---- backward: dL/dx0 = g (bf16 part) + g32 (fp32 residual-stream part)
     torch.manual_seed(7)
     g = torch.randn(plan.M, 128, device="cuda").to(torch.bfloat16)
     g32 = torch.randn(plan.M, 128, device="cuda") * 0.5
+    g[~live] = 0            # the premise of the padding-row skip: no gradient reaches a padding row
+    g32[~live] = 0
     m._prepare_grads()
     m._store.grad.zero_()
     plan.GA.copy_(g)
