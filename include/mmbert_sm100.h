@@ -110,8 +110,8 @@ typedef struct mmb_gemm_args {
                       launch behind the GEMM */
     const int32_t* row_live; /* NULL, or int32 [M]: 0 marks an output row nobody reads (a padding row, see
                       mmb_attn_schedule_args.row_list: its per-row flags).  A hint the epilogue MAY use, in units of its
-                      32-row slices: MMB_EPI_GELU_BF16 / MMB_EPI_GELU_GRAD_BF16 leave C / aux of an all-dead slice unwritten (no
-                      activation math, no stores), MMB_EPI_MUL_AUX_BF16 writes zeros there without reading aux (its wgrad consumer
+                      32-row slices: MMB_EPI_STORE_BF16 (without colsum) / MMB_EPI_GELU_BF16 / MMB_EPI_GELU_GRAD_BF16 leave C / aux of
+                      an all-dead slice unwritten (no bias / activation math, no stores), MMB_EPI_MUL_AUX_BF16 writes zeros there without reading aux (its wgrad consumer
                       reads every row).  The matrix product itself is computed for every tile.  Other epilogues ignore it. */
     int32_t dead_rows_zeroed; /* MMB_EPI_MUL_AUX_BF16 with row_live: non-zero = the caller guarantees that the all-dead
                       slices of C already hold zeros (an earlier launch of this step into the same buffer under the same

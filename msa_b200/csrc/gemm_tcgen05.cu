@@ -959,8 +959,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     for (int g = 0; g < kColsPerWarp / 64; ++g) {     // unrolled: auxr[] stays in registers
                         const int colg = colw + g * 64;
                         if (colg >= p.N) break;
-                        if (!slice_live) {                // an all-padding slice of the multiply epilogue: zeros, nothing read
-                            if (p.dead_zeroed) continue;  // (already zero from an earlier launch of this step)
+                        if (!slice_live) {                // an all-padding slice: unwritten (plain store) or zeros (multiply), nothing read
+                            if (p.dead_zeroed || p.epilogue != MMB_EPI_MUL_AUX_BF16) continue;  // (zero already: earlier launch of this step)
                             stage_acquire(lane);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) sts128(stage_buf + stage_off128(lane, j), 0u, 0u, 0u, 0u);
@@ -1350,11 +1350,13 @@ static int launch_gemm_2cta(const mmb_gemm_args* a, cudaStream_t stream) {
     const bool fused_colsum = a->colsum != nullptr && p.tma_store && !wide && (size_t)a->N * 4 <= 28 * 1024 &&
                               (a->epilogue != MMB_EPI_MUL_AUX_BF16 || a->N % 128 == 0) && !(a->dbg_flags & 48);
     p.colsum = fused_colsum ? a->colsum : nullptr;
-    // padding-row hint: the GELU epilogues on their 16-warp TMA path (slices stay unwritten), MUL_AUX on the 8-warp TMA path with whole
-    // 128-column strips (slices are zero-filled); every other combination computes all rows
+    // padding-row hint: the GELU epilogues on their 16-warp TMA path and the plain store on the 8-warp TMA path (slices stay
+    // unwritten), MUL_AUX on the 8-warp TMA path with whole 128-column strips (slices are zero-filled); every other
+    // combination computes all rows
     if (a->row_live != nullptr && p.tma_store &&
         ((wide && (a->epilogue == MMB_EPI_GELU_GRAD_BF16 || a->epilogue == MMB_EPI_GELU_BF16)) ||
-         (!wide && a->epilogue == MMB_EPI_MUL_AUX_BF16 && a->N % 128 == 0)))
+         (!wide && a->epilogue == MMB_EPI_MUL_AUX_BF16 && a->N % 128 == 0) ||
+         (!wide && a->epilogue == MMB_EPI_STORE_BF16 && a->colsum == nullptr)))
         p.row_live = a->row_live;
     p.dead_zeroed = (p.row_live != nullptr && a->dead_rows_zeroed) ? 1 : 0;
     if (wide) {

@@ -109,7 +109,7 @@ class Plan:
         self.x32 = [zbuf(M, H, dtype=F32) for _ in range(N if training else 2)]
         for _ in range(nsets):
             self.layers.append(dict(
-                qkv=buf(M, 3 * H), ctx=zbuf(M, H), lse=zbuf(nh, M, dtype=F32), y1=buf(M, H), a=zbuf(M, H),
+                qkv=zbuf(M, 3 * H), ctx=zbuf(M, H), lse=zbuf(nh, M, dtype=F32), y1=buf(M, H), a=zbuf(M, H),
                 a32=zbuf(M, H, dtype=F32),
                 m1=buf(M, dtype=F32), r1=buf(M, dtype=F32), u=zbuf(M, I), hg=zbuf(M, I), y2=buf(M, H),
                 m2=buf(M, dtype=F32), r2=buf(M, dtype=F32)))
@@ -223,7 +223,7 @@ class Plan:
             pre = f"bert.encoder.layer.{l}."
             wqkv = st.span(pre + "attention.self.query.weight", pre + "attention.self.value.weight", st.bf16).view(3 * H, H)
             bqkv = st.span(pre + "attention.self.query.bias", pre + "attention.self.value.bias")
-            self._gemm(f, xin, wqkv, L["qkv"], M, 3 * H, H, bias=bqkv)
+            self._gemm(f, xin, wqkv, L["qkv"], M, 3 * H, H, bias=bqkv, row_live=self.row_live)
             a = capi.attn_args(L["qkv"], L["ctx"], L["lse"], self.keybias, self.cu, H, self.nh, self.max_S,
                                p_drop=self.p_attn, rng_stream=(l << 8) | ST_ATTN, kv_end=self.kv_end, work=self.attn_work,
                                flags=8 if self.attn_fwd_skip else 0, row_list=self.row_list)
@@ -231,7 +231,7 @@ class Plan:
             self._seeded.append(a)
             f.append((self._fn("attn_fwd"), a))
             self._gemm(f, L["ctx"], self._w(pre + "attention.output.dense.weight"), L["y1"], M, H, H,
-                       bias=self._p(pre + "attention.output.dense.bias"))
+                       bias=self._p(pre + "attention.output.dense.bias"), row_live=self.row_live)
             a = capi.drln_fwd_args(L["y1"], xin32, self._p(pre + "attention.output.LayerNorm.weight"),
                                    self._p(pre + "attention.output.LayerNorm.bias"), L["a"], L["m1"], L["r1"],
                                    c.layer_norm_eps, p_drop=self.p_hidden, rng_stream=(l << 8) | ST_OUT1,
@@ -244,7 +244,7 @@ class Plan:
                        aux=L["u"] if self.training else None, bias=self._p(pre + "intermediate.dense.bias"),
                        row_live=self.row_live)
             self._gemm(f, L["hg"], self._w(pre + "output.dense.weight"), L["y2"], M, H, I,
-                       bias=self._p(pre + "output.dense.bias"))
+                       bias=self._p(pre + "output.dense.bias"), row_live=self.row_live)
             a = capi.drln_fwd_args(L["y2"], L["a32"], self._p(pre + "output.LayerNorm.weight"),
                                    self._p(pre + "output.LayerNorm.bias"), xout, L["m2"], L["r2"],
                                    c.layer_norm_eps, p_drop=self.p_hidden, rng_stream=(l << 8) | ST_OUT2,
@@ -337,7 +337,7 @@ class Plan:
                                                self._p(tp + "LayerNorm.weight"), self.GC, None,
                                                self._g(tp + "LayerNorm.weight"), self._g(tp + "LayerNorm.bias"),
                                                self._g(tp + "dense.bias"), row_list=self.row_list), gelu_aux=self.t_u)))
-        self._gemm(b, self.GC, self._w(tp + "dense.weight"), self.GA, M, H, H, b_major=MN)
+        self._gemm(b, self.GC, self._w(tp + "dense.weight"), self.GA, M, H, H, b_major=MN, row_live=self.row_live)
         self._gemm(b, self.GC, self.seq_out, self._g(tp + "dense.weight"), H, H, M, a_major=MN, b_major=MN,
                    epilogue=ATOM, split_k=_split_k(H, H, M))
         b.append((self._fn("heads_bwd"), self.heads_args))   # adds the [CLS]-row gradients into GA
@@ -366,7 +366,10 @@ class Plan:
             if not fuse_colsum:
                 b.append((self._fn("colsum_bf16"), capi.colsum_args(self.du, self._g(pre + "intermediate.dense.bias"))))
             # FFN1: dA = du · W1 ; gW1 += du^T · a
-            self._gemm(b, self.du, self._w(pre + "intermediate.dense.weight"), self.GA, M, H, I, b_major=MN)
+            # (GA's padding rows are read by nobody: the LayerNorm / embedding backward skip them.  dCtx below is different:
+            # the attention backward reads the padding rows that share a 128-row tile with live ones, so it is written in full)
+            self._gemm(b, self.du, self._w(pre + "intermediate.dense.weight"), self.GA, M, H, I, b_major=MN,
+                       row_live=self.row_live)
             self._gemm(b, self.du, L["a"], self._g(pre + "intermediate.dense.weight"), I, H, M, a_major=MN, b_major=MN,
                        epilogue=ATOM, split_k=_split_k(I, H, M))
             a = capi.drln_bwd_args(self.GA, self.GD, L["y1"], self.x32[l], L["m1"], L["r1"],
@@ -390,7 +393,7 @@ class Plan:
             gwqkv = st.span(pre + "attention.self.query.weight", pre + "attention.self.value.weight", st.grad).view(3 * H, H)
             gbqkv = st.span(pre + "attention.self.query.bias", pre + "attention.self.value.bias", st.grad)
             b.append((self._fn("colsum_bf16"), capi.colsum_args(self.dqkv, gbqkv, row_list=self.row_list)))
-            self._gemm(b, self.dqkv, wqkv, self.GA, M, H, 3 * H, b_major=MN)
+            self._gemm(b, self.dqkv, wqkv, self.GA, M, H, 3 * H, b_major=MN, row_live=self.row_live)
             self._gemm(b, self.dqkv, self.x[l], gwqkv, 3 * H, H, M, a_major=MN, b_major=MN, epilogue=ATOM,
                        split_k=_split_k(3 * H, H, M))
         capi.fill(self.embed_args, dx0=self.GA, dx0b=self.GB)

@@ -727,7 +727,14 @@ def test_gemm_row_live_hint_skips_only_all_padding_slices(M, N):
     c3 = torch.full((M, N), 9.0, device="cuda", dtype=torch.bfloat16)       # dead_rows_zeroed: those slices are not written
     capi.gemm(A, B, c3, M, N, K, epilogue=capi.EPI_MUL_AUX_BF16, aux=poisoned, row_live=live, dead_rows_zeroed=1)
     assert torch.equal(c3[slice_live], c1[slice_live]) and bool((c3[~slice_live] == 9.0).all())
-    # an epilogue that does not take the hint computes every row
-    c2 = torch.full((M, N), 9.0, device="cuda", dtype=torch.bfloat16)
+    # the plain store leaves all-dead slices unwritten as well (not when it also takes column sums) ...
+    c2, c4 = (torch.full((M, N), 9.0, device="cuda", dtype=torch.bfloat16) for _ in range(2))
     capi.gemm(A, B, c2, M, N, K, epilogue=capi.EPI_STORE_BF16, bias=bias, row_live=live)
-    assert _rel(c2.float(), A.float() @ B.float().t() + bias) < 2 * BF16_EPS
+    want = A.float() @ B.float().t() + bias
+    assert _rel(c2.float()[slice_live], want[slice_live]) < 2 * BF16_EPS and bool((c2[~slice_live] == 9.0).all())
+    cs = torch.zeros(N, device="cuda")
+    capi.gemm(A, B, c4, M, N, K, epilogue=capi.EPI_STORE_BF16, bias=bias, row_live=live, colsum=cs)
+    assert _rel(c4.float(), want) < 2 * BF16_EPS and _rel(cs, c4.float().sum(0)) < 1e-5
+    # ... and an epilogue that does not take the hint computes every row
+    capi.gemm(A, B, c2, M, N, K, epilogue=capi.EPI_RELU_BF16, bias=bias, row_live=live)
+    assert _rel(c2.float(), torch.relu(want)) < 2 * BF16_EPS
