@@ -182,12 +182,30 @@ def executed_train_gflop_per_sample(shape, workload, batches):
     return dense + (e_attn - d_attn) / nsamp / 1e9
 
 
+def live_row_fraction(batches):
+    """Share of the packed rows that lie before their sequence's last unmasked key (the rows DESIGN.md 3.3 calls live)."""
+    live = total = 0.0
+    for b in batches:
+        m_t, (m_tv, m_v), (m_ts, m_s) = b["attention_mask"]
+        fv = m_v[:, :, 0] if m_v.dim() == 3 else m_v
+        fs = m_s[:, :, 0] if m_s.dim() == 3 else m_s
+        for mask in (m_t, torch.cat((m_tv.double(), fv.double()), 1), torch.cat((m_ts.double(), fs.double()), 1)):
+            S = mask.shape[1]
+            e = (torch.arange(1, S + 1)[None, :] * (mask != 0)).max(dim=1).values
+            e = torch.where(e > 0, e, torch.full_like(e, S))
+            live += float(e.sum())
+            total += float(mask.numel())
+    return live / total
+
+
 def config_dict(workload, shape, world):
     B = workload.batch
     return {"workload": workload.name, "model": f"bert-base shape ({shape.num_hidden_layers} layers), random init",
             "batch_per_gpu": B, "global_batch": B * world, "positions_per_sample": workload.positions,
             "packed_rows_per_gpu": B * workload.positions, "parallelism": f"dp{world}",
             "mlm": "dense (decoder GEMM, dgrad and wgrad over all positions, as the reference); cross entropy fused into the decoder epilogue, logits not materialised", "optimizer": "AdamW (HF semantics)",
+            "padding_rows": "left alone where nothing observable reads them (DESIGN.md 3.3; GEMM FLOPs executed in full); the line's "
+                            "padding_rows object carries the same run with that switched off",
             "l2": "no explicit flush: one training step streams GiBs of saved activations (>> 126 MB L2) and 4 distinct "
                   "input batches are cycled"}
 
@@ -434,6 +452,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=None, help="samples per CPU-reference step (default: ~4 s per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-torch-baseline", action="store_true")
+    ap.add_argument("--no-all-rows", action="store_true", help="skip the extra timed run with the padding-aware paths off")
     ap.add_argument("--batches", default="1,4,16,64,256,1024", help="infer-sweep")
     ap.add_argument("--lengths", default="150,512,1024,2048", help="infer-sweep")
     ap.add_argument("--reps", type=int, default=5, help="infer-sweep")
@@ -631,7 +650,8 @@ def main():
                          "traffic": measured_traffic(workload.name),
                          "traffic_note": "DRAM read+write bytes per GEMM launch, averaged over the GEMM launches of one "
                                          "step (ncu, profiles/*_gemm_traffic.json); algorithmic_bytes = the same average "
-                                         "computed from the launch shapes",
+                                         "computed from the launch shapes (every output row counted: the measured figure is "
+                                         "lower because the epilogues do not write all-padding 32-row slices, DESIGN.md 3.3)",
                          "algorithmic_bytes": gemm_bytes / n_gemm,
                          "peak_source": gemm_peak_source, "step_peak_source": peaks["source"], "launches_per_step": n_gemm,
                          "gemm_share_of_step": gemm_ms / (ms / args.steps),
@@ -648,9 +668,35 @@ def main():
             "dp": dp,
             "clocks": clocks, "final_loss": loss_val,
         }
+        del plan
+        if world == 1 and not args.no_all_rows:
+            # The same timed region with every padding-aware path switched off: attention forward, LayerNorm,
+            # column sums, epilogues and embeddings then process the rows behind each sequence's last unmasked key as well.
+            # Same results; reported so that the saving is visible next to the headline.
+            os.environ["MMB_ATTN_FWD_QSKIP"] = "0"
+            model._plans.clear()
+            torch.cuda.empty_cache()
+            for i in range(3):
+                step(resident[i % nb])
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for i in range(args.steps):
+                step(resident[i % nb])
+            a1.record()
+            torch.cuda.synchronize()
+            del os.environ["MMB_ATTN_FWD_QSKIP"]
+            ms_all = a0.elapsed_time(a1)
+            v_all = B * args.steps / (ms_all / 1e3)
+            line["padding_rows"] = {
+                "what": "rows behind a sequence's last unmasked key (no label there: checked on the device per batch) are left "
+                        "alone by the attention forward, LayerNorm, column sums, GEMM epilogues and embeddings; every GEMM FLOP "
+                        "is executed; outputs and gradients identical (tests); MMB_ATTN_FWD_QSKIP=0 turns it off",
+                "live_row_fraction": live_row_fraction(host), "packed_rows": B * workload.positions,
+                "value_all_rows": v_all, "ms_per_step_all_rows": ms_all / args.steps,
+                "step_frac_all_rows": v_all * gf / 1e3 / peaks["tflops"]}
         if world == 1 and not args.no_gpu_torch_baseline:
             model._plans.clear()                    # hand the activation buffers back before the PyTorch model runs
-            del plan
             torch.cuda.empty_cache()
             line["gpu_torch_baseline"] = gpu_torch_baseline(shape, workload, device)
             ab = line["gpu_torch_baseline"].get("autocast_bf16", {}).get("value")

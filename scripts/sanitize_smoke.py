@@ -91,5 +91,42 @@ dg, db, dbias = torch.zeros(Hh, device=dev), torch.zeros(Hh, device=dev), torch.
 capi.drln_fwd(y, res, gamma, beta, out, mean, rstd, 1e-12, p_drop=0.1, seed=5, rng_stream=2, out_f32=out32)
 capi.drln_bwd(g1, g2, y, res, mean, rstd, gamma, d_y, d_res, dg, db, dbias, p_drop=0.1, seed=5, rng_stream=2)
 assert torch.isfinite(d_res).all() and torch.isfinite(dg).all()
+# ---- padding rows: the schedule's row list and every kernel that takes it / its per-row flags
+rl = torch.zeros(4 + 2 * rows_, device=dev, dtype=torch.int32)
+capi.call("attn_schedule", capi.attn_schedule_args(cu, kv_end, work, nh, 200, row_label=row_label, row_list=rl))
+hdr = rl[:4].tolist()
+assert hdr == [150 + 70 + 129, 50, rows_, 1], hdr            # sequence 0: 150 live + 50 in its second tile; 1 and 2 all live
+live = rl[4 + rows_:].bool()
+ctx_s, lse_s, dq_s = torch.full_like(ctx, 3.0), torch.full_like(lse, 5.0), torch.full_like(dqkv, 7.0)
+for flags in (8, 8 | 16):
+    a = capi.attn_args(qkv, ctx_s, lse_s, keybias, cu, H, nh, 200, dctx=dctx, dqkv=dq_s, bwd_ws=ws, kv_end=kv_end, p_drop=0.1, seed=3,
+                       rng_stream=1, work=work, flags=flags, row_list=rl)
+    capi.call("attn_fwd", a)
+    capi.call("attn_bwd", a)
+    assert torch.isfinite(ctx_s.float()).all() and torch.isfinite(dq_s.float()).all()
+Mr2 = rows_
+y2, g12 = bf(torch.randn(Mr2, Hh, device=dev)), bf(torch.randn(Mr2, Hh, device=dev))
+res2, g22 = torch.randn(Mr2, Hh, device=dev), torch.randn(Mr2, Hh, device=dev)
+out2, dy2 = torch.zeros_like(y2), torch.zeros_like(y2)
+out322, dres2 = torch.zeros_like(res2), torch.zeros_like(res2)
+mean2, rstd2 = torch.zeros(Mr2, device=dev), torch.zeros(Mr2, device=dev)
+capi.drln_fwd(y2, res2, gamma, beta, out2, mean2, rstd2, 1e-12, p_drop=0.1, seed=5, rng_stream=2, out_f32=out322, row_list=rl)
+for zeroed in (0, 1):
+    capi.drln_bwd(g12, g22, y2, res2, mean2, rstd2, gamma, dy2, dres2, dg, db, dbias, p_drop=0.1, seed=5, rng_stream=2, row_list=rl,
+                  dead_rows_zeroed=zeroed)
+assert bool((out2[~live] == 0).all()) and bool((dres2[~live] == 0).all()) and torch.isfinite(dres2).all()
+csl = torch.zeros(Hh, device=dev)
+capi.call("colsum_bf16", capi.colsum_args(dy2, csl, row_list=rl))
+assert rel(csl, dy2.float().sum(0)) < 1e-4
+Ar = bf(torch.randn(rows_, K, device=dev) * 0.3)
+Cr, auxr = torch.zeros(rows_, N, device=dev, dtype=torch.bfloat16), torch.zeros(rows_, N, device=dev, dtype=torch.bfloat16)
+refr = Ar.float() @ B.float().t()
+capi.gemm(Ar, B, Cr, rows_, N, K, epilogue=capi.EPI_GELU_GRAD_BF16, bias=bias, aux=auxr, row_live=rl[4 + rows_:])
+assert rel(Cr.float()[live], torch.nn.functional.gelu(refr + bias)[live]) < 1e-2
+for zeroed in (0, 1):
+    capi.gemm(Ar, B, Cr, rows_, N, K, epilogue=capi.EPI_MUL_AUX_BF16, aux=auxr, colsum=cs, row_live=rl[4 + rows_:], dead_rows_zeroed=zeroed)
+assert rel(Cr.float()[live], (refr * auxr.float())[live]) < 1e-2
+capi.gemm(Ar, B, Cr, rows_, N, K, bias=bias, row_live=rl[4 + rows_:])
+assert rel(Cr.float()[live], (refr + bias)[live]) < 1e-2
 torch.cuda.synchronize()
 print("sanitize_smoke: all launches done, results correct")
