@@ -284,6 +284,7 @@ typedef struct mmb_attn_schedule_args {
                                   read by a GEMM must hold finite values (zero-initialised once). */
 } mmb_attn_schedule_args;
 size_t mmb_attn_schedule_bytes(int nseq, int nheads, int max_seqlen);
+size_t mmb_row_list_ints(int rows); /* int32 elements of mmb_attn_schedule_args.row_list for a batch of `rows` packed rows */
 int mmb_attn_schedule(const mmb_attn_schedule_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -220,6 +220,14 @@ def attn_schedule_buffer(nseq, nheads, max_seqlen, device):
     return torch.empty(L.mmb_attn_schedule_bytes(nseq, nheads, max_seqlen) // 16, 4, device=device, dtype=torch.int32)
 
 
+def row_list_buffer(rows, device):
+    """Zeroed int32 tensor for mmb_attn_schedule_args.row_list (size from mmb_row_list_ints)."""
+    L = lib()
+    L.mmb_row_list_ints.restype = ctypes.c_size_t
+    L.mmb_row_list_ints.argtypes = [ctypes.c_int]
+    return torch.zeros(L.mmb_row_list_ints(rows), device=device, dtype=torch.int32)
+
+
 def attn_schedule_args(cu_seqlens, kv_end, work, nheads, max_seqlen, row_label=None, row_list=None):
     return fill(AttnScheduleArgs(), cu_seqlens=cu_seqlens, kv_end=kv_end, work=work, nseq=cu_seqlens.numel() - 1,
                 nheads=nheads, max_seqlen=max_seqlen, row_label=row_label, row_list=row_list)

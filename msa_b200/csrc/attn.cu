@@ -226,6 +226,8 @@ extern "C" size_t mmb_attn_schedule_bytes(int nseq, int nheads, int max_seqlen) 
     return (1 + 2 * cap) * 16;
 }
 
+extern "C" size_t mmb_row_list_ints(int rows) { return rows > 0 ? 4 + 2 * (size_t)rows : 0; }
+
 extern "C" int mmb_attn_schedule(const mmb_attn_schedule_args* a, void* stream) {
     MMB_REQUIRE(a && a->cu_seqlens && a->work, "attn_schedule: null pointer");
     MMB_REQUIRE(a->nseq > 0 && a->nseq <= kSchedMaxSeqs, "attn_schedule: nseq=%d not in [1, %d]", a->nseq, kSchedMaxSeqs);

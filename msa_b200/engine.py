@@ -99,7 +99,7 @@ class Plan:
         # mmb_attn_schedule_args.row_list).  MMB_ROW_SKIP=0 for A/B runs.
         self.row_list = None
         if self.attn_fwd_skip and os.environ.get("MMB_ROW_SKIP", "1") != "0":
-            self.row_list = torch.zeros(4 + 2 * M, device=dev, dtype=I32)
+            self.row_list = capi.row_list_buffer(M, dev)
 
         def zbuf(*shape, dtype=BF16):      # rows a skipped tile never writes are still GEMM operands: finite from the start
             return torch.zeros(*shape, device=dev, dtype=dtype) if self.attn_fwd_skip else buf(*shape, dtype=dtype)
