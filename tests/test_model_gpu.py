@@ -299,7 +299,7 @@ def test_forward_attention_tail_skip_changes_nothing_observable(monkeypatch):
     kv_end (mmb_attn_args.flags bit 3; padding rows that no loss, no head and no unmasked key ever reads), and the row
     kernels (LayerNorm forward / backward, column sums, attention-backward preparation) leave those rows alone
     (mmb_attn_schedule_args.row_list).  Two models on
-    the same weights, one built with MMB_ATTN_FWD_QSKIP=0: over three different batches through the SAME plans (so the
+    the same weights, one built with MMB_ATTN_FWD_QSKIP=0: over four different batches through the SAME plans (so the
     skipped rows hold stale values of the previous batch) every returned value and every gradient agrees to the order of
     the fp32 atomic reductions (loss sums, split-K) — the kernel-level test checks the attention output bit for bit."""
     ocfg = O.Cfg(hidden_size=128, num_hidden_layers=3, num_attention_heads=2, intermediate_size=256, vocab_size=1000,
@@ -307,7 +307,14 @@ def test_forward_attention_tail_skip_changes_nothing_observable(monkeypatch):
     sd = seeded_state_dict(ocfg, "mosei", seed=5, std=0.05)
     monkeypatch.setenv("MMB_ATTN_FWD_QSKIP", "0")         # (also turns the row lists of the row kernels off)
     m_full = _build(ocfg, "mosei", sd, fused=True).train()
-    batches = [synth.tree_to(synth.make_batch(6, 16, 400, 300, 35, 74, vocab_size=1000, seed=s, min_len=4), "cuda") for s in (1, 2, 3)]
+    batches = [synth.make_batch(6, 16, 400, 300, 35, 74, vocab_size=1000, seed=s, min_len=4) for s in (1, 2, 3, 4)]
+    # fourth batch: a masked-LM label on a PADDING frame of the visual pass (behind that sequence's last unmasked key) — the
+    # schedule must then report every row live and both models run the full computation, that row's prediction included
+    lab_v = batches[3]["masked_labels"][1]
+    pad_pos = int((batches[3]["input_ids"][1][0].abs().sum(-1) == 0).nonzero()[-1])          # last all-zero frame of sample 0
+    assert pad_pos > 200
+    lab_v[0, 16 + pad_pos] = 77
+    batches = [synth.tree_to(b, "cuda") for b in batches]
     m_full(**batches[0])
     monkeypatch.setenv("MMB_ATTN_FWD_QSKIP", "1")
     m_skip = _build(ocfg, "mosei", sd, fused=True).train()
@@ -316,12 +323,15 @@ def test_forward_attention_tail_skip_changes_nothing_observable(monkeypatch):
     if plans[0] is not None:
         assert not plans[0].attn_fwd_skip and plans[1].attn_fwd_skip
         assert plans[0].row_list is None and plans[1].row_list is not None
-    for batch in batches:
+    for bi, batch in enumerate(batches):
         for m in (m_full, m_skip):
             for p in m.parameters():
                 p.grad = None
         o0, l0 = m_full(**batch)
         o1, l1 = m_skip(**batch)
+        if plans[1] is not None:        # row-list header: [live, tile, rows, premise]
+            hdr = plans[1].row_list[:4].tolist()
+            assert hdr[3] == (0 if bi == 3 else 1) and (hdr[0] == hdr[2]) == (bi == 3), (bi, hdr)
         o0[0].backward()
         o1[0].backward()
         for a, b in zip(o0, o1):
