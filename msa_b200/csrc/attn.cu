@@ -40,39 +40,44 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dctx, const __nv_bfloat16
     pdl_trigger();
     pdl_wait();
     // one 8-lane group per (row, head): 8 lanes x 8 bf16 = 64; with a row list only the rows the backward kernels read
-    // (live rows and the rest of their 128-row tiles: the first n_live + n_tile entries)
-    const int gidx = (blockIdx.x * 256 + threadIdx.x) >> 3;
-    const int sub = threadIdx.x & 7;
+    // (live rows and the rest of their 128-row tiles: the first n_live + n_tile entries).  Persistent warps walk the groups
+    // (row-major: a warp reads 512 contiguous bytes of dctx / ctx) with a grid stride: ~27 600 one-shot CTAs cost more in
+    // scheduling than the kernel's ~35 us of HBM time.
+    const int sub = threadIdx.x & 7, lane = threadIdx.x & 31;
     const int nrows = row_list != nullptr ? __ldg(row_list) + __ldg(row_list + 1) : total_rows;
-    if ((blockIdx.x * 256) >> 3 >= nrows * nheads) return;                 // whole CTA beyond the list
-    const bool live = gidx < nrows * nheads;
-    const int li = live ? gidx / nheads : 0, head = live ? gidx - li * nheads : 0;
-    const int row = row_list != nullptr ? __ldg(row_list + 4 + li) : li;
-    const int64_t off = (int64_t)row * H + head * kD + sub * 8;
-    const uint4 a = *reinterpret_cast<const uint4*>(dctx + off);
-    const uint4 b = *reinterpret_cast<const uint4*>(ctx + off);
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
-    float s = 0.f;
+    const int ngroups = nrows * nheads;
+    const int nwarps = gridDim.x * 8;
+    for (int base = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 4; base < ngroups; base += nwarps * 4) {
+        const int gidx = base + (lane >> 3);
+        const bool live = gidx < ngroups;
+        const int li = live ? gidx / nheads : 0, head = live ? gidx - li * nheads : 0;
+        const int row = row_list != nullptr ? __ldg(row_list + 4 + li) : li;
+        const int64_t off = (int64_t)row * H + head * kD + sub * 8;
+        const uint4 a = *reinterpret_cast<const uint4*>(dctx + off);
+        const uint4 b = *reinterpret_cast<const uint4*>(ctx + off);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+        float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float2 x = unpack_bf16x2(aw[i]), y = unpack_bf16x2(bw[i]);
-        s += x.x * y.x + x.y * y.y;
-    }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (!live) return;
-    const uint32_t prob = (uint32_t)head * (uint32_t)total_rows + (uint32_t)row;
-    const int64_t o = (int64_t)head * total_rows + row;
-    // lane 0 writes the row record, lane 1 the column record; both hash in ONE instruction stream (two divergent branches
-    // would run the ~25-instruction hash twice per warp — the kernel was issue-bound at 66 %, DRAM 49 %)
-    uint32_t key = 1u;
-    if (drop && sub < 2)
-        key = rng_row_key(sub == 0 ? seed : (seed ^ 0x9E3779B97F4A7C15ull), sub == 0 ? rng_stream : (rng_stream ^ 0x5bd1e995u), prob) | 1u;
-    if (sub == 0) {
-        ws[o] = make_uint4(__float_as_uint(-lse[o]), __float_as_uint(-s), key, 0u);
-    } else if (sub == 1) {
-        ws[(int64_t)nheads * total_rows + o] = make_uint4(__float_as_uint(keybias[row] * kLog2e), key, 0u, 0u);
+        for (int i = 0; i < 4; ++i) {
+            const float2 x = unpack_bf16x2(aw[i]), y = unpack_bf16x2(bw[i]);
+            s += x.x * y.x + x.y * y.y;
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (!live) continue;
+        const uint32_t prob = (uint32_t)head * (uint32_t)total_rows + (uint32_t)row;
+        const int64_t o = (int64_t)head * total_rows + row;
+        // lane 0 writes the row record, lane 1 the column record; both hash in ONE instruction stream (two divergent branches
+        // would run the ~25-instruction hash twice per warp — the kernel was issue-bound at 66 %, DRAM 49 %)
+        uint32_t key = 1u;
+        if (drop && sub < 2)
+            key = rng_row_key(sub == 0 ? seed : (seed ^ 0x9E3779B97F4A7C15ull), sub == 0 ? rng_stream : (rng_stream ^ 0x5bd1e995u), prob) | 1u;
+        if (sub == 0) {
+            ws[o] = make_uint4(__float_as_uint(-lse[o]), __float_as_uint(-s), key, 0u);
+        } else if (sub == 1) {
+            ws[(int64_t)nheads * total_rows + o] = make_uint4(__float_as_uint(keybias[row] * kLog2e), key, 0u, 0u);
+        }
     }
 }
 
@@ -263,7 +268,9 @@ extern "C" int mmb_attn_bwd(const mmb_attn_args* a, void* stream) {
     MMB_REQUIRE(a->ctx && a->lse && a->dctx && a->dqkv && a->bwd_ws, "attn_bwd: null pointer");
     MMB_REQUIRE(((uintptr_t)a->bwd_ws % 16) == 0, "attn_bwd: workspace must be 16-byte aligned");
     const long long groups = (long long)a->total_rows * a->nheads;
-    launch_pdl(attn_bwd_prep_kernel, dim3((unsigned)((groups * 8 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
+    const long long ctas = (groups * 8 + 255) / 256;
+    launch_pdl(attn_bwd_prep_kernel, dim3((unsigned)(ctas < (long long)num_sms() * 8 ? ctas : (long long)num_sms() * 8)), dim3(256), 0,
+               (cudaStream_t)stream,
                (const __nv_bfloat16*)a->dctx, (const __nv_bfloat16*)a->ctx, a->lse, a->keybias, (uint4*)a->bwd_ws, a->total_rows,
                a->H, a->nheads, a->p_drop > 0.f ? 1 : 0, a->seed, a->rng_stream, a->row_list);
     rc = check_launch("attn_bwd_prep_kernel");
