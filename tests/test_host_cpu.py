@@ -153,6 +153,46 @@ def test_flop_accounting_matches_survey_table():
     assert abs(train_gflop_per_sample(BertShape(), synth.WORKLOADS["ur_funny_b64"]) - 166.09) < 0.01
 
 
+def test_executed_flop_accounting_and_live_row_fraction(monkeypatch):
+    """bench.py's two padding-dependent figures on hand-made masks: the attention term counted as executed (forward
+    4 q e H with q = the query rows of the 128-row tiles that start before e, backward 8 e^2 H; everything else dense) and
+    the share of packed rows before their sequence's last unmasked key."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    shape, wl = BertShape(), synth.WORKLOADS["mosei_unaligned_b64"]
+    B, T, L = 2, wl.T, 500
+
+    def batch(text_len, frame_len):
+        m_t = torch.zeros(B, T)
+        m_t[:, :text_len] = 1
+        m_f = torch.zeros(B, L, 3)
+        m_f[:, :frame_len] = 1
+        ones = torch.ones(B, T)
+        return {"attention_mask": (m_t, (ones, m_f), (ones, m_f[..., 0].clone()))}
+
+    full = batch(T, L)
+    dense = train_gflop_per_sample(shape, wl)
+    assert abs(bench.executed_train_gflop_per_sample(shape, wl, [full]) - dense) < 1e-6 * dense
+    assert bench.live_row_fraction([full]) == 1.0
+    b = batch(20, 100)          # text pass: e = 20 of 50; joint passes: e = 50 + 100 = 150 of 550 (a hole-free prefix)
+    H, N = shape.hidden_size, shape.num_hidden_layers
+    want = dense
+    for S, e in ((T, 20), (T + L, 150), (T + L, 150)):
+        q = min(S, -(-e // 128) * 128)
+        want += N * H * (4.0 * q * e + 8.0 * e * e - 12.0 * S * S) / 1e9
+    assert abs(bench.executed_train_gflop_per_sample(shape, wl, [b]) - want) < 1e-6 * dense
+    monkeypatch.setenv("MMB_ATTN_FWD_QSKIP", "0")          # forward computes every query row again
+    want0 = dense + sum(N * H * (4.0 * S * e + 8.0 * e * e - 12.0 * S * S) / 1e9 for S, e in ((T, 20), (T + L, 150), (T + L, 150)))
+    assert abs(bench.executed_train_gflop_per_sample(shape, wl, [b]) - want0) < 1e-6 * dense
+    assert abs(bench.live_row_fraction([b]) - (20 + 150 + 150) / (T + 2 * (T + L))) < 1e-12
+    hole = batch(20, 100)       # an unmasked key at the very end: nothing is padding any more
+    hole["attention_mask"][1][1][:, -1, 0] = 1
+    assert abs(bench.live_row_fraction([hole]) - (20 + 550 + 150) / (T + 2 * (T + L))) < 1e-12
+
+
 def test_bucket_schedule_partitions_the_gradient_buffer():
     from msa_b200.ddp import bucket_schedule, check_partition
     for layers in (1, 2, 12):
