@@ -189,6 +189,10 @@ def test_attention_fwd_bwd(lens, nh):
     x = qkv.float().requires_grad_(True)
     ref = _attn_ref(x, keybias, cu, H, nh)
     assert _rel(ctx.float(), ref) < 3 * BF16_EPS
+    # the first tcgen05 forward (csrc/attn_tc.cu, kept behind flags bit 2 / MMB_ATTN_FWD=tc for A/B runs): same contract
+    ctx_tc, lse_tc = torch.empty_like(ctx), torch.empty_like(lse)
+    capi.call("attn_fwd", capi.attn_args(qkv, ctx_tc, lse_tc, keybias, cu_t, H, nh, max(lens), flags=4))
+    assert _rel(ctx_tc.float(), ref) < 3 * BF16_EPS and _rel(lse_tc, lse) < 1e-3
     dctx = _bf(torch.randn(rows, H, device="cuda"))
     ref.backward(dctx.float())
     dqkv = torch.zeros(rows, 3 * H, device="cuda", dtype=torch.bfloat16)
